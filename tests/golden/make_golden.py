@@ -1,0 +1,257 @@
+"""Generate golden vectors from the REAL reference (build container only).
+
+Run:  python tests/golden/make_golden.py
+Needs ``/root/reference`` (imported through ``oracle/ref_shim.py``); writes
+small ``.npz`` fixtures next to this file.  The fixtures travel to the GPU box,
+the reference does not.
+
+Every fixture records inputs AND the reference's outputs so both the CPU
+oracle (``-m "not gpu"``) and the CUDA path (``-m gpu``) are checked against
+the same numbers.
+"""
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from causarray_b200.synth import simulate_screen  # noqa: E402
+
+
+def _init_AB(rng, X, r, p, scale=0.1):
+    n, d = X.shape
+    A0 = np.c_[X, rng.standard_normal((n, r)) * scale]
+    B0 = rng.standard_normal((p, d + r)) * scale
+    return A0, B0
+
+
+def golden_kernels(ca, family, seed, tag):
+    """nll / grad / update_with_mask (stage 1 and stage 2) on one tiny problem."""
+    import scipy.linalg
+    from causarray.gcate_opt import update_with_mask, update
+    from causarray.gcate_likelihood import nll, grad, gammaln_nb
+    rng = np.random.default_rng(seed)
+    sim = simulate_screen(n_ctrl=30, n_perts=3, cells_per_pert=10, p=70, r=2, d_cov=2, family=family, seed=seed)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    X = np.c_[Xc, Atr]
+    n, p = Y.shape
+    d, a, r = X.shape[1], Atr.shape[1], 2
+    sf = np.exp(rng.standard_normal(n) * 0.2)
+    nu = sim["disp"].copy()
+    nu[::5] = 500.0                     # > thres_disp -> Poisson branch inside the NB family
+    nu = nu.reshape(1, -1)
+    thres = 100.0
+    Yn = Y / sf[:, None]
+    Ys = -gammaln_nb(Yn + 1)
+    if family == "nb":
+        Ys = Ys + np.where(nu > thres, 0.0, gammaln_nb(nu + Yn) - gammaln_nb(nu))
+    A0, B0 = _init_AB(rng, X, r, p, scale=0.3)
+    out = dict(Y=Y, X=X, sf=sf, nu=nu[0], A0=A0, B0=B0, d=d, a=a, r=r, thres_disp=thres, Ys=Ys)
+    out["nll"] = nll(Yn, A0, B0, family, nu, Ys, thres)
+    out["grad_B"] = grad(Yn, A0, B0, family, nu, thres)
+    out["grad_A"] = grad(np.ascontiguousarray(Yn.T), B0, A0, family, np.ascontiguousarray(nu.T), thres)
+    C = 1e3 if family == "nb" else 1e5
+    Q1 = scipy.linalg.qr(X, mode="economic")[0]
+    gene_active = rng.random(p) < 0.9
+    cell_active = rng.random(n) < 0.9
+    alpha_gene = np.where(rng.random(p) < 0.5, 0.1, 0.26)
+    lam1 = np.zeros((p, d))
+    # stage 1: three consecutive iterations
+    A, B = A0.copy(), B0.copy()
+    fs = []
+    for it in range(3):
+        f, A, B = update_with_mask(Yn, A, B, d, lam1, Q1, None, family, nu, Ys, thres, d, C,
+                                   0.1, 0.5, 20, 1e-4, gene_active, cell_active, alpha_gene)
+        fs.append(f)
+        out["s1_A_%d" % it] = A.copy()
+        out["s1_B_%d" % it] = B.copy()
+    out["s1_f"] = np.array(fs)
+    out["gene_active"], out["cell_active"], out["alpha_gene"], out["Q1"] = gene_active, cell_active, alpha_gene, Q1
+    # stage 2 from the stage-1 result
+    Q2 = scipy.linalg.qr(B[:, -r:], mode="economic")[0]
+    B2 = B.copy()
+    B2[:, d - a:d] -= Q2 @ (Q2.T @ B2[:, d - a:d])
+    lam2 = 0.05 / (np.abs(B2[:, d - a:d]) + 1e-6)
+    A2 = A.copy()
+    out["s2_A_in"], out["s2_B_in"], out["lam2"], out["Q2"] = A2.copy(), B2.copy(), lam2, Q2
+    fs = []
+    for it in range(3):
+        f, A2, B2 = update_with_mask(Yn, A2, B2, d, lam2, None, Q2, family, nu, Ys, thres, a, C,
+                                     0.1, 0.5, 20, 1e-4, gene_active, cell_active, alpha_gene)
+        fs.append(f)
+        out["s2_A_%d" % it] = A2.copy()
+        out["s2_B_%d" % it] = B2.copy()
+    out["s2_f"] = np.array(fs)
+    # neither P1 nor P2 (the T4 unit-test configuration), one iteration, all active
+    A3, B3 = A0.copy(), B0.copy()
+    f, A3, B3 = update(Yn, A3, B3, d, lam1, None, None, family, nu, Ys, thres, d, C, 0.1, 0.5, 20, 1e-4)
+    out["s0_f"], out["s0_A"], out["s0_B"] = f, A3, B3
+    np.savez_compressed(os.path.join(HERE, "kernels_%s.npz" % tag), **out)
+    print("kernels", tag, "nll", out["nll"], "s1_f", out["s1_f"], "s2_f", out["s2_f"])
+
+
+def golden_alter_min(ca, family, seed, tag):
+    """Whole two-stage optimiser with explicit A0/B0 (skips GLM/SVD init)."""
+    import scipy.linalg
+    from causarray.gcate_opt import alter_min
+    rng = np.random.default_rng(seed)
+    sim = simulate_screen(n_ctrl=80, n_perts=3, cells_per_pert=25, p=180, r=3, d_cov=1, family=family, seed=seed)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    X = np.c_[Xc, Atr]
+    n, p = Y.shape
+    r, a = 3, Atr.shape[1]
+    sf = ca.comp_size_factor(Y)
+    disp = sim["disp"]
+    A0, B0 = _init_AB(rng, X, r, p, scale=0.1)
+    B0[:, 0] = np.log(Y.mean(0) + 0.1)
+    kw = dict(family=family, disp_glm=disp.copy(), size_factor=sf.copy())
+    res1 = alter_min(Y.copy(), r, X=X, P1=True, A=A0.copy(), B=B0.copy(), kwargs_glm=dict(kw),
+                     kwargs_es=dict(max_iters=30))
+    Q = scipy.linalg.qr(res1["B_Gamma"][:, -r:], mode="economic")[0]
+    res2 = alter_min(Y.copy(), r, X=X, P2=Q, A=res1["X_U"].copy(), B=res1["B_Gamma"].copy(), lam=0.05, a=a,
+                     kwargs_glm=dict(kw), kwargs_es=dict(max_iters=30))
+    out = dict(Y=Y, X=X, a=a, r=r, sf=sf, disp=disp, A0=A0, B0=B0,
+               s1_A=res1["X_U"], s1_B=res1["B_Gamma"], s1_hist=np.array(res1["hist"]), s1_n_iter=res1["n_iter"],
+               s1_gene_updates=res1["total_gene_updates"], s1_cell_updates=res1["total_cell_updates"],
+               s2_A=res2["X_U"], s2_B=res2["B_Gamma"], s2_hist=np.array(res2["hist"]), s2_n_iter=res2["n_iter"],
+               s2_gene_updates=res2["total_gene_updates"], s2_cell_updates=res2["total_cell_updates"], Q2=Q)
+    np.savez_compressed(os.path.join(HERE, "alter_min_%s.npz" % tag), **out)
+    print("alter_min", tag, "iters", res1["n_iter"], res2["n_iter"], "hist1", res1["hist"][0], res1["hist"][-1],
+          "hist2", res2["hist"][-1])
+
+
+def golden_lfc(ca, seed, tag, usevar):
+    """AIPW + LFC estimand + BH with Y_hat / pi_hat supplied (no GLM, no sklearn)."""
+    rng = np.random.default_rng(seed)
+    sim = simulate_screen(n_ctrl=60, n_perts=3, cells_per_pert=20, p=90, r=2, d_cov=1, family="nb", seed=seed)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    n, p = Y.shape
+    a = Atr.shape[1]
+    W = np.c_[Xc, sim["U"]]
+    Bcov = np.c_[np.log(Y.mean(0) + 0.05), rng.standard_normal((p, 2)) * 0.1]
+    Btrt = rng.standard_normal((p, a)) * 0.3
+    sf = ca.comp_size_factor(Y)
+    off = np.log(sf)
+    Y[:, 0] = 0.0            # all-zero gene -> filtered
+    Y[:, 1] = (rng.random(n) < 0.02) * 1.0   # very low expression
+    eta0 = W @ Bcov.T + off[:, None]
+    Y_hat = np.zeros((n, p, a, 2))
+    for k in range(a):
+        Y_hat[:, :, k, 0] = np.exp(eta0)
+        Y_hat[:, :, k, 1] = np.exp(eta0 + Btrt[:, k][None, :])
+    pi = np.clip(rng.uniform(0.05, 0.6, (n, a)), 0.01, 0.99)
+    df, est = ca.LFC(Y, W, Atr, W_A=W, family="nb", offset=off, Y_hat=Y_hat.copy(), pi_hat=pi.copy(), usevar=usevar)
+    from causarray.DR_estimation import AIPW_mean
+    tau_aipw, _ = AIPW_mean(Y, np.stack([1 - Atr, Atr], -1), Y_hat, np.stack([1 - pi, pi], -1))
+    cols = ["tau", "std", "log2fc", "log2fc_se", "stat", "rej", "pvalue", "padj", "pvalue_emp_null_adj",
+            "padj_emp_null_adj", "mean_control", "mean_treated"]
+    out = dict(Y=Y, W=W, A=Atr, Bcov=Bcov, Btrt=Btrt, offset=off, pi=pi, aipw_tau=tau_aipw,
+               estimable=df["estimable"].to_numpy().astype(np.uint8), trt=df["trt"].to_numpy(),
+               columns=np.array(list(df.columns)))
+    for c in cols:
+        out["df_" + c] = df[c].to_numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "lfc_%s.npz" % tag), **out)
+    print("lfc", tag, "n sig", int(np.nansum(df["padj"] < 0.05)), "n filtered", int(np.isinf(df["std"]).sum()))
+
+
+def golden_misc(ca):
+    from causarray.utils import subsample_ctrl_cells, subsample_pert_cells
+    from causarray.DR_inference import bh_correction
+    from causarray.nb_glm_fast import _compute_nb_deviance_residuals, _compute_poisson_deviance_residuals
+    from causarray.gcate_glm import estimate_disp
+    rng = np.random.default_rng(7)
+    sim = simulate_screen(n_ctrl=50, n_perts=2, cells_per_pert=20, p=60, r=2, seed=7)
+    Y = sim["Y"]
+    out = dict(Y=Y, size_factor=ca.comp_size_factor(Y))
+    out["ctrl_sel"] = subsample_ctrl_cells(np.arange(5, 500, 3), n_ctrl=40, random_state=3)
+    out["pert_sel"] = subsample_pert_cells(np.arange(2, 700, 5), max_cells=33, random_state=4)
+    t = rng.standard_normal(200) * 1.7 + 0.2
+    t[::17] = np.nan
+    df = rng.uniform(3, 80, 200)
+    out["bh_t"], out["bh_df"] = t, df
+    for name, arr in zip(["bh_p", "bh_q", "bh_pa", "bh_qa"], bh_correction(t.copy(), df=df)):
+        out[name] = arr
+    for name, arr in zip(["bhz_p", "bhz_q", "bhz_pa", "bhz_qa"], bh_correction(t.copy(), df=None)):
+        out[name] = arr
+    mu = np.exp(rng.standard_normal(Y.shape) * 0.5) * (Y.mean(0) + 0.1)
+    alpha = rng.uniform(0.2, 2.0, Y.shape[1])
+    out["mu"], out["alpha"] = mu, alpha
+    out["resid_nb"] = _compute_nb_deviance_residuals(Y, mu, alpha)
+    out["resid_pois"] = _compute_poisson_deviance_residuals(Y, mu)
+    off = np.log(out["size_factor"])
+    out["disp_mom"] = estimate_disp(Y, Y_hat=(mu / np.exp(off)[:, None]).copy(), offset=off)
+    Yc, A1, X1, XA1 = ca.prep_causarray_data(Y, sim["A"], X=None)
+    out["prep_Y"], out["prep_X"], out["prep_XA"] = Yc, X1, XA1
+    np.savez_compressed(os.path.join(HERE, "misc.npz"), **out)
+    print("misc ok")
+
+
+def golden_pipeline(ca, family, seed, tag):
+    """End-to-end fit_gcate + LFC through the REAL reference orchestration, with the
+    statsmodels calls served by oracle/glm.py (parity unpinned for that piece)."""
+    import causarray.gcate_glm as gg
+    sim = simulate_screen(n_ctrl=150, n_perts=2, cells_per_pert=50, p=120, r=2, d_cov=1, family=family, seed=seed,
+                          base_lo=0.0, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    disp = sim["disp"]
+    # deterministic svds: fixed start vector, signs fixed by largest-abs entry
+    import scipy.sparse.linalg as sla
+    import causarray.gcate_opt as go
+    orig = sla.svds
+
+    def svds_det(M, k, **kw):
+        v0 = np.ones(min(M.shape)) / np.sqrt(min(M.shape))
+        u, s, vt = orig(M, k=k, v0=v0, tol=1e-14)
+        for i in range(k):
+            j = np.argmax(np.abs(u[:, i]))
+            if u[j, i] < 0:
+                u[:, i] *= -1
+                vt[i] *= -1
+        return u, s, vt
+    go.svds = svds_det
+    go.sp.sparse.linalg.svds = svds_det
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    try:
+        with gg._backend_override("original"):
+            res1, res2 = ca.fit_gcate(Y.copy(), X, A, 2, family=family, disp_glm=disp.copy(),
+                                      kwargs_es_1=dict(max_iters=30), kwargs_es_2=dict(max_iters=30))
+            W = np.c_[X, res2["U"]]
+            off = np.log(res2["kwargs_glm"]["size_factor"])
+            df, est = ca.LFC(Y.copy(), W, A, W_A=W, family=family, offset=off, disp_glm=disp.copy(), backend="original")
+    finally:
+        go.svds = orig
+        go.sp.sparse.linalg.svds = orig
+        gg.Parallel = n_jobs_patch
+    out = dict(Y=Y, X=X, A=A, disp=disp, s1_A=res1["X_U"], s1_B=res1["B_Gamma"], s1_hist=np.array(res1["hist"]),
+               s2_A=res2["X_U"], s2_B=res2["B_Gamma"], s2_hist=np.array(res2["hist"]),
+               size_factor=res2["kwargs_glm"]["size_factor"], pi_hat=est["pi_hat"], pi_hat_raw=est["pi_hat_raw"],
+               Y_hat=est["Y_hat"].astype(np.float64), trt=df["trt"].to_numpy(),
+               estimable=df["estimable"].to_numpy().astype(np.uint8))
+    for c in ["tau", "std", "stat", "pvalue", "padj", "pvalue_emp_null_adj", "padj_emp_null_adj", "mean_control",
+              "mean_treated", "log2fc", "log2fc_se"]:
+        out["df_" + c] = df[c].to_numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "pipeline_%s.npz" % tag), **out)
+    print("pipeline", tag, "iters", res1["n_iter"], res2["n_iter"], "sig", int(np.nansum(df["padj"] < 0.05)))
+
+
+if __name__ == "__main__":
+    ca = ref_shim.import_reference()
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline"]
+    if "kernels" in which:
+        golden_kernels(ca, "nb", 11, "nb")
+        golden_kernels(ca, "poisson", 12, "poisson")
+    if "alter_min" in which:
+        golden_alter_min(ca, "nb", 21, "nb")
+        golden_alter_min(ca, "poisson", 22, "poisson")
+    if "lfc" in which:
+        golden_lfc(ca, 31, "unequal", "unequal")
+        golden_lfc(ca, 32, "pooled", "pooled")
+    if "misc" in which:
+        golden_misc(ca)
+    if "pipeline" in which:
+        golden_pipeline(ca, "nb", 41, "nb")
+        golden_pipeline(ca, "poisson", 42, "poisson")
