@@ -1,0 +1,147 @@
+"""ctypes binding of ``libcausarray_b200.so`` (the C ABI in ``include/causarray_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+visible every numeric entry point raises ``CausarrayCudaError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcausarray_b200.so")
+
+FAMILY = {"poisson": 0, "nb": 1}
+
+
+class CausarrayCudaError(RuntimeError):
+    pass
+
+
+class AltminParams(ctypes.Structure):
+    _fields_ = [
+        ("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("tol", ctypes.c_double), ("C", ctypes.c_double),
+        ("ls_max_iters", ctypes.c_int),
+        ("tol_gene", ctypes.c_double), ("tol_cell", ctypes.c_double),
+        ("recheck_interval", ctypes.c_int),
+        ("sparsity_threshold", ctypes.c_double), ("sparsity_boost", ctypes.c_double),
+        ("warmup_iters", ctypes.c_int),
+        ("es_max_iters", ctypes.c_int), ("es_warmup", ctypes.c_int), ("es_patience", ctypes.c_int),
+        ("es_tolerance", ctypes.c_double), ("es_rel_tol", ctypes.c_double),
+        ("lam", ctypes.c_double), ("a", ctypes.c_int),
+    ]
+
+
+class AltminResult(ctypes.Structure):
+    _fields_ = [
+        ("n_iter", ctypes.c_int), ("func_val", ctypes.c_double), ("resid", ctypes.c_double),
+        ("hist_len", ctypes.c_int),
+        ("total_gene_updates", ctypes.c_int64), ("total_cell_updates", ctypes.c_int64),
+        ("cell_evals", ctypes.c_int64), ("gene_evals", ctypes.c_int64),
+        ("loop_seconds", ctypes.c_double),
+    ]
+
+
+class LfcParams(ctypes.Structure):
+    _fields_ = [
+        ("usevar", ctypes.c_int), ("thres_min", ctypes.c_double), ("thres_diff", ctypes.c_double),
+        ("eps_var", ctypes.c_double), ("yhat_cap", ctypes.c_double),
+    ]
+
+
+_P = ctypes.c_void_p
+_D = ctypes.POINTER(ctypes.c_double)
+_U8 = ctypes.POINTER(ctypes.c_uint8)
+_I32 = ctypes.POINTER(ctypes.c_int32)
+_c_int, _c_double = ctypes.c_int, ctypes.c_double
+
+# name -> argtypes (restype is always int unless listed in _RESTYPE)
+_SIGNATURES = {
+    "ca_version": [],
+    "ca_last_error": [],
+    "ca_device_info": [ctypes.POINTER(_c_int)] * 3 + [ctypes.POINTER(ctypes.c_uint64)],
+    "ca_set_device": [_c_int],
+    "ca_gcate_create": [ctypes.POINTER(_P), _c_int, _c_int, _c_int, _c_int, _c_int, _c_double],
+    "ca_gcate_destroy": [_P],
+    "ca_gcate_load_counts": [_P, _D, _D, _D],
+    "ca_gcate_load_normalized": [_P, _D, _D, _D],
+    "ca_gcate_set_factors": [_P, _D, _D],
+    "ca_gcate_get_factors": [_P, _D, _D],
+    "ca_gcate_set_stage": [_P, _D, _c_int, _D, _c_int, _D, _c_int],
+    "ca_gcate_set_masks": [_P, _U8, _U8, _D],
+    "ca_gcate_get_masks": [_P, _U8, _U8],
+    "ca_gcate_update": [_P, _c_double, _c_double, _c_double, _c_int, _c_double, _D],
+    "ca_gcate_nll": [_P, _D],
+    "ca_gcate_grad": [_P, _c_int, _D],
+    "ca_gcate_alter_min": [_P, ctypes.POINTER(AltminParams), ctypes.POINTER(AltminResult), _D],
+    "ca_glm_create": [ctypes.POINTER(_P), _c_int, _c_int],
+    "ca_glm_destroy": [_P],
+    "ca_glm_load_counts": [_P, _D],
+    "ca_glm_share_counts": [_P, _P],
+    "ca_glm_fit": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _c_int, _D, _D, _I32, _I32],
+    "ca_glm_resid": [_P, _D],
+    "ca_glm_fitted": [_P, _D],
+    "ca_glm_disp_moments": [_P, _D, _D],
+    "ca_aipw_lfc": [_c_int] * 4 + [_D] * 8 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
+    "ca_aipw_lfc_shared": [_P, _c_int, _c_int] + [_D] * 7 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
+    "ca_aipw_lfc_yhat": [_c_int] * 3 + [_D] * 5 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
+}
+_RESTYPE = {"ca_last_error": ctypes.c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load(require_gpu=True):
+    """Load the shared library (once).  Raises ``CausarrayCudaError`` when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CausarrayCudaError(
+                "libcausarray_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, ctypes.c_int)
+        _lib = lib
+    if require_gpu:
+        sm = ctypes.c_int(0)
+        rc = _lib.ca_device_info(ctypes.byref(sm), None, None, None)
+        if rc != 0:
+            raise CausarrayCudaError("no usable CUDA device: %s" % _lib.ca_last_error().decode())
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = _lib.ca_last_error().decode() if _lib is not None else "library not loaded"
+        if rc == -2:
+            raise ValueError(msg)
+        raise CausarrayCudaError(msg)
+
+
+def dptr(a):
+    """Pointer to a C-contiguous float64 array (or NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_D)
+
+
+def u8ptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_U8)
+
+
+def i32ptr(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_I32)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,349 @@
+// Small streaming / bookkeeping kernels around the alternating minimisation
+// (K3 of SURVEY.md section 2b): size-factor normalisation + transpose, the
+// constant log h(y) sums (causarray/gcate_opt.py:343-347), thin-Q projections
+// (:176-179, :186-190), norm-ball projection (:10-26), Gamma clip (:202-203),
+// convergence masks (:427-438), the L1 objective term (:440) and the adaptive
+// lasso weights (:353).  All reductions use fixed-order trees.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ca {
+
+// ---- normalise + transpose -------------------------------------------------
+__global__ void k_normalize_transpose(const double* __restrict__ Yraw, int n, int p, long ld_in,
+                                      const double* __restrict__ sf, double* __restrict__ Yn, long ldYn,
+                                      double* __restrict__ Ynt, long ldYnt) {
+  __shared__ double tile[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, j = j0 + threadIdx.x;
+    double v = 0.0;
+    if (i < n && j < p) {
+      v = Yraw[(size_t)i * ld_in + j];
+      if (sf) v = v / sf[i];
+      if (Yn) Yn[(size_t)i * ldYn + j] = v;
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (Ynt) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int j = j0 + r, i = i0 + threadIdx.x;
+      if (j < p && i < n) Ynt[(size_t)j * ldYnt + i] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+int launch_normalize_transpose(const double* Yraw, int n, int p, long ld_in, const double* sf, double* Yn,
+                               long ldYn, double* Ynt, long ldYnt, cudaStream_t st) {
+  dim3 grid((p + 31) / 32, (n + 31) / 32), block(32, 8);
+  k_normalize_transpose<<<grid, block, 0, st>>>(Yraw, n, p, ld_in, sf, Yn, ldYn, Ynt, ldYnt);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_transpose(const double* src, int rows, int cols, long ld_in, double* dst, long ld_out, cudaStream_t st) {
+  return launch_normalize_transpose(src, rows, cols, ld_in, nullptr, nullptr, 0, dst, ld_out, st);
+}
+
+// ---- row sums of the constant term Tys -------------------------------------
+__global__ void k_tys_rowsum(const double* __restrict__ Yr, long ldY, int nrows, int ncols,
+                             const double* __restrict__ nu, int nu_per_row, int family, double thres,
+                             double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int row = blockIdx.x;
+  const double* y = Yr + (size_t)row * ldY;
+  double nur = 1.0, lgr = 0.0;
+  bool nb_row = false;
+  if (family == CA_FAMILY_NB && nu_per_row) {
+    nur = nu[row];
+    nb_row = !(nur > thres);
+    lgr = lgamma(nur);
+  }
+  double s = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    const double v = y[c];
+    double t = -lgamma(v + 1.0);
+    if (family == CA_FAMILY_NB) {
+      if (nu_per_row) {
+        if (nb_row) t += lgamma(nur + v) - lgr;
+      } else {
+        const double nc = nu[c];
+        if (!(nc > thres)) t += lgamma(nc + v) - lgamma(nc);
+      }
+    }
+    s += t;
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[row] = s;
+}
+
+int launch_tys_rowsum(const double* Yr, long ldY, int nrows, int ncols, const double* nu, int nu_per_row,
+                      int family, double thres, double* out, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  k_tys_rowsum<<<nrows, 256, 0, st>>>(Yr, ldY, nrows, ncols, nu, nu_per_row, family, thres, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_rowsum(const double* __restrict__ M, long ld, int ncols, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const double* y = M + (size_t)blockIdx.x * ld;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) s += y[c];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+int launch_rowsum(const double* M, long ld, int nrows, int ncols, double* out, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  k_rowsum<<<nrows, 256, 0, st>>>(M, ld, ncols, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_zero_fraction(const double* __restrict__ Yr, long ldY, int ncols, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const double* y = Yr + (size_t)blockIdx.x * ldY;
+  double s = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) s += (y[c] == 0.0) ? 1.0 : 0.0;
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = s / (double)ncols;
+}
+int launch_zero_fraction(const double* Yr, long ldY, int nrows, int ncols, double* out, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  k_zero_fraction<<<nrows, 256, 0, st>>>(Yr, ldY, ncols, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_sum(const double* __restrict__ v, int n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[0] = s;
+}
+int launch_sum(const double* v, int n, double* out, cudaStream_t st) {
+  k_sum<<<1, 1024, 0, st>>>(v, n, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_div_scalar(double* v, long n, double denom) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = v[i] / denom;
+}
+int launch_div_scalar(double* v, long n, double denom, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_div_scalar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n, denom);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- thin-Q projections ----------------------------------------------------
+__global__ void k_pt_v(const double* __restrict__ P, int ldP, const double* __restrict__ V, int ldV, int cv,
+                       int rows, double* __restrict__ W) {
+  __shared__ double scratch[32];
+  const int a = blockIdx.x / cv, b = blockIdx.x % cv;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) s += P[(size_t)i * ldP + a] * V[(size_t)i * ldV + b];
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) W[a * cv + b] = s;
+}
+int launch_pt_v(const double* P, int ldP, int cp, const double* V, int ldV, int cv, int rows, double* W,
+                cudaStream_t st) {
+  if (cp * cv <= 0) return 0;
+  k_pt_v<<<cp * cv, 256, 0, st>>>(P, ldP, V, ldV, cv, rows, W);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_sub_p_w(const double* __restrict__ P, int ldP, int cp, double* __restrict__ V, int ldV, int cv,
+                          int rows, const double* __restrict__ W) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)rows * cv) return;
+  const int i = (int)(e / cv), b = (int)(e % cv);
+  double s = 0.0;
+  for (int a = 0; a < cp; ++a) s += P[(size_t)i * ldP + a] * W[a * cv + b];
+  V[(size_t)i * ldV + b] -= s;
+}
+int launch_sub_p_w(const double* P, int ldP, int cp, double* V, int ldV, int cv, int rows, const double* W,
+                   cudaStream_t st) {
+  const long tot = (long)rows * cv;
+  if (tot <= 0) return 0;
+  k_sub_p_w<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P, ldP, cp, V, ldV, cv, rows, W);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- per-row line-search preparation ---------------------------------------
+__global__ void k_prep_search(PrepArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = a.rowlist ? *a.count : a.nrows;
+  if (idx >= total) return;
+  const int row = a.rowlist ? a.rowlist[idx] : idx;
+  double* g = a.g + (size_t)row * a.kpad;
+  for (int c = 0; c < a.kpad; ++c) g[c] = 0.0;
+  for (int c = 0; c < a.gc_n; ++c) g[a.gc_lo + c] = a.G[(size_t)row * a.ldG + c];
+  // inf-norm ball projection on [ball_lo, ball_hi)  (gcate_opt.py:10-26)
+  double mx = 0.0;
+  for (int c = a.ball_lo; c < a.ball_hi; ++c) mx = fmax(mx, fabs(g[c]));
+  if (mx > a.radius) {
+    const double sc = a.radius / mx;
+    for (int c = a.ball_lo; c < a.ball_hi; ++c) g[c] *= sc;
+  }
+  double ss = 0.0;
+  for (int c = 0; c < a.kpad; ++c) ss += g[c] * g[c];
+  a.normg[row] = sqrt(ss);
+  double pen = 0.0;
+  const int nprox = a.prox_hi - a.prox_lo;
+  if (a.lam && nprox > 0) {
+    const double* x = a.X + (size_t)row * a.kpad;
+    for (int c = 0; c < nprox; ++c) pen += a.lam[(size_t)row * a.ldlam + c] * fabs(x[a.prox_lo + c]);
+    pen /= (double)nprox;
+  }
+  a.f0[row] = -(a.ell0[row] + a.tys[row]) / (double)a.ncols + pen;
+}
+int launch_prep_search(const PrepArgs& a, cudaStream_t st) {
+  if (a.nrows <= 0) return 0;
+  k_prep_search<<<(a.nrows + 127) / 128, 128, 0, st>>>(a);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- mask compaction (deterministic, single CTA) ---------------------------
+__global__ void k_compact(const uint8_t* __restrict__ mask, int n, int* __restrict__ list, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const int flag = (i < n && mask[i]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int pre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (flag) list[off + pre] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream_t st) {
+  k_compact<<<1, 1024, 0, st>>>(mask, n, list, count);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- clip (records rows that changed) --------------------------------------
+__global__ void k_clip(double* X, int rows, int kpad, int lo, int hi, double bound, int* list, int* count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  bool changed = false;
+  double* x = X + (size_t)i * kpad;
+  for (int c = lo; c < hi; ++c) {
+    const double v = x[c];
+    const double w = fmin(fmax(v, -bound), bound);
+    if (w != v) {
+      x[c] = w;
+      changed = true;
+    }
+  }
+  if (changed && list) list[atomicAdd(count, 1)] = i;
+}
+int launch_clip(double* X, int rows, int kpad, int lo, int hi, double bound, int* list, int* count, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (count) CA_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+  k_clip<<<(rows + 127) / 128, 128, 0, st>>>(X, rows, kpad, lo, hi, bound, list, count);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- convergence masks -----------------------------------------------------
+__global__ void k_step_mask(const double* __restrict__ X, const double* __restrict__ Xp, int rows, int kpad, int lo,
+                            int hi, double tol, uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double ss = 0.0;
+  for (int c = lo; c < hi; ++c) {
+    const double dlt = X[(size_t)i * kpad + c] - Xp[(size_t)i * kpad + c];
+    ss += dlt * dlt;
+  }
+  mask[i] = sqrt(ss) > tol ? 1 : 0;
+}
+__global__ void k_count_u8(const uint8_t* __restrict__ m, int n, int* __restrict__ count) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += m[i] ? 1.0 : 0.0;
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) *count = (int)(s + 0.5);
+}
+int launch_step_mask(const double* X, const double* Xprev, int rows, int kpad, int lo, int hi, double tol,
+                     uint8_t* mask, int* count, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  k_step_mask<<<(rows + 127) / 128, 128, 0, st>>>(X, Xprev, rows, kpad, lo, hi, tol, mask);
+  CA_LAUNCH_CHECK();
+  if (count) {
+    k_count_u8<<<1, 1024, 0, st>>>(mask, rows, count);
+    CA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+__global__ void k_fill_u8(uint8_t* v, int n, uint8_t val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = val;
+}
+int launch_fill_u8(uint8_t* v, int n, uint8_t val, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_fill_u8<<<(n + 255) / 256, 256, 0, st>>>(v, n, val);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- L1 term and adaptive weights -------------------------------------------
+__global__ void k_l1_penalty(const double* __restrict__ X, int rows, int kpad, int lo, int hi,
+                             const double* __restrict__ lam, int ldlam, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int w = hi - lo;
+  double s = 0.0;
+  for (long e = threadIdx.x; e < (long)rows * w; e += blockDim.x) {
+    const int i = (int)(e / w), c = (int)(e % w);
+    s += fabs(X[(size_t)i * kpad + lo + c]) * lam[(size_t)i * ldlam + c];
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) out[0] = s;
+}
+int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const double* lam, int ldlam, double* out,
+                      cudaStream_t st) {
+  k_l1_penalty<<<1, 1024, 0, st>>>(X, rows, kpad, lo, hi, lam, ldlam, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void k_adaptive_weights(const double* __restrict__ X, int rows, int kpad, int lo, int hi, double lam0,
+                                   double* __restrict__ lam, int ldlam) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = hi - lo;
+  if (e >= (long)rows * w) return;
+  const int i = (int)(e / w), c = (int)(e % w);
+  lam[(size_t)i * ldlam + c] = lam0 / (fabs(X[(size_t)i * kpad + lo + c]) + 1e-6);
+}
+int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi, double lam0, double* lam, int ldlam,
+                            cudaStream_t st) {
+  const long tot = (long)rows * (hi - lo);
+  if (tot <= 0) return 0;
+  k_adaptive_weights<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, rows, kpad, lo, hi, lam0, lam, ldlam);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ca

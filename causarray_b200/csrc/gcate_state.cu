@@ -1,0 +1,661 @@
+// S1 seam: device-resident GCATE problem + the host-side driver of one
+// alternating iteration (update_with_mask, causarray/gcate_opt.py:148-206) and
+// of the optimiser loop (alter_min, causarray/gcate_opt.py:337-458).
+#include <stdarg.h>
+#include <string.h>
+#include <chrono>
+#include <cmath>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/causarray_b200.h"
+#include "common.cuh"
+#include "devbuf.h"
+#include "kernels.h"
+#include "gcate_state.h"
+
+namespace ca {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+int cuda_fail(cudaError_t e, const char* what, int line) {
+  set_error("CUDA error %d (%s) in %s at line %d", (int)e, cudaGetErrorString(e), what, line);
+  return -1;
+}
+const char* last_error() { return g_err.c_str(); }
+
+int kpad_for(int k) {
+  int kp = round_up(k, 4);
+  while (kp % 8 != 4) kp += 4;
+  return kp;
+}
+
+}  // namespace ca
+
+using namespace ca;
+
+
+static int gcate_alloc(ca_gcate* h) {
+  const int n = h->n, p = h->p, kp = h->kpad;
+  if (h->Yn.alloc((size_t)n * h->ldp) || h->Ynt.alloc((size_t)p * h->ldn)) return -1;
+  if (h->nu.alloc(p) || h->tys_row.alloc(n) || h->tys_col.alloc(p) || h->tys_total.alloc(1) || h->sparsity.alloc(p))
+    return -1;
+  if (h->A.alloc((size_t)n * kp) || h->B.alloc((size_t)p * kp) || h->Aprev.alloc((size_t)n * kp) ||
+      h->Bprev.alloc((size_t)p * kp))
+    return -1;
+  if (h->gene_active.alloc(p) || h->cell_active.alloc(n) || h->list_c.alloc(n) || h->list_g.alloc(p) ||
+      h->list_clip.alloc(p) || h->counts.alloc(8))
+    return -1;
+  if (h->ell_c.alloc(n) || h->ell_g.alloc(p) || h->ellfin_c.alloc(n) || h->ellfin_g.alloc(p) ||
+      h->Graw_c.alloc((size_t)n * h->ldG) || h->Graw_g.alloc((size_t)p * h->ldG) || h->g_c.alloc((size_t)n * kp) ||
+      h->g_g.alloc((size_t)p * kp) || h->f0_c.alloc(n) || h->f0_g.alloc(p) || h->ng_c.alloc(n) || h->ng_g.alloc(p) ||
+      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(2) || h->alpha_gene.alloc(p))
+    return -1;
+  CA_CUDA(cudaMemsetAsync(h->Yn.ptr, 0, h->Yn.bytes(), h->st));
+  CA_CUDA(cudaMemsetAsync(h->Ynt.ptr, 0, h->Ynt.bytes(), h->st));
+  CA_CUDA(cudaMemsetAsync(h->A.ptr, 0, h->A.bytes(), h->st));
+  CA_CUDA(cudaMemsetAsync(h->B.ptr, 0, h->B.bytes(), h->st));
+  CA_CUDA(cudaMemsetAsync(h->evals.ptr, 0, h->evals.bytes(), h->st));
+  if (launch_fill_u8(h->gene_active.ptr, p, 1, h->st) || launch_fill_u8(h->cell_active.ptr, n, 1, h->st)) return -1;
+  return 0;
+}
+
+extern "C" int ca_version(void) { return 100; }
+extern "C" const char* ca_last_error(void) { return ca::last_error(); }
+
+extern "C" int ca_set_device(int device) {
+  CA_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+extern "C" int ca_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem) {
+  int dev = 0;
+  CA_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CA_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = (uint64_t)prop.totalGlobalMem;
+  return 0;
+}
+
+extern "C" int ca_gcate_create(ca_gcate_t* out, int n, int p, int d, int r, int family, double thres_disp) {
+  CA_REQUIRE(out && n > 0 && p > 0 && d >= 0 && r >= 0 && d + r > 0, "bad dimensions");
+  CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
+  CA_REQUIRE(d + r <= 64, "d + r > 64 is not supported");
+  ca_gcate* h = new (std::nothrow) ca_gcate();
+  CA_REQUIRE(h, "out of host memory");
+  h->n = n;
+  h->p = p;
+  h->d = d;
+  h->r = r;
+  h->k = d + r;
+  h->kpad = kpad_for(h->k);
+  h->family = family;
+  h->thres = thres_disp;
+  h->ldp = round_up(p, 8);
+  h->ldn = round_up(n, 8);
+  h->st = 0;
+  if (gcate_alloc(h)) {
+    delete h;
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" int ca_gcate_destroy(ca_gcate_t h) {
+  if (h) {
+    cudaStreamSynchronize(h->st);
+    delete h;
+  }
+  return 0;
+}
+
+static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_or_null) {
+  const int n = h->n, p = h->p;
+  std::vector<double> ones;
+  if (!nu_host) {
+    ones.assign(p, 1.0);
+    nu_host = ones.data();
+  }
+  CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu_host, sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  if (Ys_dev_or_null) {
+    // row sums directly; column sums through a transposed copy staged in Graw buffers is too small,
+    // so reuse Ynt's shape with a temporary
+    DevBuf<double> tmp;
+    if (tmp.alloc((size_t)p * h->ldn)) return -1;
+    CA_CUDA(cudaMemsetAsync(tmp.ptr, 0, tmp.bytes(), h->st));
+    if (launch_rowsum(Ys_dev_or_null, p, n, p, h->tys_row.ptr, h->st)) return -1;
+    if (launch_transpose(Ys_dev_or_null, n, p, p, tmp.ptr, h->ldn, h->st)) return -1;
+    if (launch_rowsum(tmp.ptr, h->ldn, p, n, h->tys_col.ptr, h->st)) return -1;
+    CA_CUDA(cudaStreamSynchronize(h->st));
+  } else {
+    if (launch_tys_rowsum(h->Yn.ptr, h->ldp, n, p, h->nu.ptr, 0, h->family, h->thres, h->tys_row.ptr, h->st)) return -1;
+    if (launch_tys_rowsum(h->Ynt.ptr, h->ldn, p, n, h->nu.ptr, 1, h->family, h->thres, h->tys_col.ptr, h->st)) return -1;
+  }
+  if (launch_sum(h->tys_col.ptr, p, h->tys_total.ptr, h->st)) return -1;
+  if (launch_zero_fraction(h->Ynt.ptr, h->ldn, p, n, h->sparsity.ptr, h->st)) return -1;
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  h->counts_loaded = true;
+  return 0;
+}
+
+extern "C" int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu) {
+  CA_REQUIRE(h && Y, "null argument");
+  const int n = h->n, p = h->p;
+  if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
+  DevBuf<double> sf;
+  CA_CUDA(cudaMemcpyAsync(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  const double* sfp = nullptr;
+  if (size_factor) {
+    if (sf.alloc(n)) return -1;
+    CA_CUDA(cudaMemcpyAsync(sf.ptr, size_factor, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+    sfp = sf.ptr;
+  }
+  CA_CUDA(cudaMemsetAsync(h->Yraw_t.ptr, 0, h->Yraw_t.bytes(), h->st));
+  if (launch_transpose(h->Yraw.ptr, n, p, p, h->Yraw_t.ptr, h->ldn, h->st)) return -1;
+  if (launch_normalize_transpose(h->Yraw.ptr, n, p, p, sfp, h->Yn.ptr, h->ldp, h->Ynt.ptr, h->ldn, h->st)) return -1;
+  h->raw_loaded = true;
+  int rc = finish_load(h, nu, nullptr);
+  return rc;
+}
+
+extern "C" int ca_gcate_load_normalized(ca_gcate_t h, const double* Yn, const double* Ys, const double* nu) {
+  CA_REQUIRE(h && Yn, "null argument");
+  const int n = h->n, p = h->p;
+  DevBuf<double> tmp, ys;
+  if (tmp.alloc((size_t)n * p)) return -1;
+  CA_CUDA(cudaMemcpyAsync(tmp.ptr, Yn, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  if (launch_normalize_transpose(tmp.ptr, n, p, p, nullptr, h->Yn.ptr, h->ldp, h->Ynt.ptr, h->ldn, h->st)) return -1;
+  if (Ys) {
+    if (ys.alloc((size_t)n * p)) return -1;
+    CA_CUDA(cudaMemcpyAsync(ys.ptr, Ys, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  }
+  return finish_load(h, nu, Ys ? ys.ptr : nullptr);
+}
+
+static int upload_padded(double* dst, const double* src, int rows, int k, int kpad, cudaStream_t st) {
+  CA_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)rows * kpad, st));
+  CA_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * kpad, src, sizeof(double) * k, sizeof(double) * k, rows,
+                            cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+extern "C" int ca_gcate_set_factors(ca_gcate_t h, const double* A, const double* B) {
+  CA_REQUIRE(h, "null handle");
+  if (A && upload_padded(h->A.ptr, A, h->n, h->k, h->kpad, h->st)) return -1;
+  if (B && upload_padded(h->B.ptr, B, h->p, h->k, h->kpad, h->st)) return -1;
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  h->factors_set = true;
+  return 0;
+}
+
+extern "C" int ca_gcate_get_factors(ca_gcate_t h, double* A, double* B) {
+  CA_REQUIRE(h, "null handle");
+  if (A)
+    CA_CUDA(cudaMemcpy2DAsync(A, sizeof(double) * h->k, h->A.ptr, sizeof(double) * h->kpad, sizeof(double) * h->k,
+                              h->n, cudaMemcpyDeviceToHost, h->st));
+  if (B)
+    CA_CUDA(cudaMemcpy2DAsync(B, sizeof(double) * h->k, h->B.ptr, sizeof(double) * h->kpad, sizeof(double) * h->k,
+                              h->p, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_gcate_set_stage(ca_gcate_t h, const double* P1, int d1, const double* P2, int r2, const double* lam,
+                                  int a) {
+  CA_REQUIRE(h, "null handle");
+  CA_REQUIRE(a >= 0 && a <= h->d, "a must be in [0, d]");
+  CA_REQUIRE(!(P1 && P2), "P1 and P2 are mutually exclusive");
+  h->has_P1 = P1 != nullptr;
+  h->has_P2 = P2 != nullptr;
+  h->has_lam = lam != nullptr && a > 0;
+  h->a = a;
+  if (P1) {
+    CA_REQUIRE(d1 > 0 && d1 <= 64, "bad P1 width");
+    h->d1 = d1;
+    if (h->P1.alloc((size_t)h->n * d1)) return -1;
+    CA_CUDA(cudaMemcpyAsync(h->P1.ptr, P1, sizeof(double) * (size_t)h->n * d1, cudaMemcpyHostToDevice, h->st));
+  }
+  if (P2) {
+    CA_REQUIRE(r2 > 0 && r2 <= 64, "bad P2 width");
+    h->r2 = r2;
+    if (h->P2.alloc((size_t)h->p * r2)) return -1;
+    CA_CUDA(cudaMemcpyAsync(h->P2.ptr, P2, sizeof(double) * (size_t)h->p * r2, cudaMemcpyHostToDevice, h->st));
+  }
+  if (a > 0) {
+    if (h->lam.alloc((size_t)h->p * a)) return -1;
+    if (lam)
+      CA_CUDA(cudaMemcpyAsync(h->lam.ptr, lam, sizeof(double) * (size_t)h->p * a, cudaMemcpyHostToDevice, h->st));
+    else
+      CA_CUDA(cudaMemsetAsync(h->lam.ptr, 0, h->lam.bytes(), h->st));
+  }
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_gcate_set_masks(ca_gcate_t h, const uint8_t* gene_active, const uint8_t* cell_active,
+                                  const double* alpha_gene) {
+  CA_REQUIRE(h, "null handle");
+  if (gene_active)
+    CA_CUDA(cudaMemcpyAsync(h->gene_active.ptr, gene_active, h->p, cudaMemcpyHostToDevice, h->st));
+  else if (launch_fill_u8(h->gene_active.ptr, h->p, 1, h->st))
+    return -1;
+  if (cell_active)
+    CA_CUDA(cudaMemcpyAsync(h->cell_active.ptr, cell_active, h->n, cudaMemcpyHostToDevice, h->st));
+  else if (launch_fill_u8(h->cell_active.ptr, h->n, 1, h->st))
+    return -1;
+  h->has_alpha_gene = alpha_gene != nullptr;
+  if (alpha_gene)
+    CA_CUDA(cudaMemcpyAsync(h->alpha_gene.ptr, alpha_gene, sizeof(double) * h->p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_gcate_get_masks(ca_gcate_t h, uint8_t* gene_active, uint8_t* cell_active) {
+  CA_REQUIRE(h, "null handle");
+  if (gene_active) CA_CUDA(cudaMemcpyAsync(gene_active, h->gene_active.ptr, h->p, cudaMemcpyDeviceToHost, h->st));
+  if (cell_active) CA_CUDA(cudaMemcpyAsync(cell_active, h->cell_active.ptr, h->n, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+static RowProblem cell_problem(ca_gcate* h) {
+  RowProblem rp;
+  rp.Y = h->Yn.ptr;
+  rp.ldY = h->ldp;
+  rp.ncols = h->p;
+  rp.M = h->B.ptr;
+  rp.kpad = h->kpad;
+  rp.nu = h->nu.ptr;
+  rp.nu_per_row = 0;
+  rp.family = h->family;
+  rp.thres_disp = h->thres;
+  return rp;
+}
+static RowProblem gene_problem(ca_gcate* h) {
+  RowProblem rp;
+  rp.Y = h->Ynt.ptr;
+  rp.ldY = h->ldn;
+  rp.ncols = h->n;
+  rp.M = h->A.ptr;
+  rp.kpad = h->kpad;
+  rp.nu = h->nu.ptr;
+  rp.nu_per_row = 1;
+  rp.family = h->family;
+  rp.thres_disp = h->thres;
+  return rp;
+}
+
+// One alternating iteration, asynchronous on h->st.  On completion
+// scal[0] = sum_j ell_fin_g[j] (log-likelihood sum at the new A, B).
+static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int max_iters, double tol) {
+  const int n = h->n, p = h->p, d = h->d, k = h->k, kp = h->kpad, r = h->r;
+  cudaStream_t st = h->st;
+  int* cnt = h->counts.ptr;
+  // ---------------- A-step (cells) ----------------
+  if (r > 0) {
+    RowProblem rp = cell_problem(h);
+    if (launch_compact(h->cell_active.ptr, n, h->list_c.ptr, cnt + 0, st)) return -1;
+    if (launch_rowpass(rp, h->A.ptr, h->list_c.ptr, cnt + 0, n, true, d, r, h->ell_c.ptr, h->Graw_c.ptr, h->ldG, st))
+      return -1;
+    if (launch_div_scalar(h->Graw_c.ptr, (long)n * h->ldG, (double)p, st)) return -1;
+    PrepArgs pa;
+    pa.nrows = n;
+    pa.rowlist = h->list_c.ptr;
+    pa.count = cnt + 0;
+    pa.kpad = kp;
+    pa.ncols = p;
+    pa.G = h->Graw_c.ptr;
+    pa.ldG = h->ldG;
+    pa.gc_lo = d;
+    pa.gc_n = r;
+    pa.ball_lo = d;
+    pa.ball_hi = k;
+    pa.radius = 2.0 * C;
+    pa.X = h->A.ptr;
+    pa.lam = nullptr;
+    pa.ldlam = 0;
+    pa.prox_lo = pa.prox_hi = 0;
+    pa.ell0 = h->ell_c.ptr;
+    pa.tys = h->tys_row.ptr;
+    pa.g = h->g_c.ptr;
+    pa.f0 = h->f0_c.ptr;
+    pa.normg = h->ng_c.ptr;
+    if (launch_prep_search(pa, st)) return -1;
+    SearchLaunch s;
+    s.X = h->A.ptr;
+    s.g = h->g_c.ptr;
+    s.f0 = h->f0_c.ptr;
+    s.normg = h->ng_c.ptr;
+    s.tys = h->tys_row.ptr;
+    s.lam = nullptr;
+    s.ldlam = 0;
+    s.prox_lo = s.prox_hi = 0;
+    s.alpha_row = nullptr;
+    s.alpha = alpha;
+    s.beta = beta;
+    s.tol = tol;
+    s.max_iters = max_iters;
+    s.rowlist = h->list_c.ptr;
+    s.count = cnt + 0;
+    s.nrows = n;
+    s.ell_fin = h->ellfin_c.ptr;
+    s.neval = nullptr;
+    s.eval_total = h->evals.ptr + 0;
+    if (launch_search(rp, s, st)) return -1;
+    if (h->has_P1) {
+      if (launch_pt_v(h->P1.ptr, h->d1, h->d1, h->A.ptr + d, kp, r, n, h->W.ptr, st)) return -1;
+      if (launch_sub_p_w(h->P1.ptr, h->d1, h->d1, h->A.ptr + d, kp, r, n, h->W.ptr, st)) return -1;
+    }
+  }
+  // ---------------- B-step (genes) ----------------
+  {
+    RowProblem rp = gene_problem(h);
+    const int a = h->a;
+    int gc_lo, gc_n, ball_lo, ball_hi;
+    if (h->has_P1) {
+      gc_lo = d;
+      gc_n = r;
+      ball_lo = d;
+      ball_hi = k;
+    } else if (h->has_P2) {
+      gc_lo = d - a;
+      gc_n = a;
+      ball_lo = 0;
+      ball_hi = d;
+    } else {
+      gc_lo = 0;
+      gc_n = k;
+      ball_lo = d;
+      ball_hi = k;
+    }
+    const bool any_grad = gc_n > 0;
+    // all genes: the column log-likelihood of inactive genes changes with A
+    if (launch_rowpass(rp, h->B.ptr, nullptr, nullptr, p, any_grad, gc_lo, gc_n, h->ell_g.ptr, h->Graw_g.ptr, h->ldG, st))
+      return -1;
+    CA_CUDA(cudaMemcpyAsync(h->ellfin_g.ptr, h->ell_g.ptr, sizeof(double) * p, cudaMemcpyDeviceToDevice, st));
+    if (any_grad) {
+      if (launch_div_scalar(h->Graw_g.ptr, (long)p * h->ldG, (double)n, st)) return -1;
+      if (h->has_P2) {
+        if (launch_pt_v(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
+        if (launch_sub_p_w(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
+      }
+      if (launch_compact(h->gene_active.ptr, p, h->list_g.ptr, cnt + 1, st)) return -1;
+      PrepArgs pa;
+      pa.nrows = p;
+      pa.rowlist = h->list_g.ptr;
+      pa.count = cnt + 1;
+      pa.kpad = kp;
+      pa.ncols = n;
+      pa.G = h->Graw_g.ptr;
+      pa.ldG = h->ldG;
+      pa.gc_lo = gc_lo;
+      pa.gc_n = gc_n;
+      pa.ball_lo = ball_lo;
+      pa.ball_hi = ball_hi;
+      pa.radius = 2.0 * C;
+      pa.X = h->B.ptr;
+      pa.lam = (a > 0 && h->has_lam) ? h->lam.ptr : nullptr;
+      pa.ldlam = a;
+      pa.prox_lo = d - a;
+      pa.prox_hi = d;
+      pa.ell0 = h->ell_g.ptr;
+      pa.tys = h->tys_col.ptr;
+      pa.g = h->g_g.ptr;
+      pa.f0 = h->f0_g.ptr;
+      pa.normg = h->ng_g.ptr;
+      if (launch_prep_search(pa, st)) return -1;
+      SearchLaunch s;
+      s.X = h->B.ptr;
+      s.g = h->g_g.ptr;
+      s.f0 = h->f0_g.ptr;
+      s.normg = h->ng_g.ptr;
+      s.tys = h->tys_col.ptr;
+      s.lam = pa.lam;
+      s.ldlam = a;
+      s.prox_lo = d - a;
+      s.prox_hi = d;
+      s.alpha_row = h->has_alpha_gene ? h->alpha_gene.ptr : nullptr;
+      s.alpha = alpha;
+      s.beta = beta;
+      s.tol = tol;
+      s.max_iters = max_iters;
+      s.rowlist = h->list_g.ptr;
+      s.count = cnt + 1;
+      s.nrows = p;
+      s.ell_fin = h->ellfin_g.ptr;
+      s.neval = nullptr;
+      s.eval_total = h->evals.ptr + 1;
+      if (launch_search(rp, s, st)) return -1;
+    }
+    if (!h->has_P2 && r > 0) {
+      // clip Gamma to [-10, 10] (gcate_opt.py:202-203); re-evaluate genes that were clipped
+      if (launch_clip(h->B.ptr, p, kp, d, k, 10.0, h->list_clip.ptr, cnt + 2, st)) return -1;
+      if (launch_rowpass(rp, h->B.ptr, h->list_clip.ptr, cnt + 2, p, false, 0, 0, h->ellfin_g.ptr, nullptr, 0, st))
+        return -1;
+    }
+    if (launch_sum(h->ellfin_g.ptr, p, h->scal.ptr + 0, st)) return -1;
+  }
+  return 0;
+}
+
+static double nll_from_sum(ca_gcate* h, double ell_sum, double tys_total) {
+  return -(ell_sum + tys_total) / (double)h->n;
+}
+
+extern "C" int ca_gcate_update(ca_gcate_t h, double C, double alpha, double beta, int max_iters, double tol,
+                               double* func_val) {
+  CA_REQUIRE(h && h->counts_loaded && h->factors_set, "load counts and factors first");
+  if (enqueue_update(h, C, alpha, beta, max_iters, tol)) return -1;
+  double host[2];
+  CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaMemcpyAsync(host + 1, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  if (func_val) *func_val = nll_from_sum(h, host[0], host[1]);
+  return 0;
+}
+
+extern "C" int ca_gcate_nll(ca_gcate_t h, double* out) {
+  CA_REQUIRE(h && h->counts_loaded && h->factors_set && out, "load counts and factors first");
+  RowProblem rp = gene_problem(h);
+  if (launch_rowpass(rp, h->B.ptr, nullptr, nullptr, h->p, false, 0, 0, h->ell_g.ptr, nullptr, 0, h->st)) return -1;
+  if (launch_sum(h->ell_g.ptr, h->p, h->scal.ptr + 1, h->st)) return -1;
+  double host[2];
+  CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr + 1, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaMemcpyAsync(host + 1, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  *out = nll_from_sum(h, host[0], host[1]);
+  return 0;
+}
+
+extern "C" int ca_gcate_grad(ca_gcate_t h, int wrt_A, double* out) {
+  CA_REQUIRE(h && h->counts_loaded && h->factors_set && out, "load counts and factors first");
+  const int k = h->k;
+  RowProblem rp = wrt_A ? cell_problem(h) : gene_problem(h);
+  const int rows = wrt_A ? h->n : h->p;
+  const double* X = wrt_A ? h->A.ptr : h->B.ptr;
+  double* G = wrt_A ? h->Graw_c.ptr : h->Graw_g.ptr;
+  double* ell = wrt_A ? h->ell_c.ptr : h->ell_g.ptr;
+  if (launch_rowpass(rp, X, nullptr, nullptr, rows, true, 0, k, ell, G, h->ldG, h->st)) return -1;
+  if (launch_div_scalar(G, (long)rows * h->ldG, (double)rp.ncols, h->st)) return -1;
+  CA_CUDA(cudaMemcpy2DAsync(out, sizeof(double) * k, G, sizeof(double) * h->ldG, sizeof(double) * k, rows,
+                            cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_altmin_result* res, double* hist) {
+  CA_REQUIRE(h && prm && res && hist, "null argument");
+  CA_REQUIRE(h->counts_loaded && h->factors_set, "load counts and factors first");
+  const int n = h->n, p = h->p, d = h->d, kp = h->kpad;
+  cudaStream_t st = h->st;
+  const int a = prm->a;
+  CA_REQUIRE(a >= 0 && a <= d, "a must be in [0, d]");
+  h->a = a;
+  // stage-2 entry projection  B[:, d-a:d] -= P2 (P2^T B[:, d-a:d])   (gcate_opt.py:337-340)
+  if (h->has_P2 && a > 0) {
+    if (launch_pt_v(h->P2.ptr, h->r2, h->r2, h->B.ptr + (d - a), kp, a, p, h->W.ptr, st)) return -1;
+    if (launch_sub_p_w(h->P2.ptr, h->r2, h->r2, h->B.ptr + (d - a), kp, a, p, h->W.ptr, st)) return -1;
+  }
+  // adaptive lasso weights (gcate_opt.py:352-353)
+  h->has_lam = false;
+  if (a > 0) {
+    if (h->lam.alloc((size_t)p * a)) return -1;
+    if (launch_adaptive_weights(h->B.ptr, p, kp, d - a, d, prm->lam, h->lam.ptr, a, st)) return -1;
+    h->has_lam = prm->lam != 0.0;
+  }
+  // per-gene initial step (gcate_opt.py:366-372)
+  {
+    std::vector<double> sp(p), ag(p);
+    CA_CUDA(cudaMemcpyAsync(sp.data(), h->sparsity.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < p; ++j) {
+      ag[j] = prm->alpha;
+      if (sp[j] > prm->sparsity_threshold) ag[j] *= (1.0 + prm->sparsity_boost * sp[j]);
+    }
+    CA_CUDA(cudaMemcpyAsync(h->alpha_gene.ptr, ag.data(), sizeof(double) * p, cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    h->has_alpha_gene = true;
+  }
+  if (launch_fill_u8(h->gene_active.ptr, p, 1, st) || launch_fill_u8(h->cell_active.ptr, n, 1, st)) return -1;
+  CA_CUDA(cudaMemsetAsync(h->evals.ptr, 0, h->evals.bytes(), st));
+
+  double tys_total = 0.0;
+  CA_CUDA(cudaMemcpyAsync(&tys_total, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, st));
+  auto objective = [&](double ell_sum, double pen) { return (nll_from_sum(h, ell_sum, tys_total) + pen) / (double)p; };
+  auto penalty_async = [&]() -> int {
+    if (a > 0 && h->has_lam) return launch_l1_penalty(h->B.ptr, p, kp, d - a, d, h->lam.ptr, a, h->scal.ptr + 2, st);
+    CA_CUDA(cudaMemsetAsync(h->scal.ptr + 2, 0, sizeof(double), st));
+    return 0;
+  };
+  double host[4];
+  // initial objective
+  {
+    RowProblem rp = gene_problem(h);
+    if (launch_rowpass(rp, h->B.ptr, nullptr, nullptr, p, false, 0, 0, h->ell_g.ptr, nullptr, 0, st)) return -1;
+    if (launch_sum(h->ell_g.ptr, p, h->scal.ptr + 0, st)) return -1;
+    if (penalty_async()) return -1;
+    CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+  }
+  double f_pre = objective(host[0], host[2]);
+  double f = f_pre;
+  int nh = 0;
+  hist[nh++] = f_pre;
+  int64_t tot_g = 0, tot_c = 0;
+  int n_act_g = p, n_act_c = n;
+
+  // sparse-gene B-only warm-up (gcate_opt.py:382-398)
+  if (prm->warmup_iters > 0) {
+    std::vector<double> sp(p);
+    CA_CUDA(cudaMemcpy(sp.data(), h->sparsity.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> gm(p);
+    bool any = false;
+    for (int j = 0; j < p; ++j) {
+      gm[j] = sp[j] > prm->sparsity_threshold;
+      any |= gm[j] != 0;
+    }
+    if (any) {
+      CA_CUDA(cudaMemcpy(h->gene_active.ptr, gm.data(), p, cudaMemcpyHostToDevice));
+      if (launch_fill_u8(h->cell_active.ptr, n, 0, st)) return -1;
+      for (int w = 0; w < prm->warmup_iters; ++w)
+        if (enqueue_update(h, prm->C, prm->alpha, prm->beta, prm->ls_max_iters, prm->tol)) return -1;
+      if (penalty_async()) return -1;
+      CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+      CA_CUDA(cudaStreamSynchronize(st));
+      f_pre = objective(host[0], host[2]);
+      f = f_pre;
+      hist[0] = f_pre;
+      if (launch_fill_u8(h->gene_active.ptr, p, 1, st) || launch_fill_u8(h->cell_active.ptr, n, 1, st)) return -1;
+    }
+  }
+
+  // Early_Stopping state (causarray/utils.py:101-161)
+  int es_step = -1, es_best_step = -1;
+  double es_best = INFINITY;
+  const bool use_mask = prm->tol_gene > 0 || prm->tol_cell > 0;
+  int t = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  for (t = 0; t < prm->es_max_iters; ++t) {
+    if (use_mask) {
+      CA_CUDA(cudaMemcpyAsync(h->Bprev.ptr, h->B.ptr, h->B.bytes(), cudaMemcpyDeviceToDevice, st));
+      CA_CUDA(cudaMemcpyAsync(h->Aprev.ptr, h->A.ptr, h->A.bytes(), cudaMemcpyDeviceToDevice, st));
+    }
+    if (enqueue_update(h, prm->C, prm->alpha, prm->beta, prm->ls_max_iters, prm->tol)) return -1;
+    tot_g += n_act_g;
+    tot_c += n_act_c;
+    if (use_mask) {
+      if (prm->recheck_interval > 0 && (t + 1) % prm->recheck_interval == 0) {
+        if (launch_fill_u8(h->gene_active.ptr, p, 1, st) || launch_fill_u8(h->cell_active.ptr, n, 1, st)) return -1;
+        n_act_g = p;
+        n_act_c = n;
+        CA_CUDA(cudaMemsetAsync(h->counts.ptr + 3, 0xff, 2 * sizeof(int), st));
+      } else {
+        if (prm->tol_gene > 0) {
+          if (launch_step_mask(h->B.ptr, h->Bprev.ptr, p, kp, 0, kp, prm->tol_gene, h->gene_active.ptr,
+                               h->counts.ptr + 4, st))
+            return -1;
+        }
+        if (prm->tol_cell > 0) {
+          if (launch_step_mask(h->A.ptr, h->Aprev.ptr, n, kp, d, kp, prm->tol_cell, h->cell_active.ptr,
+                               h->counts.ptr + 3, st))
+            return -1;
+        }
+      }
+    }
+    if (penalty_async()) return -1;
+    int hc[2] = {-1, -1};
+    CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaMemcpyAsync(hc, h->counts.ptr + 3, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    if (use_mask && !(prm->recheck_interval > 0 && (t + 1) % prm->recheck_interval == 0)) {
+      if (prm->tol_cell > 0) n_act_c = hc[0];
+      if (prm->tol_gene > 0) n_act_g = hc[1];
+    }
+    f = objective(host[0], host[2]);
+    hist[nh++] = f;
+    if (!std::isfinite(f) || f > std::fmax(1e3 * std::fabs(f_pre), 1e3)) {
+      break;  // divergence guard (gcate_opt.py:442-444)
+    }
+    // Early_Stopping.__call__
+    bool stop = false;
+    es_step += 1;
+    if (es_step >= prm->es_warmup) {
+      const double thr = std::isfinite(es_best) ? prm->es_tolerance + prm->es_rel_tol * std::fabs(es_best) : 0.0;
+      if (f < es_best - thr) {
+        es_best = f;
+        es_best_step = es_step;
+      } else if (es_step - es_best_step > prm->es_patience) {
+        stop = true;
+      }
+    }
+    if (stop) break;
+    f_pre = f;
+  }
+  if (t == prm->es_max_iters) t = prm->es_max_iters - 1;  // python's loop variable after exhaustion
+  auto t1 = std::chrono::steady_clock::now();
+  unsigned long long ev[2];
+  CA_CUDA(cudaMemcpy(ev, h->evals.ptr, sizeof ev, cudaMemcpyDeviceToHost));
+  res->n_iter = t;
+  res->func_val = f;
+  res->resid = f_pre - f;
+  res->hist_len = nh;
+  res->total_gene_updates = tot_g;
+  res->total_cell_updates = tot_c;
+  res->cell_evals = (int64_t)ev[0];
+  res->gene_evals = (int64_t)ev[1];
+  res->loop_seconds = std::chrono::duration<double>(t1 - t0).count();
+  return 0;
+}

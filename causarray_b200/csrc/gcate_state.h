@@ -1,0 +1,29 @@
+// Device-resident state behind ca_gcate_t (shared with glm.cu / dr.cu so the
+// raw counts uploaded once can be reused by the GLM and AIPW stages).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "devbuf.h"
+
+using ca::DevBuf;
+
+struct ca_gcate {
+  int n, p, d, r, k, kpad, family;
+  double thres;
+  long ldp, ldn;
+  cudaStream_t st;
+  DevBuf<double> Yn, Ynt, nu, tys_row, tys_col, tys_total, sparsity;
+  DevBuf<double> A, B, Aprev, Bprev;
+  DevBuf<double> P1, P2, lam, alpha_gene;
+  int d1 = 0, r2 = 0, a = 0;
+  bool has_P1 = false, has_P2 = false, has_lam = false, has_alpha_gene = false;
+  DevBuf<uint8_t> gene_active, cell_active;
+  DevBuf<int> list_c, list_g, list_clip, counts;  // counts: [0] cells, [1] genes, [2] clip, [3] n_act_c, [4] n_act_g
+  DevBuf<double> ell_c, ell_g, ellfin_c, ellfin_g, Graw_c, Graw_g, g_c, g_g, f0_c, f0_g, ng_c, ng_g, W, scal;
+  DevBuf<unsigned long long> evals;  // [0] cell evals, [1] gene evals
+  int ldG = 64;
+  bool counts_loaded = false, factors_set = false;
+  // raw counts kept for the GLM / AIPW handles that share them
+  DevBuf<double> Yraw, Yraw_t;
+  bool raw_loaded = false;
+};

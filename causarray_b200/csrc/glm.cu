@@ -1,0 +1,656 @@
+// K4 / K5 / K6 of SURVEY.md section 2b: batched per-gene GLM fits by IRLS.
+//
+// Replaces the per-gene statsmodels fit driven from fit_glm
+// (causarray/gcate_glm.py:187-236) -- algorithm restated in oracle/glm.py:
+//   mu0 = (y + mean y)/2, eta0 = log mu0, dev0 = deviance(mu0)
+//   repeat: w = mu (Poisson) | mu/(1 + mu/nu) (NB);  z = eta + (y - mu)/mu - offset
+//           beta = argmin || sqrt(w) (z - X beta) ||   (normal equations, Cholesky)
+//           eta = X beta + offset; mu = exp(eta); dev = deviance(mu)
+//           stop when |dev - dev_prev| <= tol
+// plus the method-of-moments dispersion (gcate_glm.py:301-306) and signed
+// deviance residuals (statsmodels resid_deviance / nb_glm_fast.py:729-777).
+//
+// One warp owns one gene.  The shared design X streams through shared memory in
+// chunks of 128 cells (cp.async, double buffered) and is reused by the 8 genes
+// of the CTA.  Per 32 cells a lane evaluates eta/mu/w/z for ONE cell, then the
+// weighted Gram  X^T diag(w) X  is accumulated on the FP64 tensor cores: for a
+// 4-cell step the fragment X[cell = lane%4][col = lane/4 + 8t] is the B
+// operand as is and, multiplied by w[cell], the A operand (DMMA m8n8k4); only
+// the upper-triangular 8x8 tiles are kept.  A second kernel solves the
+// (Jacobi-equilibrated) normal equations with a warp-level Cholesky.
+#include <vector>
+#include <new>
+
+#include "../../include/causarray_b200.h"
+#include "common.cuh"
+#include "devbuf.h"
+#include "kernels.h"
+#include "glm_state.h"
+#include "gcate_state.h"
+
+namespace ca {
+
+constexpr int GLM_WARPS = 8;
+constexpr int GLM_THREADS = GLM_WARPS * 32;
+constexpr int GLM_CHUNK = 128;  // cells per staged chunk
+
+struct GlmPass {
+  const double* Yt;      // p x ldn raw counts, gene-major
+  long ldn;
+  int n, p;
+  const double* X;       // n x ldx (padded, ldx % 8 == 4)
+  int kx, ldx;
+  const double* offset;  // n or nullptr
+  const double* nu;      // p or nullptr
+  int family;
+  double thres;
+  const double* beta;    // p x kx
+  const double* ybar;    // p
+  const double* cst;     // p x 3 : sum y, sum y log y, sum (y+nu) log(y+nu)
+  double* dev;           // p : deviance at the current beta
+  double* dev_prev;      // p
+  int* status;           // p : 0 running, 1 converged, 2 numeric failure
+  int* n_iter;           // p
+  double* gram;          // p x kx x kx
+  double* rhs;           // p x kx
+  double* mu_t;          // p x ldn or nullptr (finalize)
+  int iter;              // 1-based index of the update this pass prepares
+  double tol;
+  int finalize;          // 1: only deviance (+ mu_t), no Gram
+  int* n_active;         // device counter of genes still running after this pass
+};
+
+template <int NT>
+__global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
+  extern __shared__ __align__(16) double smem[];
+  const int ldx = P.ldx, kx = P.kx;
+  double* Xs = smem;                               // 2 * GLM_CHUNK * ldx
+  double* betas = Xs + 2 * GLM_CHUNK * ldx;        // GLM_WARPS * ldx
+  double* offs = betas + GLM_WARPS * ldx;          // 2 * GLM_CHUNK
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int gene = blockIdx.x * GLM_WARPS + warp;
+  const bool gene_ok = gene < P.p;
+  bool active = gene_ok && (P.finalize ? true : (P.status[gene] == 0));
+  // CTA-wide early out when nothing to do
+  {
+    __shared__ int any;
+    if (tid == 0) any = 0;
+    __syncthreads();
+    if (active && lane == 0) atomicOr(&any, 1);
+    __syncthreads();
+    if (!any) return;
+  }
+  const bool first = (P.iter == 1) && !P.finalize;
+  double nu = 1.0;
+  bool pois = true;
+  if (gene_ok && P.family == CA_FAMILY_NB && P.nu) {
+    nu = P.nu[gene];
+    pois = nu > P.thres;
+  }
+  const double ybar = gene_ok ? P.ybar[gene] : 1.0;
+  for (int c = lane; c < ldx; c += 32) betas[warp * ldx + c] = (gene_ok && c < kx && !first) ? P.beta[(size_t)gene * kx + c] : 0.0;
+  const double* yrow = P.Yt + (size_t)(gene_ok ? gene : 0) * P.ldn;
+  double* murow = (P.mu_t && gene_ok) ? P.mu_t + (size_t)gene * P.ldn : nullptr;
+
+  constexpr int NTRI = NT * (NT + 1) / 2;
+  double acc[NTRI][2];
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double racc[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) racc[i] = 0.0;
+  double s_yeta = 0.0, s_mu = 0.0, s_log = 0.0;
+
+  const int nchunks = (P.n + GLM_CHUNK - 1) / GLM_CHUNK;
+  auto stage = [&](int c, int buf) {
+    const int c0 = c * GLM_CHUNK;
+    const int nvalid = min(GLM_CHUNK, P.n - c0);
+    const int nvec = nvalid * ldx / 2;
+    const double* src = P.X + (size_t)c0 * ldx;
+    double* dst = Xs + buf * GLM_CHUNK * ldx;
+    for (int i = tid; i < nvec; i += GLM_THREADS) cp_async16(dst + 2 * i, src + 2 * i);
+    for (int i = nvalid * ldx + tid; i < GLM_CHUNK * ldx; i += GLM_THREADS) dst[i] = 0.0;
+    for (int i = tid; i < GLM_CHUNK; i += GLM_THREADS)
+      offs[buf * GLM_CHUNK + i] = (P.offset && c0 + i < P.n) ? P.offset[c0 + i] : 0.0;
+  };
+  stage(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) {
+      stage(c + 1, (c + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (active) {
+      const double* Xc = Xs + (c & 1) * GLM_CHUNK * ldx;
+      const double* oc = offs + (c & 1) * GLM_CHUNK;
+      const double* bw = betas + warp * ldx;
+      for (int blk = 0; blk < GLM_CHUNK; blk += 32) {
+        const int cell = c * GLM_CHUNK + blk + lane;
+        const bool ok = cell < P.n;
+        if (c * GLM_CHUNK + blk >= P.n) break;
+        const double y = ok ? yrow[cell] : 0.0;
+        const double off = oc[blk + lane];
+        double eta, mu;
+        if (first) {
+          mu = 0.5 * (y + ybar);
+          eta = log(mu);
+        } else {
+          const double* xr = Xc + (blk + lane) * ldx;
+          double e = 0.0;
+          for (int q = 0; q < kx; ++q) e = fma(xr[q], bw[q], e);
+          eta = e + off;
+          mu = exp(eta);
+        }
+        double w = 0.0, wz = 0.0;
+        if (ok) {
+          s_yeta += y * eta;  // y * log(mu): eta IS log(mu) (iteration 1: log mu0 without offset)
+          s_mu += mu;
+          if (!pois) s_log += (y + nu) * log(mu + nu);
+          if (murow) murow[cell] = mu;
+          if (!P.finalize) {
+            w = pois ? mu : mu / (1.0 + mu / nu);
+            const double z = eta + (y - mu) / mu - off;
+            wz = w * z;
+          }
+        }
+        if (!P.finalize) {
+#pragma unroll
+          for (int s = 0; s < 8; ++s) {
+            const int src = s * 4 + lc;
+            const double ws = __shfl_sync(0xffffffffu, w, src);
+            const double wzs = __shfl_sync(0xffffffffu, wz, src);
+            const double* xp = Xc + (blk + src) * ldx + lr;
+            double xv[NT], av[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              xv[t] = xp[8 * t];
+              av[t] = ws * xv[t];
+              racc[t] = fma(wzs, xv[t], racc[t]);
+            }
+            int idx = 0;
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+              for (int nt = mt; nt < NT; ++nt) {
+                dmma884(acc[idx][0], acc[idx][1], av[mt], xv[nt]);
+                ++idx;
+              }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+  // ---- deviance at the current beta and convergence bookkeeping ----
+  s_yeta = warp_sum(s_yeta);
+  s_mu = warp_sum(s_mu);
+  s_log = warp_sum(s_log);
+  const double sy = P.cst[(size_t)gene * 3 + 0], sylogy = P.cst[(size_t)gene * 3 + 1], synu = P.cst[(size_t)gene * 3 + 2];
+  double dev;
+  if (pois)
+    dev = 2.0 * ((sylogy - s_yeta) - (sy - s_mu));
+  else
+    dev = 2.0 * ((sylogy - s_yeta) - (synu - s_log));
+  bool run = true;
+  if (lane == 0) {
+    if (P.finalize) {
+      P.dev[gene] = dev;
+    } else {
+      const double prev = P.dev_prev[gene];
+      P.dev[gene] = dev;
+      if (!(dev == dev) || isinf(dev)) {
+        P.status[gene] = 2;
+        P.n_iter[gene] = P.iter - 1;
+        run = false;
+      } else if (!first && fabs(dev - prev) <= P.tol) {
+        P.status[gene] = 1;
+        P.n_iter[gene] = P.iter - 1;
+        run = false;
+      } else {
+        P.dev_prev[gene] = dev;
+        atomicAdd(P.n_active, 1);
+      }
+    }
+  }
+  if (P.finalize) return;
+  run = __shfl_sync(0xffffffffu, run ? 1 : 0, 0) != 0;
+  if (!run) return;
+  // ---- write the Gram (upper tiles mirrored) and rhs ----
+  double* G = P.gram + (size_t)gene * kx * kx;
+  int idx = 0;
+#pragma unroll
+  for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+    for (int nt = mt; nt < NT; ++nt) {
+      const int m = 8 * mt + lr;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int nn = 8 * nt + 2 * lc + i;
+        if (m < kx && nn < kx) {
+          G[m * kx + nn] = acc[idx][i];
+          if (nt != mt) G[nn * kx + m] = acc[idx][i];
+        }
+      }
+      ++idx;
+    }
+  // rhs: lane holds partial over its cells (lc) for column lr + 8t -> reduce over lc
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    double v = racc[t];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    const int col = lr + 8 * t;
+    if (lc == 0 && col < kx) P.rhs[(size_t)gene * kx + col] = v;
+  }
+}
+
+// Warp-level Cholesky solve of the Jacobi-scaled normal equations, one gene per warp.
+__global__ void k_glm_solve(int p, int kx, const double* __restrict__ gram, const double* __restrict__ rhs,
+                            int* __restrict__ status, double* __restrict__ beta, int iter, int* __restrict__ n_iter) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = blockDim.x >> 5;
+  const int gene = blockIdx.x * nw + warp;
+  if (gene >= p) return;
+  if (status[gene] != 0) return;
+  const int ld = kx + 1;
+  double* L = sm + (size_t)warp * (kx * ld + 2 * kx);
+  double* sc = L + kx * ld;
+  double* b = sc + kx;
+  const double* G = gram + (size_t)gene * kx * kx;
+  for (int i = lane; i < kx; i += 32) {
+    const double dgn = G[i * kx + i];
+    sc[i] = dgn > 0.0 ? 1.0 / sqrt(dgn) : 0.0;
+  }
+  __syncwarp();
+  bool bad = false;
+  for (int e = lane; e < kx * kx; e += 32) {
+    const int i = e / kx, j = e % kx;
+    L[i * ld + j] = G[e] * sc[i] * sc[j];
+  }
+  for (int i = lane; i < kx; i += 32) {
+    b[i] = rhs[(size_t)gene * kx + i] * sc[i];
+    if (sc[i] == 0.0) bad = true;
+  }
+  __syncwarp();
+  // right-looking Cholesky, lower triangle
+  for (int j = 0; j < kx; ++j) {
+    const double djj = L[j * ld + j];
+    if (!(djj > 1e-13)) bad = true;
+    const double inv = 1.0 / sqrt(djj > 1e-300 ? djj : 1e-300);
+    __syncwarp();
+    for (int i = j + lane; i < kx; i += 32) L[i * ld + j] *= inv;
+    __syncwarp();
+    for (int e = lane; e < (kx - j - 1) * (kx - j - 1); e += 32) {
+      const int i = j + 1 + e / (kx - j - 1), c = j + 1 + e % (kx - j - 1);
+      if (c <= i) L[i * ld + c] -= L[i * ld + j] * L[c * ld + j];
+    }
+    __syncwarp();
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad) {
+    if (lane == 0) {
+      status[gene] = 2;
+      n_iter[gene] = iter;
+    }
+    return;
+  }
+  // forward / backward substitution (lane 0; kx <= 64)
+  if (lane == 0) {
+    for (int i = 0; i < kx; ++i) {
+      double s = b[i];
+      for (int c = 0; c < i; ++c) s -= L[i * ld + c] * b[c];
+      b[i] = s / L[i * ld + i];
+    }
+    for (int i = kx - 1; i >= 0; --i) {
+      double s = b[i];
+      for (int c = i + 1; c < kx; ++c) s -= L[c * ld + i] * b[c];
+      b[i] = s / L[i * ld + i];
+    }
+    bool fin = true;
+    for (int i = 0; i < kx; ++i) {
+      const double v = b[i] * sc[i];
+      beta[(size_t)gene * kx + i] = v;
+      fin = fin && (v == v) && !isinf(v);
+    }
+    if (!fin) {
+      status[gene] = 2;
+      n_iter[gene] = iter;
+    }
+  }
+}
+
+// per-gene constants: mean y, sum y, sum y log y, sum (y+nu) log(y+nu)
+__global__ void k_glm_consts(const double* __restrict__ Yt, long ldn, int n, const double* __restrict__ nu,
+                             int family, double thres, double* __restrict__ ybar, double* __restrict__ cst) {
+  __shared__ double scratch[32];
+  const int gene = blockIdx.x;
+  const double* y = Yt + (size_t)gene * ldn;
+  const bool nb = family == CA_FAMILY_NB && nu && !(nu[gene] > thres);
+  const double nuj = nb ? nu[gene] : 1.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = y[i];
+    s0 += v;
+    if (v > 0.0) s1 += v * log(v);
+    if (nb) s2 += (v + nuj) * log(v + nuj);
+  }
+  s0 = block_sum(s0, scratch);
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  if (threadIdx.x == 0) {
+    ybar[gene] = s0 / (double)n;
+    cst[(size_t)gene * 3 + 0] = s0;
+    cst[(size_t)gene * 3 + 1] = s1;
+    cst[(size_t)gene * 3 + 2] = s2;
+  }
+}
+
+// guards of causarray/gcate_glm.py:205
+__global__ void k_glm_guard(int p, int kx, int d_guard, const double* __restrict__ beta, int* __restrict__ status) {
+  const int gene = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gene >= p) return;
+  if (status[gene] == 2) return;
+  bool bad = false;
+  for (int c = 0; c < kx; ++c) {
+    const double v = beta[(size_t)gene * kx + c];
+    if (!(v == v) || isinf(v)) bad = true;
+    if (c < d_guard ? fabs(v) > 50.0 : fabs(v) > 10.0) bad = true;
+  }
+  status[gene] = bad ? 3 : status[gene];
+}
+
+// signed deviance residuals, written cell-major (n x p) through a tiled transpose
+__global__ void k_glm_resid(const double* __restrict__ Yt, const double* __restrict__ mu_t, long ldn, int n, int p,
+                            const double* __restrict__ nu, int family, double thres, const int* __restrict__ status,
+                            double* __restrict__ out, long ldo) {
+  __shared__ double tile[32][33];
+  const int g0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const int gene = g0 + rr, cell = i0 + threadIdx.x;
+    double v = 0.0;
+    if (gene < p && cell < n && (status == nullptr || status[gene] <= 1)) {
+      const double y = Yt[(size_t)gene * ldn + cell], mu = mu_t[(size_t)gene * ldn + cell];
+      const bool nb = family == CA_FAMILY_NB && nu && !(nu[gene] > thres);
+      const double r = fmax(y / mu, 2.220446049250313e-16);
+      double dd = y * log(r);
+      if (nb) {
+        const double ia = nu[gene];
+        dd -= (y + ia) * log((y + ia) / (mu + ia));
+      } else {
+        dd -= (y - mu);
+      }
+      dd *= 2.0;
+      const double sg = (y > mu) ? 1.0 : ((y < mu) ? -1.0 : 0.0);
+      v = sg * sqrt(fmax(dd, 0.0));
+    }
+    tile[rr][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const int cell = i0 + rr, gene = g0 + threadIdx.x;
+    if (cell < n && gene < p) out[(size_t)cell * ldo + gene] = tile[threadIdx.x][rr];
+  }
+}
+
+// method-of-moments NB size (gcate_glm.py:301-306), one CTA per gene
+__global__ void k_disp_moments(const double* __restrict__ Yt, const double* __restrict__ mu_t, long ldn, int n,
+                               const double* __restrict__ offset, double* __restrict__ disp) {
+  __shared__ double scratch[32];
+  const int gene = blockIdx.x;
+  const double* y = Yt + (size_t)gene * ldn;
+  const double* m = mu_t + (size_t)gene * ldn;
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double sf = offset ? exp(offset[i]) : 1.0;
+    mx = fmax(mx, y[i] / sf);
+  }
+  // block max through the sum helper: use shuffles
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, scratch[w]);
+  __syncthreads();
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double sf = offset ? exp(offset[i]) : 1.0;
+    const double yn = y[i] / sf;
+    const double yh = fmin(fmax(m[i] / sf, 0.0), mx);
+    const double dlt = yn - yh;
+    s1 += dlt * dlt - yh;
+    s2 += yh * yh;
+  }
+  s1 = block_sum(s1, scratch);
+  s2 = block_sum(s2, scratch);
+  if (threadIdx.x == 0) {
+    const double phi = (s1 / (double)n) / (s2 / (double)n);
+    double v = 1.0 / fmin(fmax(phi, 0.01), 100.0);
+    if (!(phi == phi)) v = 1.0;
+    disp[gene] = v;
+  }
+}
+
+template <int NT>
+static int launch_pass_nt(const GlmPass& P, cudaStream_t st) {
+  const size_t sm = sizeof(double) * ((size_t)2 * GLM_CHUNK * P.ldx + GLM_WARPS * P.ldx + 2 * GLM_CHUNK);
+  CA_CUDA(cudaFuncSetAttribute(k_glm_pass<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  const int grid = (P.p + GLM_WARPS - 1) / GLM_WARPS;
+  k_glm_pass<NT><<<grid, GLM_THREADS, sm, st>>>(P);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_pass(const GlmPass& P, cudaStream_t st) {
+  const int nt = (P.kx + 7) / 8;
+  switch (nt) {
+    case 1: return launch_pass_nt<1>(P, st);
+    case 2: return launch_pass_nt<2>(P, st);
+    case 3: return launch_pass_nt<3>(P, st);
+    case 4: return launch_pass_nt<4>(P, st);
+    case 5: return launch_pass_nt<5>(P, st);
+    case 6: return launch_pass_nt<6>(P, st);
+    case 7: return launch_pass_nt<7>(P, st);
+    case 8: return launch_pass_nt<8>(P, st);
+  }
+  set_error("design wider than 64 columns");
+  return -2;
+}
+
+int kpad_for(int k);
+
+}  // namespace ca
+
+using namespace ca;
+
+extern "C" int ca_glm_create(ca_glm_t* out, int n, int p) {
+  CA_REQUIRE(out && n > 0 && p > 0, "bad dimensions");
+  ca_glm* h = new (std::nothrow) ca_glm();
+  CA_REQUIRE(h, "out of host memory");
+  h->n = n;
+  h->p = p;
+  h->ldn = round_up(n, 8);
+  h->st = 0;
+  *out = h;
+  return 0;
+}
+
+extern "C" int ca_glm_destroy(ca_glm_t h) {
+  if (h) {
+    cudaStreamSynchronize(h->st);
+    delete h;
+  }
+  return 0;
+}
+
+extern "C" int ca_glm_load_counts(ca_glm_t h, const double* Y) {
+  CA_REQUIRE(h && Y, "null argument");
+  const int n = h->n, p = h->p;
+  if (h->Yraw_own.alloc((size_t)n * p) || h->Yt_own.alloc((size_t)p * h->ldn)) return -1;
+  CA_CUDA(cudaMemcpyAsync(h->Yraw_own.ptr, Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaMemsetAsync(h->Yt_own.ptr, 0, h->Yt_own.bytes(), h->st));
+  if (launch_transpose(h->Yraw_own.ptr, n, p, p, h->Yt_own.ptr, h->ldn, h->st)) return -1;
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  h->Yraw = h->Yraw_own.ptr;
+  h->Yt = h->Yt_own.ptr;
+  return 0;
+}
+
+extern "C" int ca_glm_share_counts(ca_glm_t h, ca_gcate_t g) {
+  CA_REQUIRE(h && g && g->raw_loaded, "GCATE handle holds no raw counts");
+  CA_REQUIRE(h->n == g->n && h->p == g->p, "shape mismatch");
+  h->Yraw = g->Yraw.ptr;
+  h->Yt = g->Yraw_t.ptr;
+  h->ldn = g->ldn;
+  return 0;
+}
+
+extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                          double thres_disp, int maxiter, double tol, int d_guard, double* B, double* dev,
+                          int32_t* n_iter, int32_t* status) {
+  CA_REQUIRE(h && h->Yt && X && B, "load counts first");
+  CA_REQUIRE(kx > 0 && kx <= 64, "design width must be in [1, 64]");
+  CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
+  const int n = h->n, p = h->p;
+  cudaStream_t st = h->st;
+  const int ldx = kpad_for(kx);
+  if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
+      h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
+      h->gram.alloc((size_t)p * kx * kx) || h->rhs.alloc((size_t)p * kx) || h->mu_t.alloc((size_t)p * h->ldn) ||
+      h->counter.alloc(1) || h->offset.alloc(n) || h->nu.alloc(p))
+    return -1;
+  CA_CUDA(cudaMemsetAsync(h->X.ptr, 0, h->X.bytes(), st));
+  CA_CUDA(cudaMemcpy2DAsync(h->X.ptr, sizeof(double) * ldx, X, sizeof(double) * kx, sizeof(double) * kx, n,
+                            cudaMemcpyHostToDevice, st));
+  if (offset) CA_CUDA(cudaMemcpyAsync(h->offset.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (nu) CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu, sizeof(double) * p, cudaMemcpyHostToDevice, st));
+  CA_CUDA(cudaMemsetAsync(h->beta.ptr, 0, h->beta.bytes(), st));
+  CA_CUDA(cudaMemsetAsync(h->status.ptr, 0, h->status.bytes(), st));
+  CA_CUDA(cudaMemsetAsync(h->n_iter.ptr, 0, h->n_iter.bytes(), st));
+  CA_CUDA(cudaMemsetAsync(h->dev_prev.ptr, 0, h->dev_prev.bytes(), st));
+  h->has_offset = offset != nullptr;
+  h->family = family;
+  h->thres = thres_disp;
+  h->has_nu = (nu != nullptr) && family == CA_FAMILY_NB;
+  k_glm_consts<<<p, 256, 0, st>>>(h->Yt, h->ldn, n, h->has_nu ? h->nu.ptr : nullptr, family, thres_disp, h->ybar.ptr,
+                                  h->cst.ptr);
+  CA_LAUNCH_CHECK();
+  GlmPass P;
+  P.Yt = h->Yt;
+  P.ldn = h->ldn;
+  P.n = n;
+  P.p = p;
+  P.X = h->X.ptr;
+  P.kx = kx;
+  P.ldx = ldx;
+  P.offset = offset ? h->offset.ptr : nullptr;
+  P.nu = h->has_nu ? h->nu.ptr : nullptr;
+  P.family = family;
+  P.thres = thres_disp;
+  P.beta = h->beta.ptr;
+  P.ybar = h->ybar.ptr;
+  P.cst = h->cst.ptr;
+  P.dev = h->dev.ptr;
+  P.dev_prev = h->dev_prev.ptr;
+  P.status = h->status.ptr;
+  P.n_iter = h->n_iter.ptr;
+  P.gram = h->gram.ptr;
+  P.rhs = h->rhs.ptr;
+  P.mu_t = nullptr;
+  P.tol = tol;
+  P.finalize = 0;
+  P.n_active = h->counter.ptr;
+  const int solve_warps = 4;
+  const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 2 * kx);
+  CA_CUDA(cudaFuncSetAttribute(k_glm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_sm));
+  int iters_done = 0;
+  for (int it = 1; it <= maxiter; ++it) {
+    // pass `it` evaluates the deviance after update it-1 (convergence test of that update)
+    // and, for genes still running, accumulates the normal equations of update `it`
+    CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int), st));
+    P.iter = it;
+    if (launch_pass(P, st)) return -1;
+    int nact = 0;
+    CA_CUDA(cudaMemcpyAsync(&nact, h->counter.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    if (nact == 0) break;
+    k_glm_solve<<<(p + solve_warps - 1) / solve_warps, solve_warps * 32, solve_sm, st>>>(
+        p, kx, h->gram.ptr, h->rhs.ptr, h->status.ptr, h->beta.ptr, it, h->n_iter.ptr);
+    CA_LAUNCH_CHECK();
+    iters_done = it;
+  }
+  // finalize: fitted means + deviance at the final beta for every gene
+  P.finalize = 1;
+  P.iter = iters_done + 1;
+  P.mu_t = h->mu_t.ptr;
+  if (iters_done == 0) P.iter = 2;  // never "first" in finalize
+  if (launch_pass(P, st)) return -1;
+  h->iters_done = iters_done;
+  // genes still "running" after maxiter updates: n_iter = maxiter
+  k_glm_guard<<<(p + 127) / 128, 128, 0, st>>>(p, kx, d_guard, h->beta.ptr, h->status.ptr);
+  CA_LAUNCH_CHECK();
+  std::vector<int> hs(p), hi(p);
+  CA_CUDA(cudaMemcpyAsync(B, h->beta.ptr, sizeof(double) * (size_t)p * kx, cudaMemcpyDeviceToHost, st));
+  if (dev) CA_CUDA(cudaMemcpyAsync(dev, h->dev.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaMemcpyAsync(hs.data(), h->status.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaMemcpyAsync(hi.data(), h->n_iter.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < p; ++j) {
+    int s = hs[j];
+    int it = hi[j];
+    if (s == 0) it = iters_done;  // hit maxiter without meeting the tolerance
+    // report: 0 ok (converged or maxiter), 1 guard tripped, 2 numeric failure
+    int rep = (s == 3) ? 1 : (s == 2 ? 2 : 0);
+    if (status) status[j] = rep;
+    if (n_iter) n_iter[j] = it;
+  }
+  return 0;
+}
+
+extern "C" int ca_glm_resid(ca_glm_t h, double* resid) {
+  CA_REQUIRE(h && h->mu_t.ptr && resid, "fit first");
+  const int n = h->n, p = h->p;
+  DevBuf<double> out;
+  if (out.alloc((size_t)n * p)) return -1;
+  dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+  k_glm_resid<<<grid, block, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, p, h->has_nu ? h->nu.ptr : nullptr, h->family,
+                                         h->thres, h->status.ptr, out.ptr, p);
+  CA_LAUNCH_CHECK();
+  CA_CUDA(cudaMemcpyAsync(resid, out.ptr, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_glm_fitted(ca_glm_t h, double* mu) {
+  CA_REQUIRE(h && h->mu_t.ptr && mu, "fit first");
+  const int n = h->n, p = h->p;
+  DevBuf<double> out;
+  if (out.alloc((size_t)n * p)) return -1;
+  if (launch_transpose(h->mu_t.ptr, p, n, h->ldn, out.ptr, p, h->st)) return -1;
+  CA_CUDA(cudaMemcpyAsync(mu, out.ptr, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_glm_disp_moments(ca_glm_t h, const double* offset, double* disp) {
+  CA_REQUIRE(h && h->mu_t.ptr && disp, "fit first");
+  const int n = h->n, p = h->p;
+  DevBuf<double> off, out;
+  if (out.alloc(p)) return -1;
+  if (offset) {
+    if (off.alloc(n)) return -1;
+    CA_CUDA(cudaMemcpyAsync(off.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
+  }
+  k_disp_moments<<<p, 256, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, offset ? off.ptr : nullptr, out.ptr);
+  CA_LAUNCH_CHECK();
+  CA_CUDA(cudaMemcpyAsync(disp, out.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}

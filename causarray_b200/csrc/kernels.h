@@ -1,0 +1,99 @@
+// Internal launcher interface between the translation units of
+// libcausarray_b200.  Everything here takes DEVICE pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ca {
+
+// A "row problem": rows of Y (cells for the A-step, genes for the B-step)
+// against the fixed factor M (ncols x kpad).
+struct RowProblem {
+  const double* Y;   // nrows x ldY, row-major
+  long ldY;          // multiple of 8
+  int ncols;
+  const double* M;   // ncols x kpad
+  int kpad;          // kpad % 8 == 4
+  const double* nu;  // per column (nu_per_row = 0) or per row (nu_per_row = 1)
+  int nu_per_row;
+  int family;
+  double thres_disp;
+};
+
+struct SearchLaunch {
+  double* X;            // rows x kpad, updated in place
+  const double* g;      // rows x kpad
+  const double* f0;
+  const double* normg;
+  const double* tys;
+  const double* lam;    // rows x ldlam or nullptr
+  int ldlam;
+  int prox_lo, prox_hi;
+  const double* alpha_row;
+  double alpha, beta, tol;
+  int max_iters;
+  const int* rowlist;
+  const int* count;
+  int nrows;            // launch bound on the number of rows
+  double* ell_fin;
+  int* neval;
+  unsigned long long* eval_total;  // optional device counter of candidate evaluations
+};
+
+int launch_rowpass(const RowProblem& rp, const double* X, const int* rowlist, const int* count, int nrows,
+                   bool want_grad, int gc_lo, int gc_n, double* ell_out, double* G_out, int ldG,
+                   cudaStream_t st);
+int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st);
+
+// ---- altmin_aux.cu ----
+int launch_normalize_transpose(const double* Yraw, int n, int p, long ld_in, const double* size_factor,
+                               double* Yn, long ldYn, double* Ynt, long ldYnt, cudaStream_t st);
+int launch_transpose(const double* src, int rows, int cols, long ld_in, double* dst, long ld_out, cudaStream_t st);
+int launch_tys_rowsum(const double* Yr, long ldY, int nrows, int ncols, const double* nu, int nu_per_row,
+                      int family, double thres, double* out, cudaStream_t st);
+int launch_rowsum(const double* M, long ld, int nrows, int ncols, double* out, cudaStream_t st);
+int launch_zero_fraction(const double* Yr, long ldY, int nrows, int ncols, double* out, cudaStream_t st);
+int launch_sum(const double* v, int n, double* out, cudaStream_t st);
+int launch_div_scalar(double* v, long n, double denom, cudaStream_t st);
+// W (cp x cv) = P^T V ; P rows x cp (ldP), V rows x cv (ldV)
+int launch_pt_v(const double* P, int ldP, int cp, const double* V, int ldV, int cv, int rows, double* W,
+                cudaStream_t st);
+// V -= P W
+int launch_sub_p_w(const double* P, int ldP, int cp, double* V, int ldV, int cv, int rows, const double* W,
+                   cudaStream_t st);
+
+struct PrepArgs {
+  int nrows;
+  const int* rowlist;
+  const int* count;
+  int kpad, ncols;
+  const double* G;   // scaled gradient block, rows x ldG, columns map to [gc_lo, gc_lo + gc_n)
+  int ldG, gc_lo, gc_n;
+  int ball_lo, ball_hi;
+  double radius;
+  const double* X;     // rows x kpad
+  const double* lam;   // rows x ldlam or nullptr
+  int ldlam, prox_lo, prox_hi;
+  const double* ell0;
+  const double* tys;
+  double* g;           // rows x kpad (out)
+  double* f0;
+  double* normg;
+};
+int launch_prep_search(const PrepArgs& a, cudaStream_t st);
+
+int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream_t st);
+// clip X[:, lo:hi) to [-bound, bound]; rows where something changed are appended to list/count
+int launch_clip(double* X, int rows, int kpad, int lo, int hi, double bound, int* list, int* count, cudaStream_t st);
+// mask[i] = || X[i, lo:hi) - Xprev[i, lo:hi) ||_2 > tol ; n_active written to count
+int launch_step_mask(const double* X, const double* Xprev, int rows, int kpad, int lo, int hi, double tol,
+                     uint8_t* mask, int* count, cudaStream_t st);
+int launch_fill_u8(uint8_t* v, int n, uint8_t val, cudaStream_t st);
+// out = sum_{i, c in [lo,hi)} |X[i,c]| * lam[i*ldlam + c-lo]
+int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const double* lam, int ldlam,
+                      double* out, cudaStream_t st);
+// lam[i, c] = lam0 / (|X[i, lo + c]| + 1e-6)
+int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi, double lam0, double* lam,
+                            int ldlam, cudaStream_t st);
+
+}  // namespace ca

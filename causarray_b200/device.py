@@ -1,0 +1,225 @@
+"""Thin object wrappers over the C-ABI handles (host numpy arrays in / out)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+
+class GcateDevice:
+    """Device-resident GCATE problem (``ca_gcate_t``): S1 seam of SURVEY.md section 8b."""
+
+    def __init__(self, n, p, d, r, family, thres_disp=100.0):
+        if family not in L.FAMILY:
+            raise ValueError('Family not recognized')
+        self.lib = L.load()
+        self.n, self.p, self.d, self.r, self.k = int(n), int(p), int(d), int(r), int(d + r)
+        self.family = family
+        self.h = ctypes.c_void_p()
+        L.check(self.lib.ca_gcate_create(ctypes.byref(self.h), self.n, self.p, self.d, self.r,
+                                         L.FAMILY[family], float(thres_disp)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.ca_gcate_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_counts(self, Y, size_factor=None, nu=None):
+        Y = L.f64(Y)
+        assert Y.shape == (self.n, self.p)
+        sf = None if size_factor is None else L.f64(np.ravel(size_factor))
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        L.check(self.lib.ca_gcate_load_counts(self.h, L.dptr(Y), L.dptr(sf), L.dptr(nu)))
+
+    def load_normalized(self, Yn, Ys=None, nu=None):
+        Yn = L.f64(Yn)
+        Ys = None if Ys is None else L.f64(Ys)
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        L.check(self.lib.ca_gcate_load_normalized(self.h, L.dptr(Yn), L.dptr(Ys), L.dptr(nu)))
+
+    def set_factors(self, A=None, B=None):
+        A = None if A is None else L.f64(A)
+        B = None if B is None else L.f64(B)
+        if A is not None:
+            assert A.shape == (self.n, self.k)
+        if B is not None:
+            assert B.shape == (self.p, self.k)
+        L.check(self.lib.ca_gcate_set_factors(self.h, L.dptr(A), L.dptr(B)))
+
+    def get_factors(self):
+        A = np.empty((self.n, self.k))
+        B = np.empty((self.p, self.k))
+        L.check(self.lib.ca_gcate_get_factors(self.h, L.dptr(A), L.dptr(B)))
+        return A, B
+
+    def set_stage(self, P1=None, P2=None, lam=None, a=0):
+        P1 = None if P1 is None else L.f64(P1)
+        P2 = None if P2 is None else L.f64(P2)
+        lam = None if lam is None else L.f64(lam)
+        if lam is not None:
+            assert lam.shape == (self.p, a)
+        L.check(self.lib.ca_gcate_set_stage(self.h, L.dptr(P1), 0 if P1 is None else P1.shape[1],
+                                            L.dptr(P2), 0 if P2 is None else P2.shape[1], L.dptr(lam), int(a)))
+
+    def set_masks(self, gene_active=None, cell_active=None, alpha_gene=None):
+        ga = None if gene_active is None else np.ascontiguousarray(gene_active, dtype=np.uint8)
+        ca = None if cell_active is None else np.ascontiguousarray(cell_active, dtype=np.uint8)
+        ag = None if alpha_gene is None else L.f64(alpha_gene)
+        L.check(self.lib.ca_gcate_set_masks(self.h, L.u8ptr(ga), L.u8ptr(ca), L.dptr(ag)))
+
+    def get_masks(self):
+        ga = np.empty(self.p, dtype=np.uint8)
+        ca = np.empty(self.n, dtype=np.uint8)
+        L.check(self.lib.ca_gcate_get_masks(self.h, L.u8ptr(ga), L.u8ptr(ca)))
+        return ga.astype(bool), ca.astype(bool)
+
+    def update(self, C, alpha, beta, max_iters, tol):
+        f = ctypes.c_double(0.0)
+        L.check(self.lib.ca_gcate_update(self.h, float(C), float(alpha), float(beta), int(max_iters), float(tol),
+                                         ctypes.byref(f)))
+        return f.value
+
+    def nll(self):
+        f = ctypes.c_double(0.0)
+        L.check(self.lib.ca_gcate_nll(self.h, ctypes.byref(f)))
+        return f.value
+
+    def grad(self, wrt_A):
+        out = np.empty((self.n if wrt_A else self.p, self.k))
+        L.check(self.lib.ca_gcate_grad(self.h, 1 if wrt_A else 0, L.dptr(out)))
+        return out
+
+    def alter_min(self, kwargs_ls, kwargs_es, lam, a):
+        prm = L.AltminParams(
+            alpha=kwargs_ls['alpha'], beta=kwargs_ls['beta'], tol=kwargs_ls['tol'], C=kwargs_ls['C'],
+            ls_max_iters=int(kwargs_ls['max_iters']), tol_gene=kwargs_ls['tol_gene'], tol_cell=kwargs_ls['tol_cell'],
+            recheck_interval=int(kwargs_ls['recheck_interval']), sparsity_threshold=kwargs_ls['sparsity_threshold'],
+            sparsity_boost=kwargs_ls['sparsity_boost'], warmup_iters=int(kwargs_ls['warmup_iters']),
+            es_max_iters=int(kwargs_es['max_iters']), es_warmup=int(kwargs_es['warmup']),
+            es_patience=int(kwargs_es['patience']), es_tolerance=kwargs_es['tolerance'],
+            es_rel_tol=kwargs_es['rel_tol'], lam=float(lam), a=int(a))
+        res = L.AltminResult()
+        hist = np.zeros(int(kwargs_es['max_iters']) + 1)
+        L.check(self.lib.ca_gcate_alter_min(self.h, ctypes.byref(prm), ctypes.byref(res), L.dptr(hist)))
+        return res, hist[:res.hist_len].copy()
+
+
+class GlmDevice:
+    """Batched per-gene GLM fits (``ca_glm_t``): S2 seam."""
+
+    def __init__(self, n, p):
+        self.lib = L.load()
+        self.n, self.p = int(n), int(p)
+        self.h = ctypes.c_void_p()
+        L.check(self.lib.ca_glm_create(ctypes.byref(self.h), self.n, self.p))
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.ca_glm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_counts(self, Y):
+        Y = L.f64(Y)
+        assert Y.shape == (self.n, self.p)
+        L.check(self.lib.ca_glm_load_counts(self.h, L.dptr(Y)))
+
+    def share_counts(self, gcate):
+        self._keep = gcate  # the GCATE handle owns the device copy
+        L.check(self.lib.ca_glm_share_counts(self.h, gcate.h))
+
+    def fit(self, family, X, offset=None, nu=None, thres_disp=100.0, maxiter=100, tol=1e-8, d_guard=None):
+        if family not in L.FAMILY:
+            raise ValueError('Family not recognized')
+        X = L.f64(X)
+        kx = X.shape[1]
+        off = None if offset is None else L.f64(np.ravel(offset))
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        B = np.zeros((self.p, kx))
+        dev = np.zeros(self.p)
+        n_iter = np.zeros(self.p, dtype=np.int32)
+        status = np.zeros(self.p, dtype=np.int32)
+        L.check(self.lib.ca_glm_fit(self.h, L.FAMILY[family], L.dptr(X), kx, L.dptr(off), L.dptr(nu),
+                                    float(thres_disp), int(maxiter), float(tol), int(kx if d_guard is None else d_guard),
+                                    L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
+        return B, dev, n_iter, status
+
+    def resid(self):
+        out = np.empty((self.n, self.p))
+        L.check(self.lib.ca_glm_resid(self.h, L.dptr(out)))
+        return out
+
+    def fitted(self):
+        out = np.empty((self.n, self.p))
+        L.check(self.lib.ca_glm_fitted(self.h, L.dptr(out)))
+        return out
+
+    def disp_moments(self, offset=None):
+        off = None if offset is None else L.f64(np.ravel(offset))
+        out = np.empty(self.p)
+        L.check(self.lib.ca_glm_disp_moments(self.h, L.dptr(off), L.dptr(out)))
+        return out
+
+
+def _lfc_params(usevar, thres_min, thres_diff, eps_var, yhat_cap=1e5):
+    if usevar not in ('pooled', 'unequal'):
+        raise ValueError('usevar must be either "pooled" or "unequal"')
+    return L.LfcParams(usevar=1 if usevar == 'unequal' else 0, thres_min=float(thres_min),
+                       thres_diff=float(thres_diff), eps_var=float(eps_var), yhat_cap=float(yhat_cap))
+
+
+def _lfc_outputs(a, p):
+    outs = [np.empty((a, p)) for _ in range(5)]
+    est = np.empty((a, p), dtype=np.uint8)
+    return outs, est
+
+
+def aipw_lfc(Y, W, Bcov, Btrt, offset, size_factor, A, pi, cell_mask=None, usevar='unequal', thres_min=1e-2,
+             thres_diff=1e-2, eps_var=1e-4, glm=None):
+    """Fused AIPW + LFC estimand (S3 seam).  Returns dict of (a, p) arrays."""
+    lib = L.load()
+    W, Bcov, Btrt, A, pi = L.f64(W), L.f64(Bcov), L.f64(Btrt), L.f64(A), L.f64(pi)
+    n, kw = W.shape
+    p, a = Btrt.shape
+    off = None if offset is None else L.f64(np.ravel(offset))
+    sf = L.f64(np.ravel(size_factor))
+    cm = None if cell_mask is None else np.ascontiguousarray(cell_mask, dtype=np.uint8)
+    prm = _lfc_params(usevar, thres_min, thres_diff, eps_var)
+    outs, est = _lfc_outputs(a, p)
+    tail = [L.u8ptr(cm), ctypes.byref(prm)] + [L.dptr(o) for o in outs] + [L.u8ptr(est)]
+    if glm is not None:
+        L.check(lib.ca_aipw_lfc_shared(glm.h, kw, a, L.dptr(W), L.dptr(Bcov), L.dptr(Btrt), L.dptr(off), L.dptr(sf),
+                                       L.dptr(A), L.dptr(pi), *tail))
+    else:
+        Y = L.f64(Y)
+        L.check(lib.ca_aipw_lfc(n, p, kw, a, L.dptr(Y), L.dptr(W), L.dptr(Bcov), L.dptr(Btrt), L.dptr(off),
+                                L.dptr(sf), L.dptr(A), L.dptr(pi), *tail))
+    return dict(mean0=outs[0], mean1=outs[1], tau=outs[2], var=outs[3], df=outs[4], estimable=est.astype(bool))
+
+
+def aipw_lfc_yhat(Y, Y_hat, size_factor, A, pi, cell_mask=None, usevar='unequal', thres_min=1e-2, thres_diff=1e-2,
+                  eps_var=1e-4):
+    lib = L.load()
+    Y, Y_hat, A, pi = L.f64(Y), L.f64(Y_hat), L.f64(A), L.f64(pi)
+    n, p = Y.shape
+    a = A.shape[1]
+    assert Y_hat.shape == (n, p, a, 2)
+    sf = L.f64(np.ravel(size_factor))
+    cm = None if cell_mask is None else np.ascontiguousarray(cell_mask, dtype=np.uint8)
+    prm = _lfc_params(usevar, thres_min, thres_diff, eps_var)
+    outs, est = _lfc_outputs(a, p)
+    L.check(lib.ca_aipw_lfc_yhat(n, p, a, L.dptr(Y), L.dptr(Y_hat), L.dptr(sf), L.dptr(A), L.dptr(pi), L.u8ptr(cm),
+                                 ctypes.byref(prm), *[L.dptr(o) for o in outs], L.u8ptr(est)))
+    return dict(mean0=outs[0], mean1=outs[1], tau=outs[2], var=outs[3], df=outs[4], estimable=est.astype(bool))

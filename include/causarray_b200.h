@@ -1,0 +1,177 @@
+/* causarray_b200 -- C ABI of the B200-native GCATE + doubly-robust LFC hot path.
+ *
+ * The reference (jaydu1/causarray) is pure Python and has no FFI of its own;
+ * its three Python-level seams are what these entry points
+ * replace.  Every function returns 0 on success and a negative code on error
+ * (-1 CUDA error, -2 invalid argument); ca_last_error() returns the message.
+ * No function throws, none is re-entrant on the same handle (like the
+ * reference's numba kernels, which are called from one Python thread).
+ *
+ * Unless a parameter is documented as a device pointer, pointers are HOST
+ * pointers to C-contiguous arrays; the library owns all device memory.
+ */
+#ifndef CAUSARRAY_B200_H
+#define CAUSARRAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CA_FAMILY_POISSON 0
+#define CA_FAMILY_NB 1
+
+int ca_version(void);
+const char* ca_last_error(void);
+int ca_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
+int ca_set_device(int device);
+
+/* ------------------------------------------------------------------------
+ * S1 -- optimiser seam.  Replaces causarray/gcate_opt.py:148-206
+ * (update_with_mask), :89-145 (update), :209-458 (alter_min loop) and the
+ * numba kernels they call: nll / grad (causarray/gcate_likelihood.py:46-142),
+ * line_search (causarray/gcate_opt.py:30-82), project_norm_ball (:10-26).
+ * ------------------------------------------------------------------------ */
+typedef struct ca_gcate* ca_gcate_t;
+
+/* n cells, p genes, d observed columns ([X | A], causarray/gcate.py:121),
+ * r latent factors; family CA_FAMILY_*; thres_disp as gcate_opt.py:212. */
+int ca_gcate_create(ca_gcate_t* out, int n, int p, int d, int r, int family, double thres_disp);
+int ca_gcate_destroy(ca_gcate_t h);
+
+/* Raw counts Y (n x p), size factors (n) or NULL (= ones), NB sizes nu (p) or
+ * NULL (= ones).  Computes Y / size_factor and the constant
+ * Tys = -lgamma(Y+1) [+ lgamma(nu+Y) - lgamma(nu)] sums on the device
+ * (causarray/gcate_opt.py:343-347) and the per-gene zero fraction (:305). */
+int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu);
+/* Same, for callers of update_with_mask that already hold the normalised Y
+ * and the Ys matrix (both n x p); Ys may be NULL (recomputed from nu). */
+int ca_gcate_load_normalized(ca_gcate_t h, const double* Yn, const double* Ys, const double* nu);
+
+/* A (n x (d+r)), B (p x (d+r)) */
+int ca_gcate_set_factors(ca_gcate_t h, const double* A, const double* B);
+int ca_gcate_get_factors(ca_gcate_t h, double* A, double* B);
+
+/* Stage configuration.  P1: thin Q of [X | A] (n x d1) or NULL; P2: thin Q of
+ * Gamma-hat (p x r2) or NULL; lam: L1 thresholds (p x a) or NULL (= 0);
+ * a: number of penalised columns (the block [d-a, d)). */
+int ca_gcate_set_stage(ca_gcate_t h, const double* P1, int d1, const double* P2, int r2, const double* lam, int a);
+/* gene_active (p), cell_active (n) as uint8 or NULL (= all active);
+ * alpha_gene (p) or NULL (= alpha of the call). */
+int ca_gcate_set_masks(ca_gcate_t h, const uint8_t* gene_active, const uint8_t* cell_active,
+                       const double* alpha_gene);
+int ca_gcate_get_masks(ca_gcate_t h, uint8_t* gene_active, uint8_t* cell_active);
+
+/* One alternating iteration == update_with_mask(...) ; A and B are updated on
+ * the device (fetch with ca_gcate_get_factors).  func_val = nll(Y, A, B). */
+int ca_gcate_update(ca_gcate_t h, double C, double alpha, double beta, int max_iters, double tol,
+                    double* func_val);
+
+/* nll(Y, A, B) with the current factors (gcate_likelihood.py:46-94). */
+int ca_gcate_nll(ca_gcate_t h, double* out);
+/* grad: wrt_A = 0 -> grad(Y, A, B) (p x k); wrt_A = 1 -> grad(Y^T, B, A) (n x k)
+ * (gcate_likelihood.py:98-142; call sites gcate_opt.py:168,182). */
+int ca_gcate_grad(ca_gcate_t h, int wrt_A, double* out);
+
+typedef struct {
+  /* kwargs_ls (gcate_opt.py:265-274) */
+  double alpha, beta, tol, C;
+  int ls_max_iters;
+  double tol_gene, tol_cell;
+  int recheck_interval;
+  double sparsity_threshold, sparsity_boost;
+  int warmup_iters;
+  /* kwargs_es (gcate_opt.py:280) */
+  int es_max_iters, es_warmup, es_patience;
+  double es_tolerance, es_rel_tol;
+  /* penalty (gcate_opt.py:352-353): weights = lam / (|B[:, d-a:d]| + 1e-6) */
+  double lam;
+  int a;
+} ca_altmin_params;
+
+typedef struct {
+  int n_iter;
+  double func_val, resid;
+  int hist_len;
+  int64_t total_gene_updates, total_cell_updates;
+  int64_t cell_evals, gene_evals; /* line-search evaluations actually run */
+  double loop_seconds;
+} ca_altmin_result;
+
+/* The optimiser loop of alter_min (gcate_opt.py:337-458) from the factors set
+ * with ca_gcate_set_factors and the stage set with ca_gcate_set_stage (lam of
+ * set_stage is ignored; the adaptive weights are computed on the device).
+ * hist must have room for es_max_iters + 1 doubles. */
+int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_altmin_result* res, double* hist);
+
+/* ------------------------------------------------------------------------
+ * S2 -- per-gene GLM seam.  Replaces fit_glm / fit_glm_auto
+ * (causarray/gcate_glm.py:95-272, 365-457; IRLS arithmetic = statsmodels
+ * GLM._fit_irls, see oracle/glm.py), estimate_disp (:275-308) and the
+ * deviance residuals (causarray/nb_glm_fast.py:729-777).
+ * ------------------------------------------------------------------------ */
+typedef struct ca_glm* ca_glm_t;
+
+int ca_glm_create(ca_glm_t* out, int n, int p);
+int ca_glm_destroy(ca_glm_t h);
+/* Raw counts (n x p). */
+int ca_glm_load_counts(ca_glm_t h, const double* Y);
+/* Share the counts already resident in a GCATE handle (no copy). */
+int ca_glm_share_counts(ca_glm_t h, ca_gcate_t g);
+
+/* Fit p independent GLMs  y_j ~ X beta_j + offset  (log link).
+ *   X (n x kx), offset (n) or NULL, nu (p) NB sizes (family NB) or NULL,
+ *   genes with nu > thres_disp are fitted as Poisson (gcate_glm.py:194).
+ *   d_guard: |beta[:d_guard]| > 50 or |beta[d_guard:]| > 10 marks the gene as
+ *   diverged (status 1, gcate_glm.py:205); pass kx to disable the second bound.
+ * Outputs: B (p x kx), dev (p), n_iter (p), status (p; 0 ok, 1 guard, 2 numeric).
+ * Fitted means stay on the device for ca_glm_resid / ca_glm_disp_moments. */
+int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+               double thres_disp, int maxiter, double tol, int d_guard, double* B, double* dev, int32_t* n_iter,
+               int32_t* status);
+/* Signed deviance residuals of the last fit, (n x p). */
+int ca_glm_resid(ca_glm_t h, double* resid);
+/* Fitted means of the last fit, (n x p). */
+int ca_glm_fitted(ca_glm_t h, double* mu);
+/* Method-of-moments NB size from the last (Poisson) fit (gcate_glm.py:301-306). */
+int ca_glm_disp_moments(ca_glm_t h, const double* offset, double* disp);
+
+/* ------------------------------------------------------------------------
+ * S3 -- doubly-robust reduction seam.  Replaces AIPW_mean
+ * (causarray/DR_estimation.py:624-659), the normalisation
+ * etas /= size_factors (causarray/DR_learner.py:208) and the LFC estimand
+ * closure (causarray/DR_learner.py:403-482) without materialising the
+ * (n, p, a, 2) tensors: Yhat0 = exp(W Bcov^T + offset), Yhat1_k = Yhat0 *
+ * exp(Btrt[:,k]), both clipped at yhat_cap (DR_estimation.py:615).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int usevar;          /* 0 pooled, 1 unequal (Welch) */
+  double thres_min, thres_diff, eps_var;
+  double yhat_cap;     /* 1e5 */
+} ca_lfc_params;
+
+/* Y (n x p) raw counts, W (n x kw), Bcov (p x kw), Btrt (p x a), offset (n) or
+ * NULL, size_factor (n), A (n x a) 0/1 as double, pi (n x a), cell_mask
+ * (n x a) uint8 or NULL (= ctrl | case_j).
+ * Outputs, each (a x p) treatment-major: mean0, mean1, tau, var, df,
+ * estimable (uint8). */
+int ca_aipw_lfc(int n, int p, int kw, int a, const double* Y, const double* W, const double* Bcov,
+                const double* Btrt, const double* offset, const double* size_factor, const double* A,
+                const double* pi, const uint8_t* cell_mask, const ca_lfc_params* prm, double* mean0,
+                double* mean1, double* tau, double* var, double* df, uint8_t* estimable);
+/* Same with the counts shared from a GLM handle (already on the device). */
+int ca_aipw_lfc_shared(ca_glm_t h, int kw, int a, const double* W, const double* Bcov, const double* Btrt,
+                       const double* offset, const double* size_factor, const double* A, const double* pi,
+                       const uint8_t* cell_mask, const ca_lfc_params* prm, double* mean0, double* mean1,
+                       double* tau, double* var, double* df, uint8_t* estimable);
+/* Generic variant with explicit Y_hat (n x p x a x 2) for API compatibility
+ * with LFC(..., Y_hat=...). */
+int ca_aipw_lfc_yhat(int n, int p, int a, const double* Y, const double* Yhat, const double* size_factor,
+                     const double* A, const double* pi, const uint8_t* cell_mask, const ca_lfc_params* prm,
+                     double* mean0, double* mean1, double* tau, double* var, double* df, uint8_t* estimable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAUSARRAY_B200_H */

@@ -1,0 +1,87 @@
+"""GPU parity of the S2 (per-gene GLM) and S3 (AIPW / LFC) seams."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import glm as og
+
+pytestmark = pytest.mark.gpu
+
+
+def _glm_problem(fam, seed, n_ctrl=120, p=90):
+    from causarray_b200.synth import simulate_screen
+    sim = simulate_screen(n_ctrl=n_ctrl, n_perts=3, cells_per_pert=40, p=p, r=2, d_cov=2, family=fam, seed=seed,
+                          base_lo=0.0, base_hi=2.5)
+    rng = np.random.default_rng(seed)
+    Y = sim["Y"]
+    X = np.c_[sim["X"], sim["A"], sim["U"] * 0.3]
+    off = rng.standard_normal(Y.shape[0]) * 0.2
+    return Y, X, off, sim["disp"]
+
+
+@pytest.mark.parametrize("fam", ["poisson", "nb"])
+def test_glm_fit_vs_oracle(fam):
+    from causarray_b200.device import GlmDevice
+    Y, X, off, disp = _glm_problem(fam, 3)
+    n, p = Y.shape
+    disp = disp.copy()
+    disp[::7] = 500.0   # Poisson switch inside the NB family
+    B_ref, Yhat_ref, _, _, resid_ref, status_ref, it_ref = og.fit_glm_original(
+        Y, X, None, family=fam, disp_glm=disp, offset=off, maxiter=100)
+    dev = GlmDevice(n, p)
+    dev.load_counts(Y)
+    B, dv, n_iter, status = dev.fit(fam, X, off, disp if fam == "nb" else None, maxiter=100, tol=1e-8, d_guard=2)
+    ok = (status == 0) & (status_ref == 0)
+    print(fam, "ok genes", ok.sum(), "of", p, "max |dB|", np.abs(B[ok] - B_ref[ok]).max(), "iters", n_iter[:10],
+          it_ref[:10], "iter mismatches", int((n_iter[ok] != it_ref[ok]).sum()))
+    assert ok.sum() >= p - 2
+    np.testing.assert_allclose(B[ok], B_ref[ok], rtol=1e-7, atol=1e-8)
+    assert (n_iter[ok] != it_ref[ok]).sum() <= max(1, p // 50)
+    mu = dev.fitted()
+    np.testing.assert_allclose(mu[:, ok], Yhat_ref[:, ok], rtol=1e-7)
+    resid = dev.resid()
+    np.testing.assert_allclose(resid[:, ok], resid_ref[:, ok], rtol=1e-6, atol=1e-7)
+    dm = dev.disp_moments(off)
+    dm_ref = og.estimate_disp_moments(Y, mu, off)
+    np.testing.assert_allclose(dm, dm_ref, rtol=1e-9)
+
+
+def test_glm_golden_helpers(golden_dir):
+    """MoM dispersion against the reference's own estimate_disp (golden)."""
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    Y, mu, sf = g["Y"], g["mu"], g["size_factor"]
+    ref = og.estimate_disp_moments(Y, mu, np.log(sf))
+    np.testing.assert_allclose(ref, g["disp_mom"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("usevar", ["unequal", "pooled"])
+def test_aipw_lfc_golden(golden_dir, usevar):
+    from causarray_b200.device import aipw_lfc, aipw_lfc_yhat
+    g = np.load(os.path.join(golden_dir, "lfc_%s.npz" % usevar))
+    Y, W, A = g["Y"], g["W"], g["A"]
+    n, p = Y.shape
+    a = A.shape[1]
+    sf = np.exp(g["offset"])
+    out = aipw_lfc(Y, W, g["Bcov"], g["Btrt"], g["offset"], sf, A, g["pi"], usevar=usevar)
+    tau = out["tau"].reshape(-1)
+    std = np.sqrt(out["var"]).reshape(-1)
+    fin = np.isfinite(g["df_std"])
+    print(usevar, "tau err", np.abs(tau - g["df_tau"]).max(), "std rel err",
+          np.abs(std[fin] / g["df_std"][fin] - 1).max(), "filtered", (~fin).sum())
+    np.testing.assert_array_equal(np.isfinite(std), fin)
+    np.testing.assert_allclose(tau, g["df_tau"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(std[fin], g["df_std"][fin], rtol=1e-9)
+    np.testing.assert_allclose(out["mean0"].reshape(-1), g["df_mean_control"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["mean1"].reshape(-1), g["df_mean_treated"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_array_equal(out["estimable"].reshape(-1), g["estimable"].astype(bool))
+    # explicit-Yhat variant
+    eta0 = W @ g["Bcov"].T + g["offset"][:, None]
+    Y_hat = np.zeros((n, p, a, 2))
+    for k in range(a):
+        Y_hat[:, :, k, 0] = np.exp(eta0)
+        Y_hat[:, :, k, 1] = np.exp(eta0 + g["Btrt"][:, k][None, :])
+    out2 = aipw_lfc_yhat(Y, Y_hat, sf, A, g["pi"], usevar=usevar)
+    np.testing.assert_allclose(out2["tau"].reshape(-1), g["df_tau"], rtol=1e-9, atol=1e-12)
+    std2 = np.sqrt(out2["var"]).reshape(-1)
+    np.testing.assert_allclose(std2[fin], g["df_std"][fin], rtol=1e-9)
