@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- GCATE + doubly-robust LFC throughput on the Replogle-K562-shaped workload.
+
+A "step" is one perturbation batch of ``gcate_lfc_batch`` (BASELINE.json config 3): 2,000 control
+cells + 15 perturbations x 133 cells (the ``max_cells=2000`` cap), p = 8,000 genes, r = 10 latent
+factors, NB family; i.e. ``fit_gcate`` (size factors, 2 GLM initialisations + SVD, two-stage
+alternating minimisation) followed by ``LFC`` (propensities, Poisson + NB outcome GLMs, AIPW
+reductions, BH) through the public Python API.
+
+Metric: cell*gene updates per second = n*p*(alternating iterations, both stages) + n*(sum over
+genes and GLM fits of IRLS iterations), divided by the step time.
+
+  value  -- counts already resident in HBM when the timed region starts
+  e2e    -- host numpy arrays in, result DataFrame out (H2D / D2H inside the timed region)
+
+``--impl reference`` times the CPU restatement of the same step (oracle/pipeline.py: C/OpenMP
+alternating iteration + numpy IRLS over all host cores) on a bounded gene subsample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="replogle_k562_gcate_lfc_batch", n_ctrl=2000, n_perts=15, cells_per_pert=133, p=8000, r=10,
+                family="nb", es_max_iters=30, es_rel_tol=2e-4, usevar="unequal")
+
+
+def make_batch(seed, p=None):
+    from causarray_b200.synth import simulate_screen
+    from causarray_b200.prep import prep_causarray_data
+    w = WORKLOAD
+    sim = simulate_screen(n_ctrl=w["n_ctrl"], n_perts=w["n_perts"], cells_per_pert=w["cells_per_pert"],
+                          p=p or w["p"], r=w["r"], d_cov=1, family=w["family"], seed=seed, base_lo=-1.5, base_hi=1.5)
+    Y, A = sim["Y"], sim["A"]
+    _, _, X, X_A = prep_causarray_data(Y, A)
+    return dict(Y=np.ascontiguousarray(Y), X=X, A=A, X_A=X_A, disp=sim["disp"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        # under load = upper half of the samples (the sampler also sees host-side phases)
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def gpu_step(batch, resident_ws=None):
+    """One batch through the public API.  Returns (DataFrame, stats)."""
+    import pandas as pd
+    import causarray_b200 as cb
+    from causarray_b200 import glm as cglm
+    w = WORKLOAD
+    es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
+    cglm.COUNTERS["irls_gene_iters"] = 0
+    Y, X, A, X_A = batch["Y"], batch["X"], batch["A"], batch["X_A"]
+    res1, res2 = cb.fit_gcate(Y, X, A, w["r"], family=w["family"], disp_glm=batch["disp"], offset=True,
+                              kwargs_es_1=dict(es), kwargs_es_2=dict(es), _ws=resident_ws)
+    ws = res2.pop("_ws")
+    U = res2["U"]
+    off = np.log(res2["kwargs_glm"]["size_factor"])
+    df, est = cb.LFC(Y, np.c_[X, U], pd.DataFrame(A), np.c_[X_A, U], family=w["family"], offset=off,
+                     usevar=w["usevar"], _glm=ws.glm, _trusted=True)
+    if resident_ws is None:
+        ws.close()
+    n, p = Y.shape
+    alt_iters = (len(res1["hist"]) - 1) + (len(res2["hist"]) - 1)
+    irls = cglm.COUNTERS["irls_gene_iters"]
+    stats = dict(alt_iters=alt_iters, irls_gene_iters=irls, updates=n * p * alt_iters + n * irls,
+                 cell_updates=res1["total_cell_updates"] + res2["total_cell_updates"],
+                 gene_rows=(alt_iters) * p,
+                 cell_evals=res1["line_search_evals"][0] + res2["line_search_evals"][0],
+                 gene_evals=res1["line_search_evals"][1] + res2["line_search_evals"][1],
+                 loop_seconds=res1["loop_seconds"] + res2["loop_seconds"], n=n, p=p,
+                 n_sig=int(np.nansum(df["padj"].to_numpy() < 0.05)))
+    return df, stats
+
+
+def cpu_step(batch, n_jobs):
+    from oracle import pipeline as op
+    w = WORKLOAD
+    es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
+    g, l, st = op.gcate_lfc_one_batch_cpu(batch["Y"], batch["X"], batch["A"], batch["X_A"], w["r"],
+                                          family=w["family"], disp=batch["disp"], es1=dict(es), es2=dict(es),
+                                          usevar=w["usevar"], n_jobs=n_jobs)
+    return st
+
+
+def run_reference(args, rank, world):
+    """CPU arm: rank 0 only; bounded sample = gene subsample of the same batch shape."""
+    if rank != 0:
+        return
+    from oracle import cport
+    cores = os.cpu_count() or 1
+    p_s = args.cpu_genes
+    times, upd = [], []
+    stats = None
+    for s in range(args.warmup + args.steps):
+        batch = make_batch(1000 + s, p=p_s)
+        t0 = time.perf_counter()
+        stats = cpu_step(batch, cores)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            upd.append(stats["cell_gene_updates"])
+    T = sum(times)
+    value = sum(upd) / T
+    w = WORKLOAD
+    n = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
+    sample = ("one batch of the same shape (n=%d cells, r=%d, %d perturbations) restricted to %d of %d genes; "
+              "C/OpenMP alternating iteration on %d threads + per-gene numpy IRLS over %d processes"
+              % (n, w["r"], w["n_perts"], p_s, w["p"], cport.threads(), cores))
+    out = {"impl": "reference", "metric": "gcate_lfc_cell_gene_updates_per_s", "value": value,
+           "unit": "cell*gene updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * T / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": w["name"], "n_cells": n, "n_genes_sample": p_s, "n_genes": w["p"], "r": w["r"],
+                      "perturbations": w["n_perts"], "family": w["family"]},
+           "cpu_baseline": {"value": value, "unit": "cell*gene updates/s", "cores": cores, "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": value, "unit": "cell*gene updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "phases_s": {k: round(v, 3) for k, v in stats.items() if k.startswith("t_")}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-genes", type=int, default=400, help="gene subsample of the CPU arms")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--genes", type=int, default=None, help="override p (debug only; makes the number invalid)")
+    args = ap.parse_args()
+    warnings.simplefilter("ignore")
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    from causarray_b200 import _lib as L
+    L.load()
+    L.check(L._lib.ca_set_device(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from causarray_b200.optim import BatchWorkspace
+    w = WORKLOAD
+    nb = args.warmup + args.steps
+    batches = [make_batch(100 * rank + s, p=args.genes) for s in range(min(nb, 4))]
+    n, p = batches[0]["Y"].shape
+    d = batches[0]["X"].shape[1] + batches[0]["A"].shape[1]
+
+    # ---------------- resident arm: counts uploaded outside the timed region ----------------
+    def resident_pass(nsteps, timed):
+        tot_updates, stats_all = 0, []
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        elapsed = 0.0
+        for s in range(nsteps):
+            b = batches[s % len(batches)]
+            ws = BatchWorkspace.upload(b["Y"], w["family"], d, w["r"])
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            df, st = gpu_step(b, resident_ws=ws)
+            ev1.record()
+            torch.cuda.synchronize()
+            elapsed += time.perf_counter() - t0
+            ws.close()
+            tot_updates += st["updates"]
+            stats_all.append(st)
+        return elapsed, tot_updates, stats_all
+
+    resident_pass(args.warmup, False)
+    L.profile_enable(True)
+    L.profile_reset()
+    launches0 = L.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_res, upd_res, stats_res = resident_pass(args.steps, True)
+    barrier()
+    prof = L.profile_snapshot()
+    launches = L.launch_count() - launches0
+    L.profile_enable(False)
+
+    # ---------------- end-to-end arm: host arrays in, DataFrame out ----------------
+    for s in range(min(args.warmup, 1)):
+        gpu_step(batches[s % len(batches)])
+    barrier()
+    t0 = time.perf_counter()
+    upd_e2e = 0
+    d2h = 0
+    for s in range(args.steps):
+        df, st = gpu_step(batches[s % len(batches)])
+        upd_e2e += st["updates"]
+        d2h = int(df.memory_usage(index=False).sum())
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler is not None else None
+
+    # max over ranks of the times, sum over ranks of the work
+    if world > 1:
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor([float(upd_res), float(upd_e2e)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        t_res, t_e2e = t.tolist()
+        upd_res, upd_e2e = u.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    # per-kernel-class algorithmic bytes over the timed resident steps (rank 0)
+    st_sum = {k: sum(s[k] for s in stats_res) for k in ("cell_updates", "gene_rows", "cell_evals", "gene_evals",
+                                                         "irls_gene_iters", "alt_iters")}
+    alg_bytes = {
+        # Y read once per active row: cells x p + genes x n doubles
+        "rowpass_grad": 8.0 * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
+        # one read of the row of Y per candidate evaluation
+        "search": 8.0 * (st_sum["cell_evals"] * p + st_sum["gene_evals"] * n),
+        # one read of the gene's counts per IRLS iteration
+        "glm_pass": 8.0 * st_sum["irls_gene_iters"] * n,
+    }
+    kern = {}
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    for name, (ms, cnt) in prof.items():
+        kern[name] = {"ms": round(ms, 3), "launches": cnt, "share": round(ms / tot_ms, 4)}
+        if name in alg_bytes and ms > 0:
+            kern[name]["achieved_gbs"] = round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1)
+    dom = max((k for k in alg_bytes if prof.get(k, (0, 0))[0] > 0), key=lambda k: prof[k][0], default=None)
+    roofline = None
+    if dom is not None:
+        ms, cnt = prof[dom]
+        ach = alg_bytes[dom] / (ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": round(ms / max(1, cnt), 4), "launches": cnt,
+                    "note": "FP64 transcendental-bound kernel; see DESIGN.md for the FP64 (36.5 TFLOP/s measured) "
+                            "roofline of the same kernel"}
+
+    out = {"metric": "gcate_lfc_cell_gene_updates_per_s", "value": upd_res / t_res, "unit": "cell*gene updates/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": w["name"], "n_cells": n, "n_genes": p, "r": w["r"],
+                      "perturbations_per_batch": w["n_perts"], "family": w["family"],
+                      "batches_per_step_per_gpu": 1, "parallelism": "batch-sharded x%d" % world,
+                      "l2_policy": "inputs larger than L2 (Y and Y^T are 256 MB each at fp64)"},
+           "e2e": {"value": upd_e2e / t_e2e, "unit": "cell*gene updates/s", "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "h2d_bytes_per_step": int(batches[0]["Y"].nbytes + batches[0]["X"].nbytes
+                                             + batches[0]["A"].nbytes + batches[0]["X_A"].nbytes),
+                   "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
+           "work_per_step": {k: v / args.steps for k, v in st_sum.items()},
+           "n_significant_last_step": stats_res[-1]["n_sig"]}
+
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import cport
+        cores = os.cpu_count() or 1
+        b = make_batch(1000, p=args.cpu_genes)
+        t0 = time.perf_counter()
+        st = cpu_step(b, cores)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {
+            "value": st["cell_gene_updates"] / dt, "unit": "cell*gene updates/s", "cores": cores, "kind": "port",
+            "seconds": round(dt, 2),
+            "sample": "one batch of the same shape (n=%d, r=%d, %d perturbations) restricted to %d of %d genes; "
+                      "C/OpenMP alternating iteration (%d threads) + per-gene numpy IRLS over %d processes"
+                      % (n, w["r"], w["n_perts"], args.cpu_genes, w["p"], cport.threads(), cores),
+            "phases_s": {k: round(v, 3) for k, v in st.items() if k.startswith("t_")}}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

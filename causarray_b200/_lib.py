@@ -5,6 +5,7 @@ visible every numeric entry point raises ``CausarrayCudaError``.
 """
 import ctypes
 import os
+import time
 
 import numpy as np
 
@@ -64,6 +65,9 @@ _SIGNATURES = {
     "ca_gcate_create": [ctypes.POINTER(_P), _c_int, _c_int, _c_int, _c_int, _c_int, _c_double],
     "ca_gcate_destroy": [_P],
     "ca_gcate_load_counts": [_P, _D, _D, _D],
+    "ca_gcate_upload_counts": [_P, _D] + [ctypes.POINTER(ctypes.c_int64)] * 3,
+    "ca_gcate_size_factor_medians": [_P, _D],
+    "ca_gcate_prepare": [_P, _D, _D],
     "ca_gcate_load_normalized": [_P, _D, _D, _D],
     "ca_gcate_set_factors": [_P, _D, _D],
     "ca_gcate_get_factors": [_P, _D, _D],
@@ -79,14 +83,24 @@ _SIGNATURES = {
     "ca_glm_load_counts": [_P, _D],
     "ca_glm_share_counts": [_P, _P],
     "ca_glm_fit": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _c_int, _D, _D, _I32, _I32],
+    "ca_glm_fit_ex": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _c_int, _D, _U8, _D, _D, _I32, _I32],
     "ca_glm_resid": [_P, _D],
+    "ca_glm_resid_device": [_P, ctypes.POINTER(_P)],
     "ca_glm_fitted": [_P, _D],
     "ca_glm_disp_moments": [_P, _D, _D],
     "ca_aipw_lfc": [_c_int] * 4 + [_D] * 8 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
     "ca_aipw_lfc_shared": [_P, _c_int, _c_int] + [_D] * 7 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
     "ca_aipw_lfc_yhat": [_c_int] * 3 + [_D] * 5 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],
+    "ca_profile_enable": [_c_int],
+    "ca_profile_reset": [],
+    "ca_profile_num_classes": [],
+    "ca_profile_class_name": [_c_int],
+    "ca_profile_get": [_c_int, _D, ctypes.POINTER(ctypes.c_int64)],
+    "ca_launch_count": [],
+    "ca_test_fastmath": [_D, _c_int, _c_int, _D],
 }
-_RESTYPE = {"ca_last_error": ctypes.c_char_p}
+_RESTYPE = {"ca_last_error": ctypes.c_char_p, "ca_profile_class_name": ctypes.c_char_p,
+            "ca_launch_count": ctypes.c_int64}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -109,7 +123,11 @@ def load(require_gpu=True):
         _lib = lib
     if require_gpu:
         sm = ctypes.c_int(0)
-        rc = _lib.ca_device_info(ctypes.byref(sm), None, None, None)
+        for attempt in range(5):   # the first CUDA call on a freshly booted box can race the driver
+            rc = _lib.ca_device_info(ctypes.byref(sm), None, None, None)
+            if rc == 0:
+                break
+            time.sleep(1.0)
         if rc != 0:
             raise CausarrayCudaError("no usable CUDA device: %s" % _lib.ca_last_error().decode())
     return _lib
@@ -145,3 +163,27 @@ def i32ptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def profile_enable(on=True):
+    load().ca_profile_enable(1 if on else 0)
+
+
+def profile_reset():
+    load().ca_profile_reset()
+
+
+def profile_snapshot():
+    """{class name: (total device ms, launches)} since the last reset."""
+    lib = load()
+    out = {}
+    for c in range(lib.ca_profile_num_classes()):
+        ms = ctypes.c_double(0.0)
+        cnt = ctypes.c_int64(0)
+        lib.ca_profile_get(c, ctypes.byref(ms), ctypes.byref(cnt))
+        out[lib.ca_profile_class_name(c).decode()] = (ms.value, int(cnt.value))
+    return out
+
+
+def launch_count():
+    return int(load().ca_launch_count())

@@ -347,3 +347,141 @@ int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi,
 }
 
 }  // namespace ca
+
+// ---------------------------------------------------------------------------
+// Input checks and median-of-ratios size factors on the device
+// (causarray/gcate.py:12-17 and causarray/utils.py:179-219).
+// ---------------------------------------------------------------------------
+namespace ca {
+
+// flags[0] += #non-integer entries (np.allclose(Y, trunc(Y)) tolerance), flags[1] += #non-finite
+__global__ void k_check_counts(const double* __restrict__ Y, long total, unsigned long long* flags) {
+  unsigned long long nonint = 0, nonfin = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const double v = Y[i];
+    if (!isfinite(v)) {
+      ++nonfin;
+    } else {
+      const double t = trunc(v);
+      if (fabs(v - t) > 1e-8 + 1e-5 * fabs(t)) ++nonint;
+    }
+  }
+  if (nonint) atomicAdd(flags + 0, nonint);
+  if (nonfin) atomicAdd(flags + 1, nonfin);
+}
+int launch_check_counts(const double* Y, long total, unsigned long long* flags, cudaStream_t st) {
+  CA_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(unsigned long long), st));
+  k_check_counts<<<592, 256, 0, st>>>(Y, total, flags);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+// per gene (row of Y^T): mean of log(y) over y > 0, -inf if the gene is empty
+__global__ void k_log_geomean(const double* __restrict__ Yt, long ldn, int n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const double* y = Yt + (size_t)blockIdx.x * ldn;
+  double s = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = y[i];
+    if (v > 0.0) {
+      s += log(v);
+      c += 1.0;
+    }
+  }
+  s = block_sum(s, scratch);
+  c = block_sum(c, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = c > 0.0 ? s / c : -INFINITY;
+}
+
+__device__ __forceinline__ unsigned long long key_of(double v) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double val_of(unsigned long long k) {
+  const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+// One CTA per cell: median over expressed genes of log(y) - log_geomean (radix select).
+__global__ void __launch_bounds__(256) k_row_median(const double* __restrict__ Y, long ldY, int p,
+                                                     const double* __restrict__ lg,
+                                                     unsigned long long* __restrict__ scratch_keys,
+                                                     double* __restrict__ out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_k, s_m;
+  __shared__ unsigned long long s_min;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const double* y = Y + (size_t)row * ldY;
+  unsigned long long* keys = scratch_keys + (size_t)row * p;
+  const unsigned long long INVALID = 0xffffffffffffffffull;
+  if (tid == 0) s_m = 0;
+  __syncthreads();
+  unsigned int cnt = 0;
+  for (int j = tid; j < p; j += 256) {
+    const double v = y[j], g = lg[j];
+    unsigned long long k = INVALID;
+    if (v > 0.0 && isfinite(g)) {
+      k = key_of(log(v) - g);
+      ++cnt;
+    }
+    keys[j] = k;
+  }
+  atomicAdd(&s_m, cnt);
+  __syncthreads();
+  const unsigned int m = s_m;
+  if (m == 0) {
+    if (tid == 0) out[row] = NAN;
+    return;
+  }
+  double med[2];
+  const unsigned int ranks[2] = {(m - 1) / 2, m / 2};
+  for (int which = 0; which < 2; ++which) {
+    if (which == 1 && ranks[1] == ranks[0]) {
+      med[1] = med[0];
+      break;
+    }
+    if (tid == 0) {
+      s_prefix = 0;
+      s_k = ranks[which];
+    }
+    __syncthreads();
+    for (int pass = 7; pass >= 0; --pass) {
+      hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << (8 * (pass + 1)));
+      for (int j = tid; j < p; j += 256) {
+        const unsigned long long k = keys[j];
+        if (k != INVALID && (k & himask) == prefix) atomicAdd(&hist[(k >> (8 * pass)) & 0xff], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int kk = s_k, b = 0;
+        for (; b < 256; ++b) {
+          if (kk < hist[b]) break;
+          kk -= hist[b];
+        }
+        s_k = kk;
+        s_prefix = prefix | ((unsigned long long)b << (8 * pass));
+      }
+      __syncthreads();
+    }
+    med[which] = val_of(s_prefix);
+    __syncthreads();
+  }
+  (void)s_min;
+  if (tid == 0) out[row] = (ranks[0] == ranks[1]) ? med[0] : 0.5 * (med[0] + med[1]);
+}
+
+int launch_size_factor_medians(const double* Yraw, long ldY, const double* Yraw_t, long ldn, int n, int p,
+                               double* log_geo /*p*/, unsigned long long* scratch /*n*p*/, double* out /*n*/,
+                               cudaStream_t st) {
+  k_log_geomean<<<p, 256, 0, st>>>(Yraw_t, ldn, n, log_geo);
+  CA_LAUNCH_CHECK();
+  k_row_median<<<n, 256, 0, st>>>(Yraw, ldY, p, log_geo, scratch, out);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ca

@@ -12,6 +12,7 @@ namespace ca {
 // error plumbing: every extern "C" entry returns 0 or a negative code and
 // leaves a message retrievable through ca_last_error().
 // ---------------------------------------------------------------------------
+extern long long g_launches;
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, int line);
 
@@ -21,7 +22,11 @@ int cuda_fail(cudaError_t e, const char* what, int line);
     if (_e != cudaSuccess) return ca::cuda_fail(_e, #x, __LINE__);       \
   } while (0)
 
-#define CA_LAUNCH_CHECK() CA_CUDA(cudaGetLastError())
+#define CA_LAUNCH_CHECK()            \
+  do {                               \
+    ++ca::g_launches;                \
+    CA_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define CA_REQUIRE(cond, msg)                                            \
   do {                                                                   \

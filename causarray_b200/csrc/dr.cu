@@ -28,6 +28,7 @@
 #include "devbuf.h"
 #include "kernels.h"
 #include "glm_state.h"
+#include "prof.h"
 
 namespace ca {
 
@@ -287,10 +288,16 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
     D.j0 = g * JT;
     D.nj = std::min(JT, a - D.j0);
     CA_CUDA(cudaMemcpyAsync(d_rec.ptr, recs[g].data(), sizeof(double) * (size_t)n * ldr, cudaMemcpyHostToDevice, st));
-    k_aipw<0><<<grid, DR_THREADS, sm, st>>>(D);
-    CA_LAUNCH_CHECK();
-    k_aipw<1><<<grid, DR_THREADS, sm, st>>>(D);
-    CA_LAUNCH_CHECK();
+    {
+      ProfScope prof(PROF_AIPW, st);
+      k_aipw<0><<<grid, DR_THREADS, sm, st>>>(D);
+      CA_LAUNCH_CHECK();
+    }
+    {
+      ProfScope prof(PROF_AIPW, st);
+      k_aipw<1><<<grid, DR_THREADS, sm, st>>>(D);
+      CA_LAUNCH_CHECK();
+    }
     CA_CUDA(cudaStreamSynchronize(st));  // recs[g] is reused as the staging source
   }
   const size_t ap = (size_t)a * p;

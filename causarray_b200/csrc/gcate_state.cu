@@ -46,7 +46,7 @@ using namespace ca;
 static int gcate_alloc(ca_gcate* h) {
   const int n = h->n, p = h->p, kp = h->kpad;
   if (h->Yn.alloc((size_t)n * h->ldp) || h->Ynt.alloc((size_t)p * h->ldn)) return -1;
-  if (h->nu.alloc(p) || h->tys_row.alloc(n) || h->tys_col.alloc(p) || h->tys_total.alloc(1) || h->sparsity.alloc(p))
+  if (h->nu.alloc(p) || h->inv_nu.alloc(p) || h->log_nu.alloc(p) || h->tys_row.alloc(n) || h->tys_col.alloc(p) || h->tys_total.alloc(1) || h->sparsity.alloc(p))
     return -1;
   if (h->A.alloc((size_t)n * kp) || h->B.alloc((size_t)p * kp) || h->Aprev.alloc((size_t)n * kp) ||
       h->Bprev.alloc((size_t)p * kp))
@@ -128,7 +128,14 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
     ones.assign(p, 1.0);
     nu_host = ones.data();
   }
+  std::vector<double> hin(p), hln(p);
+  for (int j = 0; j < p; ++j) {
+    hin[j] = 1.0 / nu_host[j];
+    hln[j] = std::log(nu_host[j]);
+  }
   CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu_host, sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaMemcpyAsync(h->inv_nu.ptr, hin.data(), sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaMemcpyAsync(h->log_nu.ptr, hln.data(), sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
   CA_CUDA(cudaStreamSynchronize(h->st));
   if (Ys_dev_or_null) {
     // row sums directly; column sums through a transposed copy staged in Graw buffers is too small,
@@ -151,24 +158,65 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
   return 0;
 }
 
-extern "C" int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu) {
+extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
+                                      int64_t* n_empty_genes) {
   CA_REQUIRE(h && Y, "null argument");
   const int n = h->n, p = h->p;
   if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
-  DevBuf<double> sf;
   CA_CUDA(cudaMemcpyAsync(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  CA_CUDA(cudaMemsetAsync(h->Yraw_t.ptr, 0, h->Yraw_t.bytes(), h->st));
+  if (launch_transpose(h->Yraw.ptr, n, p, p, h->Yraw_t.ptr, h->ldn, h->st)) return -1;
+  h->raw_loaded = true;
+  h->counts_loaded = false;
+  if (n_nonint || n_nonfinite || n_empty_genes) {
+    DevBuf<unsigned long long> flags;
+    if (flags.alloc(2)) return -1;
+    if (launch_check_counts(h->Yraw.ptr, (long)n * p, flags.ptr, h->st)) return -1;
+    if (launch_zero_fraction(h->Yraw_t.ptr, h->ldn, p, n, h->sparsity.ptr, h->st)) return -1;
+    unsigned long long hf[2];
+    std::vector<double> sp(p);
+    CA_CUDA(cudaMemcpyAsync(hf, flags.ptr, sizeof hf, cudaMemcpyDeviceToHost, h->st));
+    CA_CUDA(cudaMemcpyAsync(sp.data(), h->sparsity.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, h->st));
+    CA_CUDA(cudaStreamSynchronize(h->st));
+    int64_t empty = 0;
+    for (int j = 0; j < p; ++j) empty += (sp[j] >= 1.0);
+    if (n_nonint) *n_nonint = (int64_t)hf[0];
+    if (n_nonfinite) *n_nonfinite = (int64_t)hf[1];
+    if (n_empty_genes) *n_empty_genes = empty;
+  }
+  return 0;
+}
+
+extern "C" int ca_gcate_size_factor_medians(ca_gcate_t h, double* log_sf) {
+  CA_REQUIRE(h && h->raw_loaded && log_sf, "upload counts first");
+  const int n = h->n, p = h->p;
+  DevBuf<double> lg, out;
+  DevBuf<unsigned long long> scratch;
+  if (lg.alloc(p) || out.alloc(n) || scratch.alloc((size_t)n * p)) return -1;
+  if (launch_size_factor_medians(h->Yraw.ptr, p, h->Yraw_t.ptr, h->ldn, n, p, lg.ptr, scratch.ptr, out.ptr, h->st))
+    return -1;
+  CA_CUDA(cudaMemcpyAsync(log_sf, out.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st));
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_gcate_prepare(ca_gcate_t h, const double* size_factor, const double* nu) {
+  CA_REQUIRE(h && h->raw_loaded, "upload counts first");
+  const int n = h->n, p = h->p;
+  DevBuf<double> sf;
   const double* sfp = nullptr;
   if (size_factor) {
     if (sf.alloc(n)) return -1;
     CA_CUDA(cudaMemcpyAsync(sf.ptr, size_factor, sizeof(double) * n, cudaMemcpyHostToDevice, h->st));
     sfp = sf.ptr;
   }
-  CA_CUDA(cudaMemsetAsync(h->Yraw_t.ptr, 0, h->Yraw_t.bytes(), h->st));
-  if (launch_transpose(h->Yraw.ptr, n, p, p, h->Yraw_t.ptr, h->ldn, h->st)) return -1;
   if (launch_normalize_transpose(h->Yraw.ptr, n, p, p, sfp, h->Yn.ptr, h->ldp, h->Ynt.ptr, h->ldn, h->st)) return -1;
-  h->raw_loaded = true;
-  int rc = finish_load(h, nu, nullptr);
-  return rc;
+  return finish_load(h, nu, nullptr);
+}
+
+extern "C" int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu) {
+  if (int rc = ca_gcate_upload_counts(h, Y, nullptr, nullptr, nullptr)) return rc;
+  return ca_gcate_prepare(h, size_factor, nu);
 }
 
 extern "C" int ca_gcate_load_normalized(ca_gcate_t h, const double* Yn, const double* Ys, const double* nu) {
@@ -279,6 +327,8 @@ static RowProblem cell_problem(ca_gcate* h) {
   rp.M = h->B.ptr;
   rp.kpad = h->kpad;
   rp.nu = h->nu.ptr;
+  rp.inv_nu = h->inv_nu.ptr;
+  rp.log_nu = h->log_nu.ptr;
   rp.nu_per_row = 0;
   rp.family = h->family;
   rp.thres_disp = h->thres;
@@ -292,6 +342,8 @@ static RowProblem gene_problem(ca_gcate* h) {
   rp.M = h->A.ptr;
   rp.kpad = h->kpad;
   rp.nu = h->nu.ptr;
+  rp.inv_nu = h->inv_nu.ptr;
+  rp.log_nu = h->log_nu.ptr;
   rp.nu_per_row = 1;
   rp.family = h->family;
   rp.thres_disp = h->thres;

@@ -27,6 +27,8 @@
 #include "kernels.h"
 #include "glm_state.h"
 #include "gcate_state.h"
+#include "prof.h"
+#include "fastmath.cuh"
 
 namespace ca {
 
@@ -58,6 +60,9 @@ struct GlmPass {
   double tol;
   int finalize;          // 1: only deviance (+ mu_t), no Gram
   int* n_active;         // device counter of genes still running after this pass
+  const int* genelist;   // compacted list of running genes (nullptr = all genes)
+  int n_list;            // entries of genelist
+  const double* fm_tables;
 };
 
 template <int NT>
@@ -67,10 +72,13 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
   double* Xs = smem;                               // 2 * GLM_CHUNK * ldx
   double* betas = Xs + 2 * GLM_CHUNK * ldx;        // GLM_WARPS * ldx
   double* offs = betas + GLM_WARPS * ldx;          // 2 * GLM_CHUNK
+  double* s_tab = offs + 2 * GLM_CHUNK;            // FM_TABLE_DOUBLES
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
-  const int gene = blockIdx.x * GLM_WARPS + warp;
+  const int slot = blockIdx.x * GLM_WARPS + warp;
+  const int gene = P.genelist ? (slot < P.n_list ? P.genelist[slot] : P.p) : slot;
   const bool gene_ok = gene < P.p;
+  const FmTables FT = fm_load_tables(s_tab, P.fm_tables);
   bool active = gene_ok && (P.finalize ? true : (P.status[gene] == 0));
   // CTA-wide early out when nothing to do
   {
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
     pois = nu > P.thres;
   }
   const double ybar = gene_ok ? P.ybar[gene] : 1.0;
+  const int rot0 = lane % kx;
   for (int c = lane; c < ldx; c += 32) betas[warp * ldx + c] = (gene_ok && c < kx && !first) ? P.beta[(size_t)gene * kx + c] : 0.0;
   const double* yrow = P.Yt + (size_t)(gene_ok ? gene : 0) * P.ldn;
   double* murow = (P.mu_t && gene_ok) ? P.mu_t + (size_t)gene * P.ldn : nullptr;
@@ -138,23 +147,32 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
         double eta, mu;
         if (first) {
           mu = 0.5 * (y + ybar);
-          eta = log(mu);
+          eta = fm_log(mu, FT.log_t);
         } else {
+          // lane-rotated column order: lane l reads column (q + l) mod kx at step q, which makes
+          // the row-strided shared-memory reads conflict free; two partial sums for ILP
           const double* xr = Xc + (blk + lane) * ldx;
-          double e = 0.0;
-          for (int q = 0; q < kx; ++q) e = fma(xr[q], bw[q], e);
-          eta = e + off;
-          mu = exp(eta);
+          double ea = 0.0, eb = 0.0;
+          int idx = rot0;
+          for (int q = 0; q + 1 < kx; q += 2) {
+            ea = fma(xr[idx], bw[idx], ea);
+            idx = (idx + 1 >= kx) ? idx + 1 - kx : idx + 1;
+            eb = fma(xr[idx], bw[idx], eb);
+            idx = (idx + 1 >= kx) ? idx + 1 - kx : idx + 1;
+          }
+          if (kx & 1) ea = fma(xr[idx], bw[idx], ea);
+          eta = (ea + eb) + off;
+          mu = fm_exp(fmin(fmax(eta, -700.0), 700.0), FT.exp_t);
         }
         double w = 0.0, wz = 0.0;
         if (ok) {
           s_yeta += y * eta;  // y * log(mu): eta IS log(mu) (iteration 1: log mu0 without offset)
           s_mu += mu;
-          if (!pois) s_log += (y + nu) * log(mu + nu);
+          if (!pois) s_log += (y + nu) * fm_log(mu + nu, FT.log_t);
           if (murow) murow[cell] = mu;
           if (!P.finalize) {
-            w = pois ? mu : mu / (1.0 + mu / nu);
-            const double z = eta + (y - mu) / mu - off;
+            w = pois ? mu : mu * nu * __drcp_rn(nu + mu);
+            const double z = eta + (y - mu) * __drcp_rn(mu) - off;
             wz = w * z;
           }
         }
@@ -252,7 +270,8 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
 
 // Warp-level Cholesky solve of the Jacobi-scaled normal equations, one gene per warp.
 __global__ void k_glm_solve(int p, int kx, const double* __restrict__ gram, const double* __restrict__ rhs,
-                            int* __restrict__ status, double* __restrict__ beta, int iter, int* __restrict__ n_iter) {
+                            const double* __restrict__ ridge, int* __restrict__ status, double* __restrict__ beta,
+                            int iter, int* __restrict__ n_iter) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
@@ -265,14 +284,15 @@ __global__ void k_glm_solve(int p, int kx, const double* __restrict__ gram, cons
   double* b = sc + kx;
   const double* G = gram + (size_t)gene * kx * kx;
   for (int i = lane; i < kx; i += 32) {
-    const double dgn = G[i * kx + i];
+    const double dgn = G[i * kx + i] + (ridge ? ridge[i] : 0.0);
     sc[i] = dgn > 0.0 ? 1.0 / sqrt(dgn) : 0.0;
   }
   __syncwarp();
   bool bad = false;
   for (int e = lane; e < kx * kx; e += 32) {
     const int i = e / kx, j = e % kx;
-    L[i * ld + j] = G[e] * sc[i] * sc[j];
+    const double add = (ridge && i == j) ? ridge[i] : 0.0;
+    L[i * ld + j] = (G[e] + add) * sc[i] * sc[j];
   }
   for (int i = lane; i < kx; i += 32) {
     b[i] = rhs[(size_t)gene * kx + i] * sc[i];
@@ -350,6 +370,34 @@ __global__ void k_glm_consts(const double* __restrict__ Yt, long ldn, int n, con
     cst[(size_t)gene * 3 + 1] = s1;
     cst[(size_t)gene * 3 + 2] = s2;
   }
+}
+
+// list of genes still running (status == 0), in gene order (single CTA, deterministic)
+__global__ void k_glm_active_list(const int* __restrict__ status, int p, int* __restrict__ list, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i0 = 0; i0 < p; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const int flag = (i < p && status[i] == 0) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int pre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (flag) list[off + pre] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
 }
 
 // guards of causarray/gcate_glm.py:205
@@ -440,9 +488,12 @@ __global__ void k_disp_moments(const double* __restrict__ Yt, const double* __re
 
 template <int NT>
 static int launch_pass_nt(const GlmPass& P, cudaStream_t st) {
-  const size_t sm = sizeof(double) * ((size_t)2 * GLM_CHUNK * P.ldx + GLM_WARPS * P.ldx + 2 * GLM_CHUNK);
+  const size_t sm = sizeof(double) * ((size_t)2 * GLM_CHUNK * P.ldx + GLM_WARPS * P.ldx + 2 * GLM_CHUNK + FM_TABLE_DOUBLES);
   CA_CUDA(cudaFuncSetAttribute(k_glm_pass<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  const int grid = (P.p + GLM_WARPS - 1) / GLM_WARPS;
+  const int nslots = P.genelist ? P.n_list : P.p;
+  if (nslots <= 0) return 0;
+  const int grid = (nslots + GLM_WARPS - 1) / GLM_WARPS;
+  ProfScope prof(PROF_GLM_PASS, st);
   k_glm_pass<NT><<<grid, GLM_THREADS, sm, st>>>(P);
   CA_LAUNCH_CHECK();
   return 0;
@@ -515,6 +566,13 @@ extern "C" int ca_glm_share_counts(ca_glm_t h, ca_gcate_t g) {
 extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                           double thres_disp, int maxiter, double tol, int d_guard, double* B, double* dev,
                           int32_t* n_iter, int32_t* status) {
+  return ca_glm_fit_ex(h, family, X, kx, offset, nu, thres_disp, maxiter, tol, d_guard, nullptr, nullptr, B, dev, n_iter,
+                       status);
+}
+
+extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                             double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
+                             const uint8_t* gene_mask, double* B, double* dev, int32_t* n_iter, int32_t* status) {
   CA_REQUIRE(h && h->Yt && X && B, "load counts first");
   CA_REQUIRE(kx > 0 && kx <= 64, "design width must be in [1, 64]");
   CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
@@ -524,16 +582,33 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
       h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
       h->gram.alloc((size_t)p * kx * kx) || h->rhs.alloc((size_t)p * kx) || h->mu_t.alloc((size_t)p * h->ldn) ||
-      h->counter.alloc(1) || h->offset.alloc(n) || h->nu.alloc(p))
+      h->counter.alloc(2) || h->offset.alloc(n) || h->nu.alloc(p) || h->ridge.alloc(kx))
     return -1;
+  CA_REQUIRE(!gene_mask || h->fit_kx == kx, "gene_mask refit needs a previous fit of the same width");
+  h->fit_kx = kx;
   CA_CUDA(cudaMemsetAsync(h->X.ptr, 0, h->X.bytes(), st));
   CA_CUDA(cudaMemcpy2DAsync(h->X.ptr, sizeof(double) * ldx, X, sizeof(double) * kx, sizeof(double) * kx, n,
                             cudaMemcpyHostToDevice, st));
   if (offset) CA_CUDA(cudaMemcpyAsync(h->offset.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   if (nu) CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu, sizeof(double) * p, cudaMemcpyHostToDevice, st));
-  CA_CUDA(cudaMemsetAsync(h->beta.ptr, 0, h->beta.bytes(), st));
-  CA_CUDA(cudaMemsetAsync(h->status.ptr, 0, h->status.bytes(), st));
-  CA_CUDA(cudaMemsetAsync(h->n_iter.ptr, 0, h->n_iter.bytes(), st));
+  if (ridge) CA_CUDA(cudaMemcpyAsync(h->ridge.ptr, ridge, sizeof(double) * kx, cudaMemcpyHostToDevice, st));
+  if (gene_mask) {
+    // refit only the flagged genes; the others keep their coefficients and are frozen
+    std::vector<int> st0(p);
+    std::vector<double> hb((size_t)p * kx);
+    CA_CUDA(cudaMemcpy(hb.data(), h->beta.ptr, sizeof(double) * (size_t)p * kx, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < p; ++j) {
+      st0[j] = gene_mask[j] ? 0 : 1;
+      if (gene_mask[j])
+        for (int c = 0; c < kx; ++c) hb[(size_t)j * kx + c] = 0.0;
+    }
+    CA_CUDA(cudaMemcpy(h->beta.ptr, hb.data(), sizeof(double) * (size_t)p * kx, cudaMemcpyHostToDevice));
+    CA_CUDA(cudaMemcpy(h->status.ptr, st0.data(), sizeof(int) * p, cudaMemcpyHostToDevice));
+  } else {
+    CA_CUDA(cudaMemsetAsync(h->beta.ptr, 0, h->beta.bytes(), st));
+    CA_CUDA(cudaMemsetAsync(h->status.ptr, 0, h->status.bytes(), st));
+    CA_CUDA(cudaMemsetAsync(h->n_iter.ptr, 0, h->n_iter.bytes(), st));
+  }
   CA_CUDA(cudaMemsetAsync(h->dev_prev.ptr, 0, h->dev_prev.bytes(), st));
   h->has_offset = offset != nullptr;
   h->family = family;
@@ -567,13 +642,29 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
   P.tol = tol;
   P.finalize = 0;
   P.n_active = h->counter.ptr;
+  P.genelist = nullptr;
+  P.n_list = 0;
+  P.fm_tables = fastmath_tables();
+  CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
+  if (h->genelist.alloc(p)) return -1;
   const int solve_warps = 4;
   const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 2 * kx);
   CA_CUDA(cudaFuncSetAttribute(k_glm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_sm));
   int iters_done = 0;
+  int nrun = p;  // genes still running (gene_mask refits start from the flagged subset)
   for (int it = 1; it <= maxiter; ++it) {
     // pass `it` evaluates the deviance after update it-1 (convergence test of that update)
     // and, for genes still running, accumulates the normal equations of update `it`
+    if (it > 1 || gene_mask) {
+      k_glm_active_list<<<1, 1024, 0, st>>>(h->status.ptr, p, h->genelist.ptr, h->counter.ptr + 1);
+      CA_LAUNCH_CHECK();
+      if (gene_mask && it == 1) {
+        CA_CUDA(cudaMemcpyAsync(&nrun, h->counter.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CA_CUDA(cudaStreamSynchronize(st));
+      }
+      P.genelist = h->genelist.ptr;
+      P.n_list = nrun;
+    }
     CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int), st));
     P.iter = it;
     if (launch_pass(P, st)) return -1;
@@ -581,11 +672,18 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
     CA_CUDA(cudaMemcpyAsync(&nact, h->counter.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     CA_CUDA(cudaStreamSynchronize(st));
     if (nact == 0) break;
-    k_glm_solve<<<(p + solve_warps - 1) / solve_warps, solve_warps * 32, solve_sm, st>>>(
-        p, kx, h->gram.ptr, h->rhs.ptr, h->status.ptr, h->beta.ptr, it, h->n_iter.ptr);
-    CA_LAUNCH_CHECK();
+    {
+      ProfScope prof(PROF_GLM_SOLVE, st);
+      k_glm_solve<<<(p + solve_warps - 1) / solve_warps, solve_warps * 32, solve_sm, st>>>(
+          p, kx, h->gram.ptr, h->rhs.ptr, ridge ? h->ridge.ptr : nullptr, h->status.ptr, h->beta.ptr, it,
+          h->n_iter.ptr);
+      CA_LAUNCH_CHECK();
+    }
+    nrun = nact;
     iters_done = it;
   }
+  P.genelist = nullptr;
+  P.n_list = 0;
   // finalize: fitted means + deviance at the final beta for every gene
   P.finalize = 1;
   P.iter = iters_done + 1;
@@ -594,8 +692,10 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
   if (launch_pass(P, st)) return -1;
   h->iters_done = iters_done;
   // genes still "running" after maxiter updates: n_iter = maxiter
-  k_glm_guard<<<(p + 127) / 128, 128, 0, st>>>(p, kx, d_guard, h->beta.ptr, h->status.ptr);
-  CA_LAUNCH_CHECK();
+  if (d_guard >= 0) {
+    k_glm_guard<<<(p + 127) / 128, 128, 0, st>>>(p, kx, d_guard, h->beta.ptr, h->status.ptr);
+    CA_LAUNCH_CHECK();
+  }
   std::vector<int> hs(p), hi(p);
   CA_CUDA(cudaMemcpyAsync(B, h->beta.ptr, sizeof(double) * (size_t)p * kx, cudaMemcpyDeviceToHost, st));
   if (dev) CA_CUDA(cudaMemcpyAsync(dev, h->dev.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
@@ -625,6 +725,19 @@ extern "C" int ca_glm_resid(ca_glm_t h, double* resid) {
   CA_LAUNCH_CHECK();
   CA_CUDA(cudaMemcpyAsync(resid, out.ptr, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToHost, h->st));
   CA_CUDA(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+extern "C" int ca_glm_resid_device(ca_glm_t h, void** dev_ptr) {
+  CA_REQUIRE(h && h->mu_t.ptr && dev_ptr, "fit first");
+  const int n = h->n, p = h->p;
+  if (h->resid.alloc((size_t)n * p)) return -1;
+  dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+  k_glm_resid<<<grid, block, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, p, h->has_nu ? h->nu.ptr : nullptr, h->family,
+                                         h->thres, h->status.ptr, h->resid.ptr, p);
+  CA_LAUNCH_CHECK();
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  *dev_ptr = h->resid.ptr;
   return 0;
 }
 

@@ -15,6 +15,8 @@ struct RowProblem {
   const double* M;   // ncols x kpad
   int kpad;          // kpad % 8 == 4
   const double* nu;  // per column (nu_per_row = 0) or per row (nu_per_row = 1)
+  const double* inv_nu;  // 1/nu, same indexing
+  const double* log_nu;  // log(nu)
   int nu_per_row;
   int family;
   double thres_disp;
@@ -95,5 +97,9 @@ int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const
 // lam[i, c] = lam0 / (|X[i, lo + c]| + 1e-6)
 int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi, double lam0, double* lam,
                             int ldlam, cudaStream_t st);
+
+int launch_check_counts(const double* Y, long total, unsigned long long* flags, cudaStream_t st);
+int launch_size_factor_medians(const double* Yraw, long ldY, const double* Yraw_t, long ldn, int n, int p,
+                               double* log_geo, unsigned long long* scratch, double* out, cudaStream_t st);
 
 }  // namespace ca

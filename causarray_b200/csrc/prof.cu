@@ -1,0 +1,84 @@
+#include <vector>
+#include "../../include/causarray_b200.h"
+#include "common.cuh"
+#include "prof.h"
+
+namespace ca {
+
+long long g_launches = 0;
+static bool g_prof_on = false;
+struct Pending { int cls; cudaEvent_t e0, e1; };
+static std::vector<Pending> g_pending;
+static std::vector<cudaEvent_t> g_pool;
+static double g_ms[PROF_NCLASS] = {0};
+static long long g_cnt[PROF_NCLASS] = {0};
+static cudaEvent_t g_open[PROF_NCLASS];
+
+static cudaEvent_t get_event() {
+  if (!g_pool.empty()) {
+    cudaEvent_t e = g_pool.back();
+    g_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_open[cls] = get_event();
+  cudaEventRecord(g_open[cls], st);
+}
+void prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t e1 = get_event();
+  cudaEventRecord(e1, st);
+  g_pending.push_back({cls, g_open[cls], e1});
+}
+
+static void flush() {
+  for (auto& p : g_pending) {
+    cudaEventSynchronize(p.e1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      g_ms[p.cls] += ms;
+      g_cnt[p.cls] += 1;
+    }
+    g_pool.push_back(p.e0);
+    g_pool.push_back(p.e1);
+  }
+  g_pending.clear();
+}
+
+}  // namespace ca
+
+using namespace ca;
+
+extern "C" int ca_profile_enable(int on) {
+  flush();
+  g_prof_on = on != 0;
+  return 0;
+}
+extern "C" int ca_profile_reset(void) {
+  flush();
+  for (int i = 0; i < PROF_NCLASS; ++i) {
+    g_ms[i] = 0.0;
+    g_cnt[i] = 0;
+  }
+  return 0;
+}
+extern "C" int ca_profile_num_classes(void) { return PROF_NCLASS; }
+extern "C" const char* ca_profile_class_name(int cls) {
+  static const char* names[PROF_NCLASS] = {"rowpass_grad", "rowpass_ell", "search", "glm_pass", "glm_solve", "aipw",
+                                           "prep"};
+  return (cls >= 0 && cls < PROF_NCLASS) ? names[cls] : "";
+}
+extern "C" int ca_profile_get(int cls, double* total_ms, int64_t* launches) {
+  flush();
+  if (cls < 0 || cls >= PROF_NCLASS) return -2;
+  if (total_ms) *total_ms = g_ms[cls];
+  if (launches) *launches = g_cnt[cls];
+  return 0;
+}
+extern "C" int64_t ca_launch_count(void) { return (int64_t)g_launches; }

@@ -21,6 +21,8 @@
 // that the B-fragment loads of a half-warp hit 16 distinct bank pairs.
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
+#include "fastmath.cuh"
 
 namespace ca {
 
@@ -35,10 +37,14 @@ struct PassCfg {
   const double* M;
   int kpad;
   const double* nu;
+  const double* inv_nu;  // 1 / nu
+  const double* log_nu;  // log(nu)
   int nu_per_row;
   int family;
   double thres;
   int tc;  // columns per staged chunk (multiple of 8)
+  const double* fm_tables;
+  NbClip clip;
 };
 
 __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst) {
@@ -57,7 +63,7 @@ __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst
 // holds sum_col ell(y, theta) and, if GRAD, s_G[r*NGT*8 + c] holds
 // sum_col dl * M[col, gc_lo + c].
 template <bool GRAD, int NGT>
-__device__ void tile_pass(const PassCfg& P, const int* s_rows, const double* s_X, double* s_M,
+__device__ void tile_pass(const PassCfg& P, const FmTables& FT, const int* s_rows, const double* s_X, double* s_M,
                           double* s_red, double* s_Gred, int gc_lo, const unsigned char* s_skip,
                           double* s_rowsum, double* s_G) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -66,8 +72,12 @@ __device__ void tile_pass(const PassCfg& P, const int* s_rows, const double* s_X
   const int row = s_rows[lr];
   const bool rowok = (row >= 0) && !(s_skip && s_skip[lr]);
   const double* yrow = P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY;
-  const double nu_r = (P.nu_per_row && row >= 0) ? P.nu[row] : 1.0;
+  const bool row_nu = P.nu_per_row && row >= 0;
+  const double nu_r = row_nu ? P.nu[row] : 1.0;
+  const double inu_r = row_nu ? P.inv_nu[row] : 1.0;
+  const double lnu_r = row_nu ? P.log_nu[row] : 0.0;
   const bool pois_r = (P.family == CA_FAMILY_POISSON) || (P.nu_per_row && nu_r > P.thres);
+  const bool fam_nb = P.family == CA_FAMILY_NB;
   double ellsum = 0.0;
   double gacc[NGT][2];
 #pragma unroll
@@ -99,18 +109,34 @@ __device__ void tile_pass(const PassCfg& P, const int* s_rows, const double* s_X
 #pragma unroll 4
       for (int ks = 0; ks < KS; ++ks) dmma884(acc0, acc1, ap[ks * 4], bp[ks * 4]);
       const bool v0 = rowok && (col < P.ncols), v1 = rowok && (col + 1 < P.ncols);
-      double nu0 = nu_r, nu1 = nu_r;
-      bool p0 = pois_r, p1 = pois_r;
-      if (!P.nu_per_row && P.family == CA_FAMILY_NB) {
-        nu0 = v0 ? P.nu[col] : 1.0;
-        nu1 = v1 ? P.nu[col + 1] : 1.0;
-        p0 = nu0 > P.thres;
-        p1 = nu1 > P.thres;
+      double e0, e1, d0 = 0.0, d1 = 0.0;
+      if (fam_nb) {
+        double nu0 = nu_r, nu1 = nu_r, in0 = inu_r, in1 = inu_r, ln0 = lnu_r, ln1 = lnu_r;
+        bool p0 = pois_r, p1 = pois_r;
+        if (!P.nu_per_row) {
+          const int c0 = min(col, P.ncols - 1), c1 = min(col + 1, P.ncols - 1);
+          nu0 = P.nu[c0];
+          nu1 = P.nu[c1];
+          in0 = P.inv_nu[c0];
+          in1 = P.inv_nu[c1];
+          ln0 = P.log_nu[c0];
+          ln1 = P.log_nu[c1];
+          p0 = nu0 > P.thres;
+          p1 = nu1 > P.thres;
+        }
+        fm_entry<GRAD>(acc0, yv.x, nu0, in0, ln0, p0, FT, P.clip, e0, d0);
+        fm_entry<GRAD>(acc1, yv.y, nu1, in1, ln1, p1, FT, P.clip, e1, d1);
+      } else {
+        const double x0 = fmin(acc0, 100.0), x1 = fmin(acc1, 100.0);
+        const double m0 = fm_exp(fmax(x0, -700.0), FT.exp_t), m1 = fm_exp(fmax(x1, -700.0), FT.exp_t);
+        e0 = fma(yv.x, x0, -m0);
+        e1 = fma(yv.y, x1, -m1);
+        if (GRAD) {
+          d0 = m0 - yv.x;
+          d1 = m1 - yv.y;
+        }
       }
-      double e0 = 0.0, e1 = 0.0, d0 = 0.0, d1 = 0.0;
-      if (v0) entry_terms<GRAD>(acc0, yv.x, nu0, p0, e0, d0);
-      if (v1) entry_terms<GRAD>(acc1, yv.y, nu1, p1, e1, d1);
-      ellsum += e0 + e1;
+      ellsum += (v0 ? e0 : 0.0) + (v1 ? e1 : 0.0);
       if (GRAD) {
         if (!v0) d0 = 0.0;
         if (!v1) d1 = 0.0;
@@ -153,6 +179,7 @@ __device__ void tile_pass(const PassCfg& P, const int* s_rows, const double* s_X
 }
 
 struct Smem {
+  double* tab;    // FM_TABLE_DOUBLES
   double* M;      // 2 * tc * kpad + 64 slack
   double* X;      // 8 * kpad
   double* X0;     // 8 * kpad
@@ -165,6 +192,8 @@ struct Smem {
 
 __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, bool search) {
   Smem s;
+  s.tab = base;
+  base += FM_TABLE_DOUBLES;
   s.M = base;
   base += 2 * tc * kpad + 64;
   s.X = base;
@@ -183,7 +212,7 @@ __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, 
 }
 
 size_t rowpass_smem_bytes(int tc, int kpad, int ngt, bool search) {
-  size_t n = 2 * (size_t)tc * kpad + 64 + 8 * kpad + (search ? 16 * kpad : 0) + 64 + 8 + 64 * ngt * 8 + 8 * ngt * 8;
+  size_t n = FM_TABLE_DOUBLES + 2 * (size_t)tc * kpad + 64 + 8 * kpad + (search ? 16 * kpad : 0) + 64 + 8 + 64 * ngt * 8 + 8 * ngt * 8;
   return n * sizeof(double);
 }
 
@@ -203,6 +232,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rowpass(PassCfg P, const double* X
   const int total = rowlist ? *count : nrows;
   const int tile0 = blockIdx.x * TILE_ROWS;
   if (tile0 >= total) return;
+  const FmTables FT = fm_load_tables(S.tab, P.fm_tables);
   if (threadIdx.x < 8) {
     const int i = tile0 + threadIdx.x;
     s_rows[threadIdx.x] = (i < total) ? (rowlist ? rowlist[i] : i) : -1;
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(NTHREADS) k_rowpass(PassCfg P, const double* X
     S.X[e] = (row >= 0) ? X[(size_t)row * P.kpad + c] : 0.0;
   }
   __syncthreads();
-  tile_pass<GRAD, NGT>(P, s_rows, S.X, S.M, S.red, S.Gred, gc_lo, nullptr, S.rowsum, S.G);
+  tile_pass<GRAD, NGT>(P, FT, s_rows, S.X, S.M, S.red, S.Gred, gc_lo, nullptr, S.rowsum, S.G);
   if (threadIdx.x < 8 && s_rows[threadIdx.x] >= 0) ell_out[s_rows[threadIdx.x]] = S.rowsum[threadIdx.x];
   if (GRAD) {
     for (int e = threadIdx.x; e < 8 * NGT * 8; e += NTHREADS) {
@@ -271,6 +301,7 @@ __global__ void __launch_bounds__(NTHREADS) k_search(PassCfg P, SearchArgs A) {
   const int total = A.rowlist ? *A.count : A.nrows;
   const int tile0 = blockIdx.x * TILE_ROWS;
   if (tile0 >= total) return;
+  const FmTables FT = fm_load_tables(S.tab, P.fm_tables);
   const int kpad = P.kpad;
   if (tid < 8) {
     const int i = tile0 + tid;
@@ -307,7 +338,7 @@ __global__ void __launch_bounds__(NTHREADS) k_search(PassCfg P, SearchArgs A) {
       }
     }
     __syncthreads();
-    tile_pass<false, 1>(P, s_rows, S.X, S.M, S.red, S.Gred, 0, s_done, S.rowsum, S.G);
+    tile_pass<false, 1>(P, FT, s_rows, S.X, S.M, S.red, S.Gred, 0, s_done, S.rowsum, S.G);
     if (tid < 8 && !s_done[tid]) {
       const int row = s_rows[tid];
       double pen = 0.0;
@@ -384,6 +415,10 @@ static PassCfg make_cfg(const RowProblem& rp) {
   P.M = rp.M;
   P.kpad = rp.kpad;
   P.nu = rp.nu;
+  P.inv_nu = rp.inv_nu;
+  P.log_nu = rp.log_nu;
+  P.fm_tables = fastmath_tables();
+  P.clip = nb_clip_constants();
   P.nu_per_row = rp.nu_per_row;
   P.family = rp.family;
   P.thres = rp.thres_disp;
@@ -404,7 +439,9 @@ int launch_rowpass(const RowProblem& rp, const double* X, const int* rowlist, co
   CA_REQUIRE(rp.ldY % 8 == 0, "ldY must be a multiple of 8");
   if (nrows <= 0) return 0;
   PassCfg P = make_cfg(rp);
+  CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   const int grid = (nrows + TILE_ROWS - 1) / TILE_ROWS;
+  ProfScope prof(want_grad ? PROF_ROWPASS_GRAD : PROF_ROWPASS_ELL, st);
   if (!want_grad) {
     size_t sm = rowpass_smem_bytes(P.tc, P.kpad, 1, false);
     if (set_smem(k_rowpass<false, 1>, sm)) return -1;
@@ -434,6 +471,7 @@ int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st) 
   CA_REQUIRE(rp.kpad % 8 == 4, "kpad must be congruent to 4 mod 8");
   if (s.nrows <= 0) return 0;
   PassCfg P = make_cfg(rp);
+  CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   SearchArgs A;
   A.X = s.X;
   A.g = s.g;
@@ -458,6 +496,7 @@ int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st) 
   size_t sm = rowpass_smem_bytes(P.tc, P.kpad, 1, true);
   if (set_smem(k_search, sm)) return -1;
   const int grid = (s.nrows + TILE_ROWS - 1) / TILE_ROWS;
+  ProfScope prof(PROF_SEARCH, st);
   k_search<<<grid, NTHREADS, sm, st>>>(P, A);
   CA_LAUNCH_CHECK();
   return 0;

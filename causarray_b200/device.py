@@ -37,6 +37,26 @@ class GcateDevice:
         nu = None if nu is None else L.f64(np.ravel(nu))
         L.check(self.lib.ca_gcate_load_counts(self.h, L.dptr(Y), L.dptr(sf), L.dptr(nu)))
 
+    def upload_counts(self, Y, check=True):
+        """H2D of the raw counts; returns (#non-integer entries, #non-finite, #all-zero genes)."""
+        Y = L.f64(Y)
+        assert Y.shape == (self.n, self.p)
+        c = [ctypes.c_int64(0) for _ in range(3)]
+        refs = [ctypes.byref(x) for x in c] if check else [None, None, None]
+        L.check(self.lib.ca_gcate_upload_counts(self.h, L.dptr(Y), *refs))
+        return tuple(int(x.value) for x in c)
+
+    def size_factors(self):
+        """Median-of-ratios size factors (``comp_size_factor(method='geomeans')``) from the device copy."""
+        log_sf = np.empty(self.n)
+        L.check(self.lib.ca_gcate_size_factor_medians(self.h, L.dptr(log_sf)))
+        return np.exp(log_sf - np.mean(log_sf))
+
+    def prepare(self, size_factor=None, nu=None):
+        sf = None if size_factor is None else L.f64(np.ravel(size_factor))
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        L.check(self.lib.ca_gcate_prepare(self.h, L.dptr(sf), L.dptr(nu)))
+
     def load_normalized(self, Yn, Ys=None, nu=None):
         Yn = L.f64(Yn)
         Ys = None if Ys is None else L.f64(Ys)
@@ -140,21 +160,33 @@ class GlmDevice:
         self._keep = gcate  # the GCATE handle owns the device copy
         L.check(self.lib.ca_glm_share_counts(self.h, gcate.h))
 
-    def fit(self, family, X, offset=None, nu=None, thres_disp=100.0, maxiter=100, tol=1e-8, d_guard=None):
+    def fit(self, family, X, offset=None, nu=None, thres_disp=100.0, maxiter=100, tol=1e-8, d_guard=None,
+            ridge=None, gene_mask=None):
+        """IRLS fit of all genes.  ``d_guard=None`` disables the second coefficient bound,
+        ``d_guard=-1`` disables the guard altogether; ``ridge`` (kx,) / ``gene_mask`` (p,)
+        select the penalised refit of a gene subset (see ``ca_glm_fit_ex``)."""
         if family not in L.FAMILY:
             raise ValueError('Family not recognized')
         X = L.f64(X)
         kx = X.shape[1]
         off = None if offset is None else L.f64(np.ravel(offset))
         nu = None if nu is None else L.f64(np.ravel(nu))
+        rd = None if ridge is None else L.f64(np.ravel(ridge))
+        gm = None if gene_mask is None else np.ascontiguousarray(gene_mask, dtype=np.uint8)
         B = np.zeros((self.p, kx))
         dev = np.zeros(self.p)
         n_iter = np.zeros(self.p, dtype=np.int32)
         status = np.zeros(self.p, dtype=np.int32)
-        L.check(self.lib.ca_glm_fit(self.h, L.FAMILY[family], L.dptr(X), kx, L.dptr(off), L.dptr(nu),
-                                    float(thres_disp), int(maxiter), float(tol), int(kx if d_guard is None else d_guard),
-                                    L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
+        L.check(self.lib.ca_glm_fit_ex(self.h, L.FAMILY[family], L.dptr(X), kx, L.dptr(off), L.dptr(nu),
+                                       float(thres_disp), int(maxiter), float(tol),
+                                       int(kx if d_guard is None else d_guard), L.dptr(rd), L.u8ptr(gm),
+                                       L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
         return B, dev, n_iter, status
+
+    def resid_device_ptr(self):
+        ptr = ctypes.c_void_p()
+        L.check(self.lib.ca_glm_resid_device(self.h, ctypes.byref(ptr)))
+        return ptr.value
 
     def resid(self):
         out = np.empty((self.n, self.p))

@@ -1,0 +1,542 @@
+"""Doubly-robust (AIPW) log-fold-change estimation -- the S3 seam of SURVEY.md section 8(b).
+
+Interface of the reference's ``causarray/DR_estimation.py`` (``AIPW_mean``
+``:624-659``, ``cross_fitting`` ``:472-618``, ``estimate_propensity_scores``
+``:66-200``) and ``causarray/DR_learner.py`` (``compute_causal_estimand``
+``:32-269``, ``LFC`` ``:272-493``, ``gcate_lfc_batch`` ``:584-866``, ``LFC_batch``
+``:869-883``): same arguments, defaults, DataFrame columns and error behaviour.
+
+What differs by design: the (n, p, a, 2) tensors ``Y_hat`` and the pseudo-outcomes
+are never materialised on the fast path.  The outcome model is one joint GLM per
+gene, so ``Yhat_0 = exp(W b_cov + offset)`` and ``Yhat_1[k] = Yhat_0 * exp(b_trt[k])``;
+``ca_aipw_lfc`` recomputes them inside the fused reduction (``csrc/dr.cu``).
+``estimation['Y_hat']`` is therefore a lazy ``YhatFactors`` object (call
+``.materialize()`` for the dense tensor).  A user-supplied dense ``Y_hat`` goes
+through ``ca_aipw_lfc_yhat``.  Propensity scores stay on the host (sklearn
+lbfgs, as in the reference -- SURVEY.md section 2, row 7).
+"""
+import contextlib
+import gc
+import warnings
+from typing import Literal
+
+import numpy as np
+import pandas as pd
+from sklearn.linear_model import LogisticRegression
+from sklearn.model_selection import KFold
+
+from . import glm as _glm_mod
+from .device import GlmDevice, aipw_lfc, aipw_lfc_yhat
+from .inference import bh_correction, fdx_control
+from .prep import comp_size_factor, _filter_params, reset_random_seeds
+
+__version__ = "0.1.0"
+
+
+class YhatFactors:
+    """Factorised counterfactual predictions of the joint outcome GLM."""
+
+    def __init__(self, W, Bcov, Btrt, offset, cap=1e5):
+        self.W, self.Bcov, self.Btrt, self.offset, self.cap = W, Bcov, Btrt, offset, cap
+        self.shape = (W.shape[0], Bcov.shape[0], Btrt.shape[1], 2)
+
+    def materialize(self, dtype=np.float64):
+        eta0 = self.W @ self.Bcov.T
+        if self.offset is not None:
+            eta0 = eta0 + self.offset[:, None]
+        out = np.empty(self.shape, dtype=dtype)
+        with np.errstate(over='ignore'):
+            out[:, :, :, 0] = np.minimum(np.exp(eta0), self.cap)[:, :, None]
+            out[:, :, :, 1] = np.minimum(np.exp(eta0[:, :, None] + self.Btrt[None, :, :]), self.cap)
+        return out
+
+
+def AIPW_mean(Y, A, mu, pi):
+    """AIPW pseudo-outcomes ``A/pi (Y - mu) + mu`` and their float64 means.
+
+    ``Y (n, p)``, ``A, pi (n, a, 2)``, ``mu (n, p, a, 2)`` -> ``tau (p, a, 2)``,
+    ``pseudo_y (n, p, a, 2)``.  Compatibility helper for small inputs (it materialises
+    the 4-D tensor); ``LFC`` uses the fused device reduction instead.
+    """
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        w = (A / pi)[:, None, ...]
+    pseudo_y = w * (np.asarray(Y)[:, :, None, None] - mu) + mu
+    return np.mean(pseudo_y, axis=0, dtype=np.float64), pseudo_y
+
+
+def _validate_clip(clip):
+    msg = 'clip must be None or a pair 0 <= lower < upper <= 1'
+    if isinstance(clip, (str, bytes)) or np.ndim(clip) != 1:
+        raise ValueError(msg)
+    try:
+        lo, hi = (float(b) for b in clip)
+    except (TypeError, ValueError):
+        raise ValueError(msg) from None
+    if not 0 <= lo < hi <= 1:
+        raise ValueError(msg)
+    return lo, hi
+
+
+def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip=None, random_state=0,
+                               verbose=False, class_weight='balanced', **kwargs):
+    """Per-treatment logistic propensity scores against the shared all-zero control group.
+
+    Logistic model: no intercept, ``C = 1``, ``class_weight`` (default ``'balanced'``), fitted on
+    control plus case cells of each treatment; constant designs short-circuit to the class
+    prior.  ``K > 1`` yields out-of-fold predictions.
+    """
+    A = np.asarray(A)
+    if A.ndim == 1:
+        A = A[:, None]
+    X_A = np.asarray(X_A)
+    if A.ndim != 2 or X_A.ndim != 2 or A.shape[0] != X_A.shape[0]:
+        raise ValueError('A and X_A must be two-dimensional with matching rows')
+    if not np.all(np.isin(A, (0, 1))):
+        raise ValueError('A must contain only binary treatment indicators')
+    try:
+        K_int = int(K)
+    except (TypeError, ValueError) as exc:
+        raise ValueError('K must be a positive integer') from exc
+    if K_int != K or K_int < 1:
+        raise ValueError('K must be a positive integer')
+    K = K_int
+    if K > A.shape[0]:
+        raise ValueError('K cannot exceed the number of samples')
+    if mask is not None:
+        mask = np.asarray(mask, dtype=bool)
+        if mask.ndim == 1:
+            mask = mask[:, None]
+        if mask.shape != A.shape:
+            raise ValueError('Mask must have the same shape as the treatment matrix')
+    if ps_model != 'logistic':
+        raise ValueError('Invalid propensity score model.' if ps_model not in ('random_forest_cv', 'ensemble')
+                         else 'only the logistic propensity model is part of the accelerated path')
+    lr_kw = {**{'fit_intercept': False, 'C': 1e0, 'class_weight': class_weight, 'random_state': 0}, **kwargs}
+    lr_kw = _filter_params(LogisticRegression().get_params(), lr_kw)
+    n = A.shape[0]
+    if K == 1:
+        folds = [(np.arange(n), np.arange(n))]
+    elif K == n:
+        folds = [(np.delete(np.arange(n), j), np.array([j])) for j in range(n)]
+    else:
+        folds = KFold(n_splits=K, random_state=random_state, shuffle=True).split(X_A)
+    pi_hat = np.zeros(A.shape, dtype=float)
+    for tr, te in folds:
+        A_tr, X_tr, X_te = A[tr], X_A[tr], X_A[te]
+        ctrl = np.sum(A_tr, axis=1) == 0
+        for j in range(A.shape[1]):
+            elig = mask[tr, j] if mask is not None else (ctrl | (A_tr[:, j] == 1))
+            y = A_tr[elig, j]
+            if y.size == 0 or np.unique(y).size != 2:
+                raise ValueError(f'Treatment {j} needs at least one eligible control and case in every '
+                                 'training fold')
+            x = X_tr[elig]
+            if np.all(np.ptp(x, axis=0) == 0):
+                if class_weight == 'balanced':
+                    pi_hat[te, j] = 0.5
+                elif isinstance(class_weight, dict):
+                    sw = np.asarray([class_weight.get(int(v), 1.0) for v in y])
+                    pi_hat[te, j] = np.average(y, weights=sw)
+                else:
+                    pi_hat[te, j] = np.mean(y)
+            else:
+                pi_hat[te, j] = LogisticRegression(**lr_kw).fit(x, y).predict_proba(X_te)[:, 1]
+    if clip is not None:
+        lo, hi = _validate_clip(clip)
+        pi_hat = np.clip(pi_hat, lo, hi)
+    return pi_hat
+
+
+def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model='logistic',
+                  ps_class_weight='balanced', Y_hat=None, pi_hat=None, mask=None, ps_clip=(0.01, 0.99),
+                  return_raw_pi=False, verbose=False, _glm=None, **kwargs):
+    """Nuisance estimation: propensity scores and the outcome model.
+
+    Returns ``(Y_hat, pi_hat[, pi_hat_raw])``.  With ``K == 1`` (in-sample, the default of
+    ``LFC``) ``Y_hat`` is a ``YhatFactors`` object; with ``K > 1`` the folds are fitted one by
+    one and a dense ``(n, p, a, 2)`` tensor is returned, like the reference.
+    """
+    kwargs = dict(kwargs)
+    if 'class_weight' in kwargs:
+        warnings.warn('Passing class_weight through LFC/cross_fitting is deprecated; use ps_class_weight instead.',
+                      FutureWarning, stacklevel=2)
+        ps_class_weight = kwargs.pop('class_weight')
+    params_glm = _filter_params(_glm_mod.fit_glm, {**kwargs, 'verbose': verbose})
+    params_glm.pop('_glm', None)
+    params_glm.pop('_lazy', None)
+    A = np.asarray(A, dtype=float)
+    X = np.asarray(X, dtype=float)
+    n = X.shape[0]
+    if pi_hat is None:
+        ps_kwargs = {k: v for k, v in kwargs.items() if k != 'random_state'}
+        ps_kwargs = _filter_params(LogisticRegression().get_params(), ps_kwargs)
+        pi_hat_raw = estimate_propensity_scores(A, X_A, K=K, ps_model=ps_model, mask=mask,
+                                                random_state=kwargs.get('random_state', 0), verbose=verbose,
+                                                class_weight=ps_class_weight, **ps_kwargs)
+    else:
+        pi_hat_raw = np.asarray(pi_hat, dtype=float).reshape(A.shape)
+    if ps_clip is None:
+        pi_hat = pi_hat_raw.copy()
+    else:
+        if len(ps_clip) != 2 or not 0 <= ps_clip[0] < ps_clip[1] <= 1:
+            raise ValueError('ps_clip must be None or a pair 0 <= lower < upper <= 1')
+        pi_hat = np.clip(pi_hat_raw, ps_clip[0], ps_clip[1])
+    if Y_hat is None:
+        d = X.shape[1]
+        if K > 1:
+            Yn = np.asarray(Y, dtype=float)
+            if K >= n:
+                folds = [([i for i in range(n) if i != j], [j]) for j in range(n)]
+            else:
+                folds = KFold(n_splits=int(K), random_state=0, shuffle=True).split(X)
+            Y_hat = np.zeros((n, Yn.shape[1], A.shape[1], 2))
+            for tr, te in folds:
+                pg = dict(params_glm)
+                off_te = None
+                if isinstance(pg.get('offset'), np.ndarray):
+                    off_te = pg['offset'][te]
+                    pg['offset'] = pg['offset'][tr]
+                B = _glm_mod.fit_glm(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True, **pg)[0]
+                Y_hat[te] = YhatFactors(X[te], B[:, :d], B[:, d:], off_te, cap=np.inf).materialize()
+            Y_hat = np.clip(Y_hat, None, 1e5)
+        else:
+            B, fit, disp, offsets, _ = _glm_mod.fit_glm(Y, X, A, family=family, alpha=glm_alpha, _glm=_glm,
+                                                        _lazy=True, **params_glm)
+            Y_hat = YhatFactors(X, np.ascontiguousarray(B[:, :d]), np.ascontiguousarray(B[:, d:]), offsets)
+            Y_hat.disp_glm = disp
+            Y_hat.glm = fit.dev
+    elif not isinstance(Y_hat, YhatFactors):
+        Y_hat = np.clip(Y_hat, None, 1e5)
+    if return_raw_pi:
+        return Y_hat, pi_hat, pi_hat_raw
+    return Y_hat, pi_hat
+
+
+def _add_log2fc_columns(df_res):
+    """(Re)compute ``log2fc`` / ``log2fc_se`` right after ``std`` as exact rescalings of ``tau`` / ``std``."""
+    ln2 = np.log(2.0)
+    l2, l2se = df_res['tau'].to_numpy() / ln2, df_res['std'].to_numpy() / ln2
+    for name in ('log2fc', 'log2fc_se'):
+        if name in df_res.columns:
+            df_res.pop(name)
+    at = df_res.columns.get_loc('std') + 1
+    df_res.insert(at, 'log2fc', l2)
+    df_res.insert(at + 1, 'log2fc_se', l2se)
+    return df_res
+
+
+def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=False, Y_hat=None, pi_hat=None,
+                            mask=None, fdx=False, fdx_B=1000, fdx_alpha=0.05, fdx_c=0.1, verbose=False,
+                            random_state=0, backend: str = "auto", K=1, ps_clip=(0.01, 0.99),
+                            ps_class_weight='balanced', _glm=None, _trusted=False, **kwargs):
+    """AIPW estimation of a causal estimand for every (treatment, gene) pair.
+
+    ``estimand`` is either the string ``'LFC'`` together with ``_lfc_opts`` in ``kwargs`` (the
+    fused device path used by :func:`LFC`) or a callable ``(etas, A) -> (eta_est, tau, var[, df,
+    info])`` as in the reference, which needs the dense pseudo-outcomes and is meant for small
+    problems.
+    """
+    reset_random_seeds(random_state)
+    if 'clip_pseudo_outcomes' in kwargs:
+        raise TypeError('clip_pseudo_outcomes has been removed; AIPW pseudo-outcomes are always left unclipped')
+    lfc_opts = kwargs.pop('_lfc_opts', None)
+    ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
+    if isinstance(Y, pd.DataFrame):
+        gene_names = Y.columns
+        Y = Y.values
+    else:
+        gene_names = range(Y.shape[1])
+    Y = np.asarray(Y).astype(float, copy=False)
+    n, p = Y.shape
+    # (_trusted: the counts were already validated on the device when the workspace was uploaded)
+    if not _trusted and not np.all(np.isfinite(Y)):
+        raise ValueError('Y must contain only finite values')
+    if len(A.shape) == 1:
+        A = A.reshape(-1, 1)
+    if isinstance(A, pd.DataFrame):
+        trt_names = A.columns
+        A = A.values
+    else:
+        trt_names = range(A.shape[1])
+    A = np.asarray(A, dtype=float)
+    if isinstance(W, pd.DataFrame):
+        W = W.values
+    if W_A is None:
+        W_A = W
+    elif isinstance(W_A, pd.DataFrame):
+        W_A = W_A.values
+    if mask is not None:
+        mask = np.array(mask).astype(bool)
+        if len(mask.shape) == 1:
+            mask = mask.reshape(-1, 1)
+        if mask.shape != A.shape:
+            raise ValueError('Mask must have the same shape as the treatment matrix')
+    kwargs = {k: v for k, v in kwargs.items()
+              if k not in ['kwargs_ls_1', 'kwargs_ls_2', 'kwargs_es_1', 'kwargs_es_2', 'c1', 'num_d']}
+    if offset is not None and offset is not False:
+        if type(offset) == bool and offset is True:
+            size_factors = comp_size_factor(Y, **_filter_params(comp_size_factor, kwargs))
+            offset = np.log(size_factors)
+        else:
+            size_factors = np.exp(offset)
+    else:
+        offset = None
+        size_factors = np.ones(n)
+    size_factors = np.asarray(size_factors, dtype=float)
+    if size_factors.shape != (n,) or not np.all(np.isfinite(size_factors)) or np.any(size_factors <= 0):
+        raise ValueError('Size factors must be finite, positive, and have length n')
+    if _glm is None and Y_hat is None:
+        _glm = GlmDevice(n, p)
+        _glm.load_counts(Y)
+    with ctx:
+        Y_hat, pi_hat, pi_hat_raw = cross_fitting(
+            Y, A, W, W_A, family=family, K=K, offset=offset, Y_hat=Y_hat, pi_hat=pi_hat, mask=mask,
+            ps_clip=ps_clip, ps_class_weight=ps_class_weight, return_raw_pi=True, random_state=random_state,
+            verbose=verbose, _glm=_glm, **kwargs)
+    pi_hat = pi_hat.reshape(*A.shape)
+    dense = not isinstance(Y_hat, YhatFactors)
+    if dense and not np.all(np.isfinite(Y_hat)):
+        raise ValueError('Outcome-model predictions must contain only finite values')
+    if not dense and not (np.all(np.isfinite(Y_hat.Bcov)) and np.all(np.isfinite(Y_hat.Btrt))):
+        raise ValueError('Outcome-model predictions must contain only finite values')
+    if not np.all(np.isfinite(pi_hat)) or np.any((pi_hat <= 0) | (pi_hat >= 1)):
+        raise ValueError('Propensity scores used by AIPW must be finite and strictly between 0 and 1; '
+                         'pass ps_clip bounds or provide valid pi_hat values')
+
+    per_trt = []
+    if lfc_opts is not None:
+        cm = None if mask is None else mask.astype(np.uint8)
+        if dense:
+            out = aipw_lfc_yhat(Y, np.asarray(Y_hat, dtype=float), size_factors, A, pi_hat, cell_mask=cm, **lfc_opts)
+        else:
+            out = aipw_lfc(Y, Y_hat.W, Y_hat.Bcov, Y_hat.Btrt, Y_hat.offset, size_factors, A, pi_hat,
+                           cell_mask=cm, glm=getattr(Y_hat, 'glm', None) or _glm, **lfc_opts)
+        ctrl = np.sum(A, axis=1) == 0.
+        for j in range(A.shape[1]):
+            cells = mask[:, j] if mask is not None else (ctrl | (A[:, j] == 1.))
+            n0, n1 = int(np.sum(A[cells, j] == 0)), int(np.sum(A[cells, j] == 1))
+            if lfc_opts['usevar'] == 'unequal' and (n0 < 2 or n1 < 2):
+                warnings.warn(f"Welch variance requires at least 2 cells per arm; got n_0={n0}, n_1={n1} for this "
+                              "perturbation. Per-gene variance and df will be NaN; results for these genes are "
+                              "silently dropped by downstream BH correction. Pass ``usevar='pooled'`` if you need "
+                              "finite estimates in this regime.", RuntimeWarning, stacklevel=3)
+            df_eff = out['df'][j] if lfc_opts['usevar'] == 'unequal' else None
+            info = {'mean_control': out['mean0'][j], 'mean_treated': out['mean1'][j],
+                    'estimable': out['estimable'][j]}
+            if df_eff is not None:
+                filt = np.isinf(out['var'][j])
+                silent = int(np.sum(np.isnan(df_eff) & ~filt))
+                if silent > 0:
+                    warnings.warn(f"{silent} gene(s) produced NaN Welch df despite passing the low-expression "
+                                  "filter; these will be reported as NaN p-values in the result DataFrame.",
+                                  RuntimeWarning, stacklevel=3)
+            per_trt.append((None, out['tau'][j].copy(), out['var'][j].copy(), df_eff, info))
+    else:
+        mu = Y_hat if dense else Y_hat.materialize()
+        _, etas = AIPW_mean(Y, np.stack([1 - A, A], axis=-1), mu, np.stack([1 - pi_hat, pi_hat], axis=-1))
+        etas /= size_factors[:, None, None, None]
+        ctrl = np.sum(A, axis=1) == 0.
+        for j in range(A.shape[1]):
+            cells = mask[:, j] if mask is not None else (ctrl | (A[:, j] == 1.))
+            ret = estimand(etas[cells, :, j], A[cells, j], **kwargs)
+            per_trt.append((ret[0], ret[1], ret[2], ret[3] if len(ret) > 3 else None,
+                            ret[4] if len(ret) > 4 else None))
+
+    frames = []
+    for j, (eta_est, tau_est, var_est, df_est, info) in enumerate(per_trt):
+        with np.errstate(invalid='ignore', divide='ignore'):
+            std_est = np.sqrt(var_est)
+            tvals = tau_est / std_est
+        if fdx:
+            if eta_est is None:
+                raise NotImplementedError('fdx=True needs the dense influence values; pass a callable estimand')
+            V = fdx_control(tau_est, tvals, eta_est, std_est, fdx, fdx_B, fdx_alpha, fdx_c)
+        else:
+            V = np.zeros(tvals.shape[0])
+        tvals[np.isinf(std_est)] = np.nan
+        pv, qv, pva, qva = bh_correction(tvals, df=df_est)
+        df_res = pd.DataFrame({'gene_names': gene_names, 'tau': tau_est, 'std': std_est, 'stat': tvals, 'rej': V,
+                               'pvalue': pv, 'padj': qv, 'pvalue_emp_null_adj': pva, 'padj_emp_null_adj': qva})
+        if info is not None:
+            for name, values in info.items():
+                df_res[name] = values
+            n_bad = int(np.sum(~np.asarray(info['estimable'], dtype=bool)))
+            if n_bad:
+                trt = trt_names[j] if A.shape[1] > 1 else 0
+                warnings.warn(f'{n_bad} gene(s) for treatment {trt!r} have nonfinite or nonpositive AIPW '
+                              'counterfactual means and are reported as non-estimable.', RuntimeWarning,
+                              stacklevel=2)
+        if A.shape[1] > 1:
+            df_res['trt'] = trt_names[j]
+        frames.append(df_res)
+    df_res = pd.concat(frames, axis=0).reset_index(drop=True)
+    estimation = {**{'pi_hat': pi_hat, 'pi_hat_raw': pi_hat_raw, 'Y_hat': Y_hat, 'offset': offset,
+                     'size_factors': size_factors, 'ps_class_weight': ps_class_weight}, **kwargs}
+    return df_res, estimation
+
+
+def LFC(Y, W, A, W_A=None, family='nb', offset=False, Y_hat=None, pi_hat=None, cross_est=False, K=None,
+        mask=None, usevar: Literal['unequal', 'pooled'] = 'unequal', thres_min=1e-2, thres_diff=1e-2,
+        eps_var=1e-4, fdx=False, fdx_alpha=0.05, fdx_c=0.1, verbose=False, backend: str = "auto",
+        ps_clip=(0.01, 0.99), ps_class_weight='balanced', **kwargs):
+    """Doubly-robust log-fold changes ``log E[Y(1)] / E[Y(0)]`` with Welch (``'unequal'``) or pooled
+    variance, low-expression filter, t / BH inference.
+
+    Returns ``(df, estimation)``; ``df`` columns in order: ``gene_names, tau, std, log2fc,
+    log2fc_se, stat, rej, pvalue, padj, pvalue_emp_null_adj, padj_emp_null_adj, mean_control,
+    mean_treated, estimable[, trt]``.
+    """
+    if usevar not in ('pooled', 'unequal'):
+        raise ValueError('usevar must be either "pooled" or "unequal"')
+    if K is None:
+        K = 2 if cross_est else 1
+    opts = dict(usevar=usevar, thres_min=thres_min, thres_diff=thres_diff, eps_var=eps_var)
+    if fdx:
+        # FDX needs the per-cell influence values: dense reference-style estimand (small problems)
+        estimand = _dense_lfc_estimand(**opts)
+        df_res, estimation = compute_causal_estimand(
+            estimand, Y, W, A, W_A, family, offset, Y_hat=Y_hat, pi_hat=pi_hat, mask=mask, fdx=fdx,
+            fdx_alpha=fdx_alpha, fdx_c=fdx_c, verbose=verbose, backend=backend, K=K, ps_clip=ps_clip,
+            ps_class_weight=ps_class_weight, **kwargs)
+    else:
+        df_res, estimation = compute_causal_estimand(
+            'LFC', Y, W, A, W_A, family, offset, Y_hat=Y_hat, pi_hat=pi_hat, mask=mask, fdx=False,
+            fdx_alpha=fdx_alpha, fdx_c=fdx_c, verbose=verbose, backend=backend, K=K, ps_clip=ps_clip,
+            ps_class_weight=ps_class_weight, _lfc_opts=opts, **kwargs)
+    return _add_log2fc_columns(df_res), estimation
+
+
+def _dense_lfc_estimand(usevar, thres_min, thres_diff, eps_var):
+    """Host estimand on dense pseudo-outcomes (only used when ``fdx=True``)."""
+    def estimand(etas, A, **kw):
+        e0, e1 = etas[..., 0], etas[..., 1]
+        m0, m1 = np.mean(e0, axis=0, dtype=np.float64), np.mean(e1, axis=0, dtype=np.float64)
+        est = np.isfinite(m0) & np.isfinite(m1) & (m0 > 0) & (m1 > 0)
+        t0 = np.where(est, np.maximum(m0, thres_diff), 1.0)
+        t1 = np.where(est, np.maximum(m1, thres_diff), 1.0)
+        with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+            tau = np.log(t1 / t0)
+            IF = e1 / t1[None, :] - e0 / t0[None, :]
+        df_eff = None
+        if usevar == 'pooled':
+            var = (np.var(IF, axis=0, ddof=1) + eps_var) / IF.shape[0]
+        else:
+            n0, n1 = int(np.sum(A == 0)), int(np.sum(A == 1))
+            with np.errstate(invalid='ignore', divide='ignore'):
+                v0 = (np.var(IF[A == 0], axis=0, ddof=1) + eps_var) / n0
+                v1 = (np.var(IF[A == 1], axis=0, ddof=1) + eps_var) / n1
+                var = v0 + v1
+                df_eff = (v0 + v1) ** 2 / (v0 ** 2 / (n0 - 1) + v1 ** 2 / (n1 - 1))
+        drop = ~est | (np.maximum(m0, m1) < thres_min) | (np.abs(m1 - m0) < thres_diff)
+        tau[drop] = 0.
+        IF[:, drop] = 0.
+        var[drop] = np.inf
+        if df_eff is not None:
+            df_eff[drop] = np.nan
+        return IF, tau, var, df_eff, {'mean_control': m0, 'mean_treated': m1, 'estimable': est}
+    return estimand
+
+
+def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cells=2000, n_ctrl=2000,
+                    family='nb', offset=True, warm_start_U=False, cache_path=None, random_state=0, verbose=False,
+                    gcate_kwargs=None, lfc_kwargs=None, **kwargs):
+    """Batch-wise GCATE + doubly-robust LFC over chunks of perturbations.
+
+    Same call and result as the reference (rows batch-major, then treatment-major, then gene
+    order; columns of :func:`LFC` plus ``trt`` and ``batch``; optional resumable HDF5 cache).
+    The counts of each batch are uploaded once and stay on the device through the GCATE fit,
+    the outcome GLM and the AIPW reduction.
+    """
+    from .estimators import _dense_counts
+    gcate_kwargs = {} if gcate_kwargs is None else gcate_kwargs
+    lfc_kwargs = {} if lfc_kwargs is None else lfc_kwargs
+    gene_names = list(Y.columns) if isinstance(Y, pd.DataFrame) else None
+    Y_np = _dense_counts(Y)
+    X_np = np.asarray(X)
+    W_A_np = np.asarray(W_A) if W_A is not None else None
+    if isinstance(A, pd.DataFrame):
+        A_np = A.values.astype(float)
+        names = list(A.columns)
+    else:
+        A_np = np.asarray(A, dtype=float)
+        names = list(range(A_np.shape[1]))
+    cached, skip = {}, set()
+    if cache_path is not None:
+        meta = None
+        try:
+            with pd.HDFStore(cache_path, mode='r') as store:
+                keys = store.keys()
+                if '/meta' in keys:
+                    meta = store['/meta']
+                for key in keys:
+                    if key.startswith('/batch_'):
+                        try:
+                            idx = int(key.split('_')[1])
+                            cached[idx] = key
+                            skip.add(idx)
+                        except (ValueError, IndexError):
+                            pass
+        except (FileNotFoundError, OSError):
+            pass
+        if meta is not None:
+            for k_, v_ in {'family': family, 'a_total': int(A_np.shape[1])}.items():
+                if k_ in meta.columns and meta.iloc[0][k_] != v_:
+                    raise ValueError(f"gcate_lfc_batch cache at {cache_path!r} was written with "
+                                     f"{k_}={meta.iloc[0][k_]!r}, but the current call uses {k_}={v_!r}.  Refusing "
+                                     "to mix incompatible schemas -- delete the cache file or pass a fresh "
+                                     "cache_path to start over.")
+    col_of = {name: i for i, name in enumerate(names)}
+    new = {}
+    # one batch at a time: GCATE fit -> LFC on the same device-resident counts
+    from .estimators import iter_gcate_batches
+    for br in iter_gcate_batches(Y_np, X_np, A, r, batch_size=batch_size, n_batches=n_batches, max_cells=max_cells,
+                                 n_ctrl=n_ctrl, family=family, offset=offset, warm_start_U=warm_start_U,
+                                 skip_batches=skip, random_state=random_state, verbose=verbose,
+                                 **{**kwargs, **gcate_kwargs}):
+        if br.get('skipped'):
+            continue
+        batch_i, cell_idx, res_2 = br['batch_i'], br['cell_idx'], br['res_2']
+        ws = res_2.pop('_ws', None)
+        U_b = res_2['U'].copy()
+        off_b = np.log(res_2['kwargs_glm']['size_factor'])
+        Y_b_np = Y_np[cell_idx]
+        Y_b = pd.DataFrame(Y_b_np, columns=gene_names) if gene_names is not None else Y_b_np
+        X_b = X_np[cell_idx]
+        cols = [col_of[name] for name in br['pert_names']]
+        A_b = A_np[np.ix_(cell_idx, cols)]
+        W_b = np.c_[X_b, U_b]
+        W_A_b = np.c_[W_A_np[cell_idx], U_b] if W_A_np is not None else W_b
+        df_b, est_b = LFC(Y_b, W_b, pd.DataFrame(A_b, columns=br['pert_names']), W_A_b, family=family,
+                          offset=off_b, verbose=verbose, _glm=None if ws is None else ws.glm,
+                          _trusted=ws is not None, **{**kwargs, **lfc_kwargs})
+        df_b['batch'] = batch_i
+        new[batch_i] = df_b
+        if cache_path is not None:
+            with pd.HDFStore(cache_path, mode='a') as store:
+                if '/meta' not in store.keys():
+                    store.put('/meta', pd.DataFrame({'causarray_version': [__version__], 'family': [family],
+                                                     'a_total': [int(A_np.shape[1])],
+                                                     'columns': [','.join(df_b.columns.astype(str))]}),
+                              format='fixed')
+                store.put(f'batch_{batch_i:04d}', df_b, format='fixed')
+        del est_b
+        if ws is not None:
+            ws.close()
+        br['res_1'] = None
+        br['res_2'] = None
+        gc.collect()
+    idx_all = sorted(set(new) | set(cached))
+    if cached and cache_path is not None:
+        with pd.HDFStore(cache_path, mode='r') as store:
+            frames = [new[i] if i in new else store[cached[i]] for i in idx_all]
+            result = pd.concat(frames, axis=0).reset_index(drop=True)
+    else:
+        result = pd.concat([new[i] for i in idx_all], axis=0).reset_index(drop=True)
+    return _add_log2fc_columns(result)
+
+
+def LFC_batch(*args, **kwargs):
+    """Deprecated alias of :func:`gcate_lfc_batch`."""
+    warnings.warn("LFC_batch is deprecated and will be removed in a future release. Use gcate_lfc_batch instead.",
+                  DeprecationWarning, stacklevel=2)
+    return gcate_lfc_batch(*args, **kwargs)

@@ -45,6 +45,19 @@ int ca_gcate_destroy(ca_gcate_t h);
  * Tys = -lgamma(Y+1) [+ lgamma(nu+Y) - lgamma(nu)] sums on the device
  * (causarray/gcate_opt.py:343-347) and the per-gene zero fraction (:305). */
 int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu);
+/* The same in three steps, so that the input checks of fit_gcate
+ * (causarray/gcate.py:12-17: integer-valued, no all-zero gene) and the
+ * median-of-ratios size factors (causarray/utils.py:179-219) run on the device
+ * copy instead of as host passes:
+ *   upload:  H2D of the raw counts (+ transpose); optionally counts entries
+ *            that are not integer-valued / not finite and genes that are empty
+ *   size_factor_medians: log_sf[i] = median_j (log Y_ij - mean_i' log Y_i'j) over
+ *            expressed genes (the caller centres and exponentiates, utils.py:213)
+ *   prepare: normalisation by the size factors + constant-term sums. */
+int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
+                           int64_t* n_empty_genes);
+int ca_gcate_size_factor_medians(ca_gcate_t h, double* log_sf);
+int ca_gcate_prepare(ca_gcate_t h, const double* size_factor, const double* nu);
 /* Same, for callers of update_with_mask that already hold the normalised Y
  * and the Ys matrix (both n x p); Ys may be NULL (recomputed from nu). */
 int ca_gcate_load_normalized(ca_gcate_t h, const double* Yn, const double* Ys, const double* nu);
@@ -130,8 +143,21 @@ int ca_glm_share_counts(ca_glm_t h, ca_gcate_t g);
 int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                double thres_disp, int maxiter, double tol, int d_guard, double* B, double* dev, int32_t* n_iter,
                int32_t* status);
+/* Extended fit: ridge (kx) is added to the diagonal of every gene's normal
+ * equations (penalised IRLS; the device-side stand-in for the reference's
+ * regularised fallback, gcate_glm.py:209); gene_mask (p, uint8) restricts the
+ * fit to the flagged genes -- the others keep the coefficients of the previous
+ * fit of the same width.  Either may be NULL. */
+int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                  double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
+                  const uint8_t* gene_mask, double* B, double* dev, int32_t* n_iter, int32_t* status);
 /* Signed deviance residuals of the last fit, (n x p). */
 int ca_glm_resid(ca_glm_t h, double* resid);
+/* Same residual matrix left on the device: *dev_ptr receives a DEVICE pointer
+ * to (n x p) row-major doubles owned by the handle (valid until the next
+ * call on it).  Used to run the initial top-r SVD (gcate_opt.py:312) without
+ * a host round trip. */
+int ca_glm_resid_device(ca_glm_t h, void** dev_ptr);
 /* Fitted means of the last fit, (n x p). */
 int ca_glm_fitted(ca_glm_t h, double* mu);
 /* Method-of-moments NB size from the last (Poisson) fit (gcate_glm.py:301-306). */
@@ -170,6 +196,20 @@ int ca_aipw_lfc_shared(ca_glm_t h, int kw, int a, const double* W, const double*
 int ca_aipw_lfc_yhat(int n, int p, int a, const double* Y, const double* Yhat, const double* size_factor,
                      const double* A, const double* pi, const uint8_t* cell_mask, const ca_lfc_params* prm,
                      double* mean0, double* mean1, double* tau, double* var, double* df, uint8_t* estimable);
+
+/* ------------------------------------------------------------------------
+ * Measurement hooks (bench.py): per-kernel-class device time from CUDA events
+ * recorded on the launching stream, and the number of kernels launched so far.
+ * ------------------------------------------------------------------------ */
+int ca_profile_enable(int on);
+int ca_profile_reset(void);
+int ca_profile_num_classes(void);
+const char* ca_profile_class_name(int cls);
+int ca_profile_get(int cls, double* total_ms, int64_t* launches);
+int64_t ca_launch_count(void);
+/* Test hook: out[i] = fm_exp(x[i]) (op 0, -700 <= x <= 100) or fm_log(x[i]) (op 1, x > 0 normal),
+ * the table-driven FP64 functions of csrc/fastmath.cuh. */
+int ca_test_fastmath(const double* x, int n, int op, double* out);
 
 #ifdef __cplusplus
 }
