@@ -10,7 +10,7 @@ import time
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcausarray_b200.so")
+LIB_PATH = os.environ.get("CAUSARRAY_B200_LIB", os.path.join(_HERE, "libcausarray_b200.so"))
 
 FAMILY = {"poisson": 0, "nb": 1}
 

@@ -32,12 +32,10 @@ const double* fastmath_tables() {
 
 NbClip nb_clip_constants() {
   NbClip c;
-  c.u_hi = 1e6 - 1.0;
   c.u_lo = 1.0 / (1.0 - 1e-6) - 1.0;
-  c.l1p_hi = log1p(-1e-6);
-  c.lq_hi = log(1e-6);
-  c.l1p_lo = log1p(-(1.0 - 1e-6));
-  c.lq_lo = log(1.0 - 1e-6);
+  c.u_hi = 1e6 - 1.0;
+  c.lu_lo = log(c.u_lo);
+  c.lu_hi = log(c.u_hi);
   return c;
 }
 

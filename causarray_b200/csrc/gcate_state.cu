@@ -46,7 +46,7 @@ using namespace ca;
 static int gcate_alloc(ca_gcate* h) {
   const int n = h->n, p = h->p, kp = h->kpad;
   if (h->Yn.alloc((size_t)n * h->ldp) || h->Ynt.alloc((size_t)p * h->ldn)) return -1;
-  if (h->nu.alloc(p) || h->inv_nu.alloc(p) || h->log_nu.alloc(p) || h->tys_row.alloc(n) || h->tys_col.alloc(p) || h->tys_total.alloc(1) || h->sparsity.alloc(p))
+  if (h->nu.alloc(p) || h->inv_nu.alloc(p) || h->log_nu.alloc(p) || h->colparm.alloc((size_t)4 * p) || h->tys_row.alloc(n) || h->tys_col.alloc(p) || h->tys_total.alloc(1) || h->sparsity.alloc(p))
     return -1;
   if (h->A.alloc((size_t)n * kp) || h->B.alloc((size_t)p * kp) || h->Aprev.alloc((size_t)n * kp) ||
       h->Bprev.alloc((size_t)p * kp))
@@ -128,11 +128,16 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
     ones.assign(p, 1.0);
     nu_host = ones.data();
   }
-  std::vector<double> hin(p), hln(p);
+  std::vector<double> hin(p), hln(p), hcp((size_t)4 * p);
   for (int j = 0; j < p; ++j) {
     hin[j] = 1.0 / nu_host[j];
     hln[j] = std::log(nu_host[j]);
+    hcp[4 * j + 0] = nu_host[j];
+    hcp[4 * j + 1] = hin[j];
+    hcp[4 * j + 2] = hln[j];
+    hcp[4 * j + 3] = (nu_host[j] > h->thres) ? 1.0 : 0.0;
   }
+  CA_CUDA(cudaMemcpyAsync(h->colparm.ptr, hcp.data(), sizeof(double) * 4 * p, cudaMemcpyHostToDevice, h->st));
   CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu_host, sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
   CA_CUDA(cudaMemcpyAsync(h->inv_nu.ptr, hin.data(), sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
   CA_CUDA(cudaMemcpyAsync(h->log_nu.ptr, hln.data(), sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
@@ -329,6 +334,7 @@ static RowProblem cell_problem(ca_gcate* h) {
   rp.nu = h->nu.ptr;
   rp.inv_nu = h->inv_nu.ptr;
   rp.log_nu = h->log_nu.ptr;
+  rp.colparm = h->colparm.ptr;
   rp.nu_per_row = 0;
   rp.family = h->family;
   rp.thres_disp = h->thres;
@@ -344,6 +350,7 @@ static RowProblem gene_problem(ca_gcate* h) {
   rp.nu = h->nu.ptr;
   rp.inv_nu = h->inv_nu.ptr;
   rp.log_nu = h->log_nu.ptr;
+  rp.colparm = nullptr;
   rp.nu_per_row = 1;
   rp.family = h->family;
   rp.thres_disp = h->thres;

@@ -12,7 +12,7 @@ struct ca_gcate {
   double thres;
   long ldp, ldn;
   cudaStream_t st;
-  DevBuf<double> Yn, Ynt, nu, inv_nu, log_nu, tys_row, tys_col, tys_total, sparsity;
+  DevBuf<double> Yn, Ynt, nu, inv_nu, log_nu, colparm, tys_row, tys_col, tys_total, sparsity;
   DevBuf<double> A, B, Aprev, Bprev;
   DevBuf<double> P1, P2, lam, alpha_gene;
   int d1 = 0, r2 = 0, a = 0;

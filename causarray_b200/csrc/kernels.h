@@ -17,6 +17,7 @@ struct RowProblem {
   const double* nu;  // per column (nu_per_row = 0) or per row (nu_per_row = 1)
   const double* inv_nu;  // 1/nu, same indexing
   const double* log_nu;  // log(nu)
+  const void* colparm;   // per column (nu, 1/nu, log nu, poisson flag) as double4, for nu_per_row = 0
   int nu_per_row;
   int family;
   double thres_disp;

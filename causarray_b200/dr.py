@@ -437,6 +437,15 @@ def _dense_lfc_estimand(usevar, thres_min, thres_diff, eps_var):
     return estimand
 
 
+def _cache_put(cache_path, batch_i, df_b, family, a_total):
+    with pd.HDFStore(cache_path, mode='a') as store:
+        if '/meta' not in store.keys():
+            store.put('/meta', pd.DataFrame({'causarray_version': [__version__], 'family': [family],
+                                             'a_total': [a_total],
+                                             'columns': [','.join(df_b.columns.astype(str))]}), format='fixed')
+        store.put(f'batch_{batch_i:04d}', df_b, format='fixed')
+
+
 def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cells=2000, n_ctrl=2000,
                     family='nb', offset=True, warm_start_U=False, cache_path=None, random_state=0, verbose=False,
                     gcate_kwargs=None, lfc_kwargs=None, **kwargs):
@@ -487,6 +496,15 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
                                      "cache_path to start over.")
     col_of = {name: i for i, name in enumerate(names)}
     new = {}
+    # multi-GPU: every rank takes the batches i with i % world == rank (no data-path collective);
+    # the frames are gathered on rank 0 at the end (causarray_b200/parallel.py)
+    from . import parallel as _par
+    import math as _math
+    _rank, _world = _par.dist_info()
+    if _world > 1:
+        _nb = n_batches if n_batches is not None else _math.ceil(A_np.shape[1] / batch_size)
+        _nb = max(1, min(_nb, A_np.shape[1]))
+        skip = set(skip) | _par.foreign_batches(_nb, _rank, _world)
     # one batch at a time: GCATE fit -> LFC on the same device-resident counts
     from .estimators import iter_gcate_batches
     for br in iter_gcate_batches(Y_np, X_np, A, r, batch_size=batch_size, n_batches=n_batches, max_cells=max_cells,
@@ -511,20 +529,21 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
                           _trusted=ws is not None, **{**kwargs, **lfc_kwargs})
         df_b['batch'] = batch_i
         new[batch_i] = df_b
-        if cache_path is not None:
-            with pd.HDFStore(cache_path, mode='a') as store:
-                if '/meta' not in store.keys():
-                    store.put('/meta', pd.DataFrame({'causarray_version': [__version__], 'family': [family],
-                                                     'a_total': [int(A_np.shape[1])],
-                                                     'columns': [','.join(df_b.columns.astype(str))]}),
-                              format='fixed')
-                store.put(f'batch_{batch_i:04d}', df_b, format='fixed')
+        if cache_path is not None and _world == 1:
+            _cache_put(cache_path, batch_i, df_b, family, int(A_np.shape[1]))
         del est_b
         if ws is not None:
             ws.close()
         br['res_1'] = None
         br['res_2'] = None
         gc.collect()
+    if _world > 1:
+        new = _par.gather_frames(new)
+        if new is None:
+            return None   # only rank 0 returns the table
+        if cache_path is not None:   # HDF5 is not concurrent-safe: rank 0 writes everything
+            for _i in sorted(new):
+                _cache_put(cache_path, _i, new[_i], family, int(A_np.shape[1]))
     idx_all = sorted(set(new) | set(cached))
     if cached and cache_path is not None:
         with pd.HDFStore(cache_path, mode='r') as store:

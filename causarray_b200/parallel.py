@@ -1,0 +1,57 @@
+"""Multi-GPU sharding of the hot path.
+
+``gcate_lfc_batch`` partitions by perturbation batch: batches share only the control
+subsample and the dispersion (``causarray/gcate.py:494-510``), so rank ``q`` of ``W`` takes the
+batches ``i`` with ``i % W == q`` -- no data-path collective.  The only exchange is the final
+gather of the per-batch result frames to rank 0 (which also owns the HDF5 cache).  Works with
+any initialised ``torch.distributed`` backend (``nccl`` on the GPUs, ``gloo`` in the CPU tests).
+"""
+import os
+
+import pandas as pd
+
+
+def dist_info():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def owned_batches(n_batches, rank, world_size):
+    """Batch indices processed by ``rank`` (round-robin: balances the ragged last batch)."""
+    return [i for i in range(n_batches) if i % world_size == rank]
+
+
+def foreign_batches(n_batches, rank, world_size):
+    return set(range(n_batches)) - set(owned_batches(n_batches, rank, world_size))
+
+
+def gather_frames(frames_by_batch, dst=0):
+    """Gather ``{batch_i: DataFrame}`` dicts from all ranks on ``dst``; returns the merged
+    dict there and ``None`` elsewhere.  Single-process: returns the input."""
+    rank, world = dist_info()
+    if world == 1:
+        return frames_by_batch
+    import torch.distributed as dist
+    out = [None] * world if rank == dst else None
+    dist.gather_object(frames_by_batch, out, dst=dst)
+    if rank != dst:
+        return None
+    merged = {}
+    for part in out:
+        merged.update(part)
+    return merged
+
+
+def set_device_from_env():
+    """Bind this process to ``cuda:LOCAL_RANK`` (torchrun convention) for the C-ABI library."""
+    from . import _lib as L
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L.load()
+    L.check(L._lib.ca_set_device(local))
+    return local

@@ -1,0 +1,165 @@
+"""CPU: host-side mirror of the reference interface (no compute calls into the CUDA library)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import causarray_b200 as cb
+from causarray_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports every function include/causarray_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "causarray_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ca_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = L.load(require_gpu=False)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+    assert lib.ca_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.CausarrayCudaError):
+        cb.nll(np.ones((4, 3)), np.ones((4, 2)), np.ones((3, 2)), "poisson", np.ones(3), np.zeros((4, 3)))
+
+
+def test_public_api_surface():
+    for name in ["LFC", "gcate_lfc_batch", "LFC_batch", "fit_glm", "fit_glm_fast", "fit_glm_auto", "fit_gcate",
+                 "fit_gcate_batch", "estimate_r", "estimate", "alter_min", "nll", "grad", "update",
+                 "update_with_mask", "Early_Stopping", "prep_causarray_data", "comp_size_factor",
+                 "estimate_propensity_scores", "compute_causal_estimand", "cross_fitting", "AIPW_mean",
+                 "reset_random_seeds", "bh_correction"]:
+        assert hasattr(cb, name), name
+    import inspect
+    sig = inspect.signature(cb.gcate_lfc_batch)
+    assert list(sig.parameters)[:4] == ["Y", "X", "A", "r"]
+    assert sig.parameters["batch_size"].default == 10 and sig.parameters["max_cells"].default == 2000
+    assert sig.parameters["family"].default == "nb" and sig.parameters["offset"].default is True
+    sig = inspect.signature(cb.LFC)
+    assert sig.parameters["usevar"].default == "unequal" and sig.parameters["thres_min"].default == 1e-2
+    assert sig.parameters["ps_clip"].default == (0.01, 0.99)
+    sig = inspect.signature(cb.fit_gcate)
+    assert sig.parameters["c1"].default is None and sig.parameters["backend"].default == "auto"
+
+
+def test_prep_and_size_factors_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    np.testing.assert_allclose(cb.comp_size_factor(g["Y"]), g["size_factor"], rtol=1e-13)
+    Yc, A1, X1, XA1 = cb.prep_causarray_data(g["Y"], np.zeros((g["Y"].shape[0], 2)), X=None)
+    np.testing.assert_allclose(Yc, g["prep_Y"])
+    np.testing.assert_allclose(X1, g["prep_X"])
+    np.testing.assert_allclose(XA1, g["prep_XA"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        cb.comp_size_factor(g["Y"], method="bogus")
+
+
+def test_subsamplers_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    np.testing.assert_array_equal(cb.subsample_ctrl_cells(np.arange(5, 500, 3), n_ctrl=40, random_state=3),
+                                  g["ctrl_sel"])
+    np.testing.assert_array_equal(cb.subsample_pert_cells(np.arange(2, 700, 5), max_cells=33, random_state=4),
+                                  g["pert_sel"])
+    idx = np.arange(10)
+    assert cb.subsample_ctrl_cells(idx, n_ctrl=20) is not None and len(cb.subsample_ctrl_cells(idx, n_ctrl=20)) == 10
+    assert len(cb.subsample_pert_cells(idx, max_cells=None)) == 10
+
+
+def test_bh_correction_golden_and_edges(golden_dir):
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    for pre, df in (("bh", g["bh_df"]), ("bhz", None)):
+        out = cb.bh_correction(g["bh_t"].copy(), df=df)
+        for got, name in zip(out, ["p", "q", "pa", "qa"]):
+            np.testing.assert_allclose(got, g["%s_%s" % (pre, name)], rtol=1e-12, equal_nan=True)
+    # NaN propagation and the mad == 0 branch (reference tests/test_inference_comprehensive.py:317-394)
+    t = np.array([np.nan, 2.0, 2.0, 2.0])
+    p, q, pa, qa = cb.bh_correction(t)
+    assert np.isnan(p[0]) and np.isnan(q[0]) and np.all(np.isnan(pa))
+    assert np.all(np.isnan(cb.bh_correction(np.full(3, np.nan))[0]))
+
+
+def test_early_stopping_matches_reference_rule():
+    es = cb.Early_Stopping(warmup=0, patience=2, tolerance=0.0, rel_tol=1e-2)
+    seq = [1.0, 0.9, 0.895, 0.894, 0.893, 0.892]
+    out = [es(v) for v in seq]
+    assert out == [False, False, False, False, True, True]
+    assert "Best Epoch: 1" in es.info
+
+
+def test_filter_params_and_log2_columns():
+    from causarray_b200.dr import _add_log2fc_columns
+    from causarray_b200.prep import _filter_params
+    import pandas as pd
+    assert _filter_params(cb.comp_size_factor, dict(method="scale", foo=1)) == {"method": "scale"}
+    assert _filter_params({"a": 1}, dict(a=2, b=3)) == {"a": 2}
+    with pytest.raises(ValueError):
+        _filter_params(3, {})
+    df = pd.DataFrame({"gene_names": [0, 1], "tau": [np.log(2.0), 0.0], "std": [np.log(4.0), 1.0], "stat": [1., 2.]})
+    out = _add_log2fc_columns(df)
+    assert list(out.columns) == ["gene_names", "tau", "std", "log2fc", "log2fc_se", "stat"]
+    np.testing.assert_allclose(out["log2fc"], [1.0, 0.0])
+    np.testing.assert_allclose(out["log2fc_se"], [2.0, 1.0 / np.log(2.0)])
+
+
+def test_propensity_scores_host():
+    rng = np.random.default_rng(0)
+    n = 300
+    X = np.c_[np.ones(n), rng.standard_normal((n, 2))]
+    A = np.zeros((n, 2))
+    A[:60, 0] = 1
+    A[60:110, 1] = 1
+    pi = cb.estimate_propensity_scores(A, X, clip=(0.01, 0.99))
+    assert pi.shape == (n, 2) and np.all((pi >= 0.01) & (pi <= 0.99))
+    # constant design short-cut
+    np.testing.assert_allclose(cb.estimate_propensity_scores(A, np.ones((n, 1))), 0.5)
+    with pytest.raises(ValueError):
+        cb.estimate_propensity_scores(A * 2, X)
+    with pytest.raises(ValueError):
+        cb.estimate_propensity_scores(A, X, K=0)
+    with pytest.raises(ValueError):
+        cb.estimate_propensity_scores(A, X, clip=(0.5, 0.2))
+
+
+def test_aipw_mean_host_helper():
+    """Reference tests/test_DR_learner.py:76-101: pseudo-outcomes are left unclipped."""
+    rng = np.random.default_rng(1)
+    n, p, a = 20, 3, 1
+    Y = rng.poisson(3.0, (n, p)).astype(float)
+    A = (rng.random((n, a)) < 0.5).astype(float)
+    pi = np.full((n, a), 0.5)
+    mu = np.full((n, p, a, 2), 3.0)
+    tau, psi = cb.AIPW_mean(Y, np.stack([1 - A, A], -1), mu, np.stack([1 - pi, pi], -1))
+    assert tau.shape == (p, a, 2) and psi.shape == (n, p, a, 2) and tau.dtype == np.float64
+    assert psi.min() < 0
+    np.testing.assert_allclose(tau, psi.mean(0))
+
+
+def test_yhat_factors_materialize():
+    from causarray_b200.dr import YhatFactors
+    rng = np.random.default_rng(2)
+    W = rng.standard_normal((5, 2))
+    Bc, Bt = rng.standard_normal((4, 2)), rng.standard_normal((4, 3))
+    off = rng.standard_normal(5) * 0.1
+    yh = YhatFactors(W, Bc, Bt, off).materialize()
+    assert yh.shape == (5, 4, 3, 2)
+    np.testing.assert_allclose(yh[:, :, 1, 0], np.exp(W @ Bc.T + off[:, None]))
+    np.testing.assert_allclose(yh[:, :, 2, 1], np.exp(W @ Bc.T + off[:, None] + Bt[:, 2][None, :]))
+
+
+def test_lowrank_product_svd():
+    from causarray_b200.svd import lowrank_product_svd
+    rng = np.random.default_rng(3)
+    U, G = rng.standard_normal((30, 3)), rng.standard_normal((40, 3))
+    u, s, vt = lowrank_product_svd(U, G)
+    np.testing.assert_allclose((u * s) @ vt, U @ G.T, atol=1e-10)
+    s_ref = np.linalg.svd(U @ G.T, compute_uv=False)[:3]
+    np.testing.assert_allclose(s, s_ref, rtol=1e-10)
