@@ -222,7 +222,10 @@ def main():
             stats_all.append(st)
         return elapsed, tot_updates, stats_all
 
+    from causarray_b200 import _timing
     resident_pass(args.warmup, False)
+    _timing.enable(True)
+    _timing.reset()
     L.profile_enable(True)
     L.profile_reset()
     launches0 = L.launch_count()
@@ -233,6 +236,8 @@ def main():
     prof = L.profile_snapshot()
     launches = L.launch_count() - launches0
     L.profile_enable(False)
+    phases = {k: round(1e3 * v / args.steps, 2) for k, v in _timing.TOTALS.items()}
+    _timing.enable(False)
 
     # ---------------- end-to-end arm: host arrays in, DataFrame out ----------------
     for s in range(min(args.warmup, 1)):
@@ -311,6 +316,7 @@ def main():
                                              + batches[0]["A"].nbytes + batches[0]["X_A"].nbytes),
                    "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
+           "phases_ms_per_step": phases,
            "work_per_step": {k: v / args.steps for k, v in st_sum.items()},
            "n_significant_last_step": stats_res[-1]["n_sig"]}
 

@@ -29,6 +29,7 @@ from . import glm as _glm_mod
 from .device import GlmDevice, aipw_lfc, aipw_lfc_yhat
 from .inference import bh_correction, fdx_control
 from .prep import comp_size_factor, _filter_params, reset_random_seeds
+from ._timing import phase
 
 __version__ = "0.1.0"
 
@@ -170,9 +171,10 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
     if pi_hat is None:
         ps_kwargs = {k: v for k, v in kwargs.items() if k != 'random_state'}
         ps_kwargs = _filter_params(LogisticRegression().get_params(), ps_kwargs)
-        pi_hat_raw = estimate_propensity_scores(A, X_A, K=K, ps_model=ps_model, mask=mask,
-                                                random_state=kwargs.get('random_state', 0), verbose=verbose,
-                                                class_weight=ps_class_weight, **ps_kwargs)
+        with phase('lfc_propensity'):
+            pi_hat_raw = estimate_propensity_scores(A, X_A, K=K, ps_model=ps_model, mask=mask,
+                                                    random_state=kwargs.get('random_state', 0), verbose=verbose,
+                                                    class_weight=ps_class_weight, **ps_kwargs)
     else:
         pi_hat_raw = np.asarray(pi_hat, dtype=float).reshape(A.shape)
     if ps_clip is None:
@@ -200,8 +202,9 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
                 Y_hat[te] = YhatFactors(X[te], B[:, :d], B[:, d:], off_te, cap=np.inf).materialize()
             Y_hat = np.clip(Y_hat, None, 1e5)
         else:
-            B, fit, disp, offsets, _ = _glm_mod.fit_glm(Y, X, A, family=family, alpha=glm_alpha, _glm=_glm,
-                                                        _lazy=True, **params_glm)
+            with phase('lfc_outcome_glm'):
+                B, fit, disp, offsets, _ = _glm_mod.fit_glm(Y, X, A, family=family, alpha=glm_alpha, _glm=_glm,
+                                                            _lazy=True, **params_glm)
             Y_hat = YhatFactors(X, np.ascontiguousarray(B[:, :d]), np.ascontiguousarray(B[:, d:]), offsets)
             Y_hat.disp_glm = disp
             Y_hat.glm = fit.dev
@@ -309,8 +312,9 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         if dense:
             out = aipw_lfc_yhat(Y, np.asarray(Y_hat, dtype=float), size_factors, A, pi_hat, cell_mask=cm, **lfc_opts)
         else:
-            out = aipw_lfc(Y, Y_hat.W, Y_hat.Bcov, Y_hat.Btrt, Y_hat.offset, size_factors, A, pi_hat,
-                           cell_mask=cm, glm=getattr(Y_hat, 'glm', None) or _glm, **lfc_opts)
+            with phase('lfc_aipw'):
+                out = aipw_lfc(Y, Y_hat.W, Y_hat.Bcov, Y_hat.Btrt, Y_hat.offset, size_factors, A, pi_hat,
+                               cell_mask=cm, glm=getattr(Y_hat, 'glm', None) or _glm, **lfc_opts)
         ctrl = np.sum(A, axis=1) == 0.
         for j in range(A.shape[1]):
             cells = mask[:, j] if mask is not None else (ctrl | (A[:, j] == 1.))
@@ -343,6 +347,8 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
                             ret[4] if len(ret) > 4 else None))
 
     frames = []
+    _t_inf = phase('lfc_inference_frames')
+    _t_inf.__enter__()
     for j, (eta_est, tau_est, var_est, df_est, info) in enumerate(per_trt):
         with np.errstate(invalid='ignore', divide='ignore'):
             std_est = np.sqrt(var_est)
@@ -370,6 +376,7 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
             df_res['trt'] = trt_names[j]
         frames.append(df_res)
     df_res = pd.concat(frames, axis=0).reset_index(drop=True)
+    _t_inf.__exit__(None, None, None)
     estimation = {**{'pi_hat': pi_hat, 'pi_hat_raw': pi_hat_raw, 'Y_hat': Y_hat, 'offset': offset,
                      'size_factors': size_factors, 'ps_class_weight': ps_class_weight}, **kwargs}
     return df_res, estimation

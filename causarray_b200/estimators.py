@@ -21,6 +21,7 @@ from scipy.special import gammaln
 from . import glm as _glm_mod
 from .optim import alter_min, BatchWorkspace, type_f
 from .prep import comp_size_factor, _filter_params, subsample_ctrl_cells, subsample_pert_cells
+from ._timing import phase
 
 
 def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0, **kwargs):
@@ -108,8 +109,9 @@ def fit_gcate(Y, X, A, r, family='nb', disp_glm=None, disp_family=None, offset=T
     a = np.asarray(A).shape[1]
     ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
     with ctx:
-        Y, kwargs_glm, lam1, ws = _check_input(np.asarray(Y), X, family, disp_glm, disp_family, offset, c1,
-                                               _ws=_ws, r=int(r), **kwargs)
+        with phase('gcate_upload_checks_sizefactors'):
+            Y, kwargs_glm, lam1, ws = _check_input(np.asarray(Y), X, family, disp_glm, disp_family, offset, c1,
+                                                   _ws=_ws, r=int(r), **kwargs)
         res_1, res_2 = estimate(Y, X, int(r), a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2,
                                 kwargs_es_2, A_init=A_init, _ws=ws, **kwargs)
     return res_1, res_2

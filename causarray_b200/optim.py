@@ -19,6 +19,7 @@ import scipy.linalg
 from . import glm as _glm_mod
 from .device import GcateDevice, GlmDevice
 from .svd import topr_svd_device, lowrank_product_svd
+from ._timing import phase
 
 type_f = np.float64
 
@@ -183,10 +184,12 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     if A is None:
         if verbose:
             pprint.pprint('Estimating initial latent variables with GLMs...')
-        Bx, fit, _, _, _ = _glm_mod.fit_glm(Y, X, offset=offset, family=family, disp_glm=nuisance, maxiter=100,
-                                            verbose=verbose, _glm=ws.glm, _lazy=True)
-        ptr = ws.glm.resid_device_ptr()
-        u, s, vt = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask)
+        with phase('gcate_init_glm'):
+            Bx, fit, _, _, _ = _glm_mod.fit_glm(Y, X, offset=offset, family=family, disp_glm=nuisance, maxiter=100,
+                                                verbose=verbose, _glm=ws.glm, _lazy=True)
+        with phase('gcate_init_svd'):
+            ptr = ws.glm.resid_device_ptr()
+            u, s, vt = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask)
         if u.shape[1] < r:
             raise ValueError('The number of latent factors is larger than the rank of deviance residuals '
                              '({}). Try to decrease the value of r.'.format(u.shape[1]))
@@ -198,8 +201,9 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     if B is None:
         if verbose:
             pprint.pprint('Estimating initial coefficients with GLMs...')
-        B = _glm_mod.fit_glm(Y, A, offset=offset, family=family, disp_glm=nuisance, maxiter=100, verbose=verbose,
-                             _glm=ws.glm, _lazy=True)[0]
+        with phase('gcate_init_glm'):
+            B = _glm_mod.fit_glm(Y, A, offset=offset, family=family, disp_glm=nuisance, maxiter=100, verbose=verbose,
+                                 _glm=ws.glm, _lazy=True)[0]
         u, s, vt = lowrank_product_svd(A[:, d:], B[:, d:])
         A[:, d:] = u * s[None, :] ** (1 / 2)
         B[:, d:] = vt.T * s[None, :] ** (1 / 2)
@@ -213,8 +217,9 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     if verbose:
         pprint.pprint({'kwargs_glm': kwargs_glm, 'kwargs_ls': kwargs_ls, 'kwargs_es': kwargs_es}, compact=True)
         pprint.pprint(f'Fitting GCATE (step {2 if P1 is None else 1})...')
-    res_c, hist = g.alter_min(kwargs_ls, kwargs_es, lam, a)
-    A, B = g.get_factors()
+    with phase('gcate_altmin_stage%d' % (2 if P1 is None else 1)):
+        res_c, hist = g.alter_min(kwargs_ls, kwargs_es, lam, a)
+        A, B = g.get_factors()
     kwargs_glm['disp_glm'] = nuisance
     res = {'n_iter': res_c.n_iter, 'func_val': res_c.func_val, 'resid': res_c.resid, 'hist': list(hist),
            'kwargs_glm': kwargs_glm, 'kwargs_ls': kwargs_ls, 'kwargs_es': kwargs_es,
