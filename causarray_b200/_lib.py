@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ca_last_error": [],
     "ca_device_info": [ctypes.POINTER(_c_int)] * 3 + [ctypes.POINTER(ctypes.c_uint64)],
     "ca_set_device": [_c_int],
+    "ca_release_cached": [],
     "ca_gcate_create": [ctypes.POINTER(_P), _c_int, _c_int, _c_int, _c_int, _c_int, _c_double],
     "ca_gcate_destroy": [_P],
     "ca_gcate_load_counts": [_P, _D, _D, _D],
@@ -105,11 +106,12 @@ _RESTYPE = {"ca_last_error": ctypes.c_char_p, "ca_profile_class_name": ctypes.c_
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+_gpu_ok = False
 
 
 def load(require_gpu=True):
     """Load the shared library (once).  Raises ``CausarrayCudaError`` when it is absent."""
-    global _lib
+    global _lib, _gpu_ok
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise CausarrayCudaError(
@@ -121,7 +123,7 @@ def load(require_gpu=True):
             fn.argtypes = argtypes
             fn.restype = _RESTYPE.get(name, ctypes.c_int)
         _lib = lib
-    if require_gpu:
+    if require_gpu and not _gpu_ok:
         sm = ctypes.c_int(0)
         for attempt in range(5):   # the first CUDA call on a freshly booted box can race the driver
             rc = _lib.ca_device_info(ctypes.byref(sm), None, None, None)
@@ -130,6 +132,7 @@ def load(require_gpu=True):
             time.sleep(1.0)
         if rc != 0:
             raise CausarrayCudaError("no usable CUDA device: %s" % _lib.ca_last_error().decode())
+        _gpu_ok = True
     return _lib
 
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ void entry_terms(double theta, double y, double nu, b
 // m8n8k4 FP64 tensor-core MMA (DMMA.8x8x4): D = A(8x4,row) * B(4x8,col) + C.
 // Fragment ownership (lane = 4*g + t): A[g][t], B[t][g], C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }

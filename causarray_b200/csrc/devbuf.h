@@ -1,10 +1,20 @@
-// Minimal owning device buffer (cudaMalloc / cudaFree), no exceptions.
+// Owning device buffer on top of a small caching allocator, no exceptions.
+//
+// cudaFree of the ~1.6 GB a perturbation batch needs costs ~230 ms (measured through the
+// Python profiler on the B200 box), more than the whole device-side LFC stage, and
+// gcate_lfc_batch creates and destroys one workspace per batch.  Freed blocks therefore go to a
+// size-keyed free list (batches have identical shapes, so reuse is exact); the cache is bounded
+// (CA_POOL_GB, default 24 GB) and ca_release_cached() returns everything to the driver.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include "common.cuh"
 
 namespace ca {
+
+void* pool_alloc(size_t bytes);          // nullptr on failure (error recorded)
+void pool_free(void* p, size_t bytes);
+void pool_release_all();
 
 template <typename T>
 struct DevBuf {
@@ -15,7 +25,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) pool_free(ptr, count * sizeof(T));
     ptr = nullptr;
     count = 0;
   }
@@ -24,11 +34,8 @@ struct DevBuf {
     if (n == count && ptr) return 0;
     release();
     if (n == 0) return 0;
-    cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
-    if (e != cudaSuccess) {
-      ptr = nullptr;
-      return cuda_fail(e, "cudaMalloc", __LINE__);
-    }
+    ptr = static_cast<T*>(pool_alloc(n * sizeof(T)));
+    if (!ptr) return -1;
     count = n;
     return 0;
   }

@@ -22,6 +22,8 @@
 // JT so that the 4*JT running sums stay in registers.
 #include <vector>
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 
 #include "../../include/causarray_b200.h"
 #include "common.cuh"
@@ -209,6 +211,15 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
                     cudaStream_t st) {
   CA_REQUIRE(prm && A && pi && size_factor, "null argument");
   CA_REQUIRE(prm->usevar == 0 || prm->usevar == 1, "usevar must be either \"pooled\" or \"unequal\"");
+  const bool dbg = getenv("CA_TIMING") != nullptr;
+  auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    cudaStreamSynchronize(st);
+    auto T1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[run_aipw] %-12s %.3f ms\n", what, std::chrono::duration<double, std::milli>(T1 - T0).count());
+    T0 = T1;
+  };
   int ldr = kw + 2 + 3 * JT;
   if (ldr % 2 == 0) ldr += 1;
   // inclusion, arm counts (causarray/DR_learner.py:212-219, 426-427)
@@ -230,6 +241,7 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
     CA_CUDA(cudaMemcpyAsync(d_Bcov.ptr, Bcov, sizeof(double) * (size_t)p * kw, cudaMemcpyHostToDevice, st));
     CA_CUDA(cudaMemcpyAsync(d_Btrt.ptr, Btrt, sizeof(double) * (size_t)p * a, cudaMemcpyHostToDevice, st));
   }
+  lap("alloc+h2d");
   std::vector<std::vector<double>> recs(ngroups, std::vector<double>((size_t)n * ldr, 0.0));
   for (int g = 0; g < ngroups; ++g) {
     std::vector<double>& R = recs[g];
@@ -254,6 +266,7 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
       }
     }
   }
+  lap("pack");
   CA_CUDA(cudaMemcpyAsync(d_cnt.ptr, cnt.data(), sizeof(double) * a * 3, cudaMemcpyHostToDevice, st));
   DrArgs D;
   D.Yt = Yt_dev;
@@ -300,6 +313,7 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
     }
     CA_CUDA(cudaStreamSynchronize(st));  // recs[g] is reused as the staging source
   }
+  lap("kernels");
   const size_t ap = (size_t)a * p;
   CA_CUDA(cudaMemcpyAsync(mean0, D.mean0, sizeof(double) * ap, cudaMemcpyDeviceToHost, st));
   CA_CUDA(cudaMemcpyAsync(mean1, D.mean1, sizeof(double) * ap, cudaMemcpyDeviceToHost, st));
@@ -308,6 +322,7 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
   CA_CUDA(cudaMemcpyAsync(df, D.df, sizeof(double) * ap, cudaMemcpyDeviceToHost, st));
   CA_CUDA(cudaMemcpyAsync(estimable, d_est.ptr, ap, cudaMemcpyDeviceToHost, st));
   CA_CUDA(cudaStreamSynchronize(st));
+  lap("d2h");
   return 0;
 }
 

@@ -100,15 +100,23 @@ struct NbClip {
   double u_lo, u_hi, lu_lo, lu_hi;
 };
 
-// Per-entry NB terms, branch free.  ell = y*log1p(-q) + nu*log(q),  dl = (m - y) * q.
+// Per-entry NB terms.  ell = y*log1p(-q) + nu*log(q),  dl = (m - y) * q.
+// The clip of q is almost never active (it needs e^xi / nu outside [1e-6, 1e6]); it is applied
+// behind a warp vote so that the common path carries no selects.
 template <bool WANT_DL>
 __device__ __forceinline__ void fm_entry_nb(double theta, double y, double nu, double inv_nu, double log_nu,
                                             const FmTables& T, const NbClip& C, double& ell, double& dl, double& xi,
                                             double& m) {
-  xi = fmin(theta, 100.0);                              // the reference clips from above only
-  m = fm_exp(fmax(xi, -700.0), T.exp_t);                // exp(-700) ~ 1e-304 stands in for the underflow to 0
-  const double uc = fmin(fmax(m * inv_nu, C.u_lo), C.u_hi);
-  const double lu = fmin(fmax(xi - log_nu, C.lu_lo), C.lu_hi);
+  xi = theta < 100.0 ? theta : 100.0;                   // the reference clips from above only
+  const double xe = xi > -700.0 ? xi : -700.0;          // exp(-700) ~ 1e-304 stands in for the underflow to 0
+  m = fm_exp(xe, T.exp_t);
+  double uc = m * inv_nu;
+  double lu = xi - log_nu;
+  const bool lo = uc < C.u_lo, hi = uc > C.u_hi;
+  if (__any_sync(0xffffffffu, lo || hi)) {
+    uc = lo ? C.u_lo : (hi ? C.u_hi : uc);
+    lu = lo ? C.lu_lo : (hi ? C.lu_hi : lu);
+  }
   const double w = 1.0 + uc;
   const double L = fm_log(w, T.log_t);                  // log1p(u_c) = -log(q_c)
   ell = fma(y, lu, -(y + nu) * L);                      // y (lu - L) - nu L

@@ -8,7 +8,7 @@ static int pick_tc(int kpad) {
   // two staged chunks of tc x (kpad + 4) doubles; keep them under ~64 KB so that three CTAs
   // fit on an SM for kpad <= 28.
   int tc = CA_TC;
-  while (tc > 16 && 2 * (size_t)tc * (kpad + 4) * 8 > 64 * 1024) tc >>= 1;
+  while (tc > 16 && 2 * (size_t)tc * (kpad + 4 + 8) * 8 > 88 * 1024) tc >>= 1;
   return tc;
 }
 

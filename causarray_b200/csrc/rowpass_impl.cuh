@@ -87,6 +87,7 @@ struct Smem {
   double* tab;     // FM_TABLE_DOUBLES
   double* M;       // 2 * tc * kpad + 64 slack
   double4* cp;     // 2 * tc   (column parameters)
+  double* Ys;      // 2 * 8 * (tc + 8)  (rows of Y for the chunk)
   double* X;       // 8 * kpad
   double* X0;      // 8 * kpad (search)
   double* Gd;      // 8 * kpad (search)
@@ -97,7 +98,7 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t smem_doubles(int tc, int kpad, int ngt, bool search) {
-  return FM_TABLE_DOUBLES + 2 * (size_t)tc * kpad + 64 + 2 * (size_t)tc * 4 + 8 * kpad + (search ? 16 * kpad : 0) + 64 +
+  return FM_TABLE_DOUBLES + 2 * (size_t)tc * kpad + 64 + 2 * (size_t)tc * 4 + 2 * 8 * ((size_t)tc + 8) + 8 * kpad + (search ? 16 * kpad : 0) + 64 +
          8 + 64 * (size_t)ngt * 8 + 8 * (size_t)ngt * 8;
 }
 
@@ -109,6 +110,8 @@ __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, 
   base += 2 * tc * kpad + 64;
   s.cp = reinterpret_cast<double4*>(base);
   base += 2 * tc * 4;
+  s.Ys = base;
+  base += 2 * 8 * (tc + 8);
   s.X = base;
   base += 8 * kpad;
   s.X0 = base;
@@ -125,10 +128,21 @@ __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, 
 }
 
 template <int KS>
-__device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dstM, double4* dstC) {
+__device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dstM, double4* dstC, double* dstY,
+                                            const int* s_rows) {
   constexpr int KPAD = 4 * KS;
   const int col0 = c * P.tc;
   const int nvalid = min(P.tc, P.ncols - col0);
+  {
+    // the 8 rows of Y for this chunk (rows of Y are padded with zeros up to ldY, a multiple of 8)
+    const int ny = round_up(nvalid, 8) / 2;  // 16-byte units per row
+    const int ldy = P.tc + 8;
+    for (int i = threadIdx.x; i < 8 * ny; i += NTHREADS) {
+      const int r = i / ny, u = i - r * ny;
+      const int row = s_rows[r];
+      cp_async16(dstY + r * ldy + 2 * u, P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + col0 + 2 * u);
+    }
+  }
   const int nvec = nvalid * KPAD / 2;  // 16-byte units
   const double* src = P.M + (size_t)col0 * KPAD;
 #if CA_ABL == 2
@@ -147,44 +161,70 @@ __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst
     for (int i = nvalid + threadIdx.x; i < npad; i += NTHREADS) dstC[i] = make_double4(1.0, 1.0, 0.0, 0.0);
 }
 
+enum PassMode { MODE_POIS = 0, MODE_NB_ROW = 1, MODE_NB_COL = 2 };
+
+// Likelihood terms of one matrix entry (branch free).
+template <int MODE, bool GRAD>
+__device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& clip, double theta, double y, double nu,
+                                           double inu, double lnu, bool pois, double& e, double& d) {
+  if (MODE == MODE_POIS) {
+    const double x = theta < 100.0 ? theta : 100.0;
+    const double m = fm_exp(x > -700.0 ? x : -700.0, FT.exp_t);
+    e = fma(y, x, -m);
+    if (GRAD) d = m - y;
+  } else {
+    double x, m;
+    fm_entry_nb<GRAD>(theta, y, nu, inu, lnu, FT, clip, e, d, x, m);
+    if (__any_sync(0xffffffffu, pois)) {  // Poisson branch (nu > thres_disp): rare, behind a warp vote
+      e = pois ? fma(y, x, -m) : e;
+      if (GRAD) d = pois ? (m - y) : d;
+    }
+  }
+}
+
 // One pass over all columns for the 8 rows listed in s_rows (-1 = empty slot; its sums are
 // garbage and ignored by the callers).  s_X: 8 x kpad candidate rows.  On return (after a
 // __syncthreads) s_rowsum[r] holds sum_col ell(y, theta) and, if GRAD, s_G[r*NGT*8 + c] holds
 // sum_col dl * M[col, gc_lo + c].
-template <int KS, bool GRAD, int NGT>
-__device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, const int* s_rows, const double* s_X,
-                                          const Smem& S, int gc_lo) {
+//
+// Per iteration a warp handles TWO 8x8 tiles (t and t + 8): four independent per-entry
+// dependency chains per lane and 2 x NACC independent DMMA accumulators, because both the
+// FP64 pipe (~8-10 cycles) and DMMA (~250 cycles) are latency bound with one chain per warp.
+template <int KS, bool GRAD, int NGT, int MODE>
+__device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
+                                               const double* s_X, const Smem& S, int gc_lo) {
   constexpr int KPAD = 4 * KS;
+  constexpr int NACC = KS < 4 ? KS : 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
   const int tc = P.tc;
   const int row = s_rows[lr];
-  const double* yrow = P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + 2 * lc;
-  const bool fam_nb = P.family == CA_FAMILY_NB;
-  const bool per_row = P.nu_per_row != 0;
   double nu_r = 1.0, inu_r = 1.0, lnu_r = 0.0;
-  bool pois_r = !fam_nb;
-  if (per_row && row >= 0 && fam_nb) {
+  bool pois_r = false;
+  if (MODE == MODE_NB_ROW && row >= 0) {
     nu_r = P.nu[row];
     inu_r = P.inv_nu[row];
     lnu_r = P.log_nu[row];
     pois_r = nu_r > P.thres;
   }
+  const NbClip clip = P.clip;
   double afrag[KS];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) afrag[ks] = s_X[lr * KPAD + ks * 4 + lc];
   double ellsum = 0.0;
-  double gacc[NGT][2], gacb[NGT][2];  // two accumulator sets: the two columns of a lane go to separate chains
+  double gacc[NGT][2], gacb[NGT][2];  // two accumulator sets (the two tiles of an iteration)
 #pragma unroll
   for (int j = 0; j < NGT; ++j) gacc[j][0] = gacc[j][1] = gacb[j][0] = gacb[j][1] = 0.0;
 
   const int nchunks = (P.ncols + tc - 1) / tc;
   const int chunk_elems = tc * KPAD;
-  stage_chunk<KS>(P, 0, S.M, S.cp);
+  const int ldy = tc + 8;
+  stage_chunk<KS>(P, 0, S.M, S.cp, S.Ys, s_rows);
   cp_async_commit();
   for (int c = 0; c < nchunks; ++c) {
     if (c + 1 < nchunks) {
-      stage_chunk<KS>(P, c + 1, S.M + ((c + 1) & 1) * chunk_elems, S.cp + ((c + 1) & 1) * tc);
+      stage_chunk<KS>(P, c + 1, S.M + ((c + 1) & 1) * chunk_elems, S.cp + ((c + 1) & 1) * tc,
+                      S.Ys + ((c + 1) & 1) * 8 * ldy, s_rows);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -193,91 +233,70 @@ __device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, 
     __syncthreads();
     const double* Mb = S.M + (c & 1) * chunk_elems;
     const double4* Cb = S.cp + (c & 1) * tc;
+    const double* Yb = S.Ys + (c & 1) * 8 * ldy + lr * ldy + 2 * lc;
     const int col0 = c * tc;
     const int nrem = P.ncols - col0;
     const int ntile = min(tc, round_up(nrem, 8)) >> 3;
 #pragma unroll 1
-    for (int t = warp; t < ntile; t += NWARPS) {
-      const int cl = t * 8 + 2 * lc;  // column within the chunk
-#if CA_ABL == 3
-      const double2 yv = make_double2(1.0, 2.0);
-#else
-      const double2 yv = *reinterpret_cast<const double2*>(yrow + col0 + t * 8);
-#endif
-      // The DMMA latency on sm_100a is ~250 cycles (tools/fp64_microbench: 16 chains per SMSP
-      // are needed to reach the 36.5 TFLOP/s peak), so the k-steps go to independent
-      // accumulators and are summed afterwards instead of forming one dependent chain.
-      constexpr int NACC = KS < 7 ? KS : 7;
-      double pa[NACC][2];
-      const double* bp = Mb + (t * 8 + lr) * KPAD + lc;
+    for (int t = warp; t < ntile; t += 2 * NWARPS) {
+      const bool hasB = t + NWARPS < ntile;            // warp uniform
+      const int tA = t, tB = hasB ? t + NWARPS : t;
+      const int clA = tA * 8 + 2 * lc, clB = tB * 8 + 2 * lc;  // columns within the chunk
+      const double2 yA = *reinterpret_cast<const double2*>(Yb + tA * 8);
+      const double2 yB = *reinterpret_cast<const double2*>(Yb + tB * 8);
+      double pa[NACC][2], pb[NACC][2];
+      const double* bpA = Mb + (tA * 8 + lr) * KPAD + lc;
+      const double* bpB = Mb + (tB * 8 + lr) * KPAD + lc;
 #pragma unroll
       for (int ks = 0; ks < NACC; ++ks) {
-        pa[ks][0] = pa[ks][1] = 0.0;
-        dmma884(pa[ks][0], pa[ks][1], afrag[ks], bp[ks * 4]);
+        pa[ks][0] = pa[ks][1] = pb[ks][0] = pb[ks][1] = 0.0;
+        dmma884(pa[ks][0], pa[ks][1], afrag[ks], bpA[ks * 4]);
+        dmma884(pb[ks][0], pb[ks][1], afrag[ks], bpB[ks * 4]);
       }
 #pragma unroll
-      for (int ks = NACC; ks < KS; ++ks) dmma884(pa[ks % NACC][0], pa[ks % NACC][1], afrag[ks], bp[ks * 4]);
+      for (int ks = NACC; ks < KS; ++ks) {
+        dmma884(pa[ks % NACC][0], pa[ks % NACC][1], afrag[ks], bpA[ks * 4]);
+        dmma884(pb[ks % NACC][0], pb[ks % NACC][1], afrag[ks], bpB[ks * 4]);
+      }
 #pragma unroll
       for (int st = 1; st < NACC; st <<= 1)
 #pragma unroll
         for (int i = 0; i + st < NACC; i += 2 * st) {
           pa[i][0] += pa[i + st][0];
           pa[i][1] += pa[i + st][1];
+          pb[i][0] += pb[i + st][0];
+          pb[i][1] += pb[i + st][1];
         }
-      const double acc0 = pa[0][0], acc1 = pa[0][1];
-      double e0, e1, d0 = 0.0, d1 = 0.0;
-#if CA_ABL == 1
-      e0 = acc0 * yv.x; e1 = acc1 * yv.y; d0 = acc0; d1 = acc1;
-      if (false) {
-#else
-      if (fam_nb) {
-#endif
-        double x0, x1, m0, m1;
-        if (per_row) {
-          fm_entry_nb<GRAD>(acc0, yv.x, nu_r, inu_r, lnu_r, FT, P.clip, e0, d0, x0, m0);
-          fm_entry_nb<GRAD>(acc1, yv.y, nu_r, inu_r, lnu_r, FT, P.clip, e1, d1, x1, m1);
-          if (pois_r) {
-            e0 = fma(yv.x, x0, -m0);
-            e1 = fma(yv.y, x1, -m1);
-            if (GRAD) {
-              d0 = m0 - yv.x;
-              d1 = m1 - yv.y;
-            }
-          }
-        } else {
-          const double4 c0 = Cb[cl], c1 = Cb[cl + 1];
-          fm_entry_nb<GRAD>(acc0, yv.x, c0.x, c0.y, c0.z, FT, P.clip, e0, d0, x0, m0);
-          fm_entry_nb<GRAD>(acc1, yv.y, c1.x, c1.y, c1.z, FT, P.clip, e1, d1, x1, m1);
-          if (c0.w != 0.0) {
-            e0 = fma(yv.x, x0, -m0);
-            if (GRAD) d0 = m0 - yv.x;
-          }
-          if (c1.w != 0.0) {
-            e1 = fma(yv.y, x1, -m1);
-            if (GRAD) d1 = m1 - yv.y;
-          }
-        }
-      } else {
-        const double x0 = fmin(acc0, 100.0), x1 = fmin(acc1, 100.0);
-        const double m0 = fm_exp(fmax(x0, -700.0), FT.exp_t), m1 = fm_exp(fmax(x1, -700.0), FT.exp_t);
-        e0 = fma(yv.x, x0, -m0);
-        e1 = fma(yv.y, x1, -m1);
-        if (GRAD) {
-          d0 = m0 - yv.x;
-          d1 = m1 - yv.y;
-        }
+      double4 cA0 = make_double4(nu_r, inu_r, lnu_r, pois_r ? 1.0 : 0.0), cA1 = cA0, cB0 = cA0, cB1 = cA0;
+      if (MODE == MODE_NB_COL) {
+        cA0 = Cb[clA];
+        cA1 = Cb[clA + 1];
+        cB0 = Cb[clB];
+        cB1 = Cb[clB + 1];
       }
-      if (t * 8 + 8 > nrem) {  // ragged last tile (warp uniform)
-        if (cl >= nrem) e0 = d0 = 0.0;
-        if (cl + 1 >= nrem) e1 = d1 = 0.0;
+      double eA0, eA1, eB0, eB1, dA0 = 0.0, dA1 = 0.0, dB0 = 0.0, dB1 = 0.0;
+      eval_entry<MODE, GRAD>(FT, clip, pa[0][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, eA0, dA0);
+      eval_entry<MODE, GRAD>(FT, clip, pa[0][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, eA1, dA1);
+      eval_entry<MODE, GRAD>(FT, clip, pb[0][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, eB0, dB0);
+      eval_entry<MODE, GRAD>(FT, clip, pb[0][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, eB1, dB1);
+      if (!hasB || tB * 8 + 8 > nrem) {  // missing / ragged second tile (warp uniform)
+        if (!hasB || clB >= nrem) eB0 = dB0 = 0.0;
+        if (!hasB || clB + 1 >= nrem) eB1 = dB1 = 0.0;
       }
-      ellsum += e0 + e1;
+      if (tA * 8 + 8 > nrem) {
+        if (clA >= nrem) eA0 = dA0 = 0.0;
+        if (clA + 1 >= nrem) eA1 = dA1 = 0.0;
+      }
+      ellsum += (eA0 + eA1) + (eB0 + eB1);
       if (GRAD) {
-        const double* g0 = Mb + (t * 8 + 2 * lc) * KPAD + gc_lo + lr;
+        const double* gA = Mb + (tA * 8 + 2 * lc) * KPAD + gc_lo + lr;
+        const double* gB = Mb + (tB * 8 + 2 * lc) * KPAD + gc_lo + lr;
 #pragma unroll
         for (int j = 0; j < NGT; ++j) {
-          dmma884(gacc[j][0], gacc[j][1], d0, g0[8 * j]);
-          dmma884(gacb[j][0], gacb[j][1], d1, g0[KPAD + 8 * j]);
+          dmma884(gacc[j][0], gacc[j][1], dA0, gA[8 * j]);
+          dmma884(gacb[j][0], gacb[j][1], dB0, gB[8 * j]);
+          dmma884(gacc[j][0], gacc[j][1], dA1, gA[KPAD + 8 * j]);
+          dmma884(gacb[j][0], gacb[j][1], dB1, gB[KPAD + 8 * j]);
         }
       }
     }
@@ -311,6 +330,17 @@ __device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, 
     }
   }
   __syncthreads();
+}
+
+template <int KS, bool GRAD, int NGT>
+__device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, const int* s_rows, const double* s_X,
+                                          const Smem& S, int gc_lo) {
+  if (P.family != CA_FAMILY_NB)
+    tile_pass_mode<KS, GRAD, NGT, MODE_POIS>(P, FT, s_rows, s_X, S, gc_lo);
+  else if (P.nu_per_row)
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW>(P, FT, s_rows, s_X, S, gc_lo);
+  else
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_COL>(P, FT, s_rows, s_X, S, gc_lo);
 }
 
 // ---------------------------------------------------------------------------

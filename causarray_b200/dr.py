@@ -27,11 +27,14 @@ from sklearn.model_selection import KFold
 
 from . import glm as _glm_mod
 from .device import GlmDevice, aipw_lfc, aipw_lfc_yhat
-from .inference import bh_correction, fdx_control
+from .inference import bh_correction, bh_correction_multi, fdx_control
 from .prep import comp_size_factor, _filter_params, reset_random_seeds
 from ._timing import phase
 
 __version__ = "0.1.0"
+
+import concurrent.futures as _cf
+_PS_POOL = _cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix='causarray_ps')
 
 
 class YhatFactors:
@@ -168,21 +171,25 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
     A = np.asarray(A, dtype=float)
     X = np.asarray(X, dtype=float)
     n = X.shape[0]
+    if ps_clip is not None and (len(ps_clip) != 2 or not 0 <= ps_clip[0] < ps_clip[1] <= 1):
+        raise ValueError('ps_clip must be None or a pair 0 <= lower < upper <= 1')
+    ps_future = None
     if pi_hat is None:
         ps_kwargs = {k: v for k, v in kwargs.items() if k != 'random_state'}
         ps_kwargs = _filter_params(LogisticRegression().get_params(), ps_kwargs)
-        with phase('lfc_propensity'):
-            pi_hat_raw = estimate_propensity_scores(A, X_A, K=K, ps_model=ps_model, mask=mask,
-                                                    random_state=kwargs.get('random_state', 0), verbose=verbose,
-                                                    class_weight=ps_class_weight, **ps_kwargs)
+
+        def _fit_ps():
+            return estimate_propensity_scores(A, X_A, K=K, ps_model=ps_model, mask=mask,
+                                              random_state=kwargs.get('random_state', 0), verbose=verbose,
+                                              class_weight=ps_class_weight, **ps_kwargs)
+        if Y_hat is None and K == 1:
+            # the host-side logistic fits (sklearn) overlap with the outcome GLM running on the device
+            ps_future = _PS_POOL.submit(_fit_ps)
+        else:
+            with phase('lfc_propensity'):
+                pi_hat_raw = _fit_ps()
     else:
         pi_hat_raw = np.asarray(pi_hat, dtype=float).reshape(A.shape)
-    if ps_clip is None:
-        pi_hat = pi_hat_raw.copy()
-    else:
-        if len(ps_clip) != 2 or not 0 <= ps_clip[0] < ps_clip[1] <= 1:
-            raise ValueError('ps_clip must be None or a pair 0 <= lower < upper <= 1')
-        pi_hat = np.clip(pi_hat_raw, ps_clip[0], ps_clip[1])
     if Y_hat is None:
         d = X.shape[1]
         if K > 1:
@@ -210,6 +217,10 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
             Y_hat.glm = fit.dev
     elif not isinstance(Y_hat, YhatFactors):
         Y_hat = np.clip(Y_hat, None, 1e5)
+    if ps_future is not None:
+        with phase('lfc_propensity_wait'):
+            pi_hat_raw = ps_future.result()
+    pi_hat = pi_hat_raw.copy() if ps_clip is None else np.clip(pi_hat_raw, ps_clip[0], ps_clip[1])
     if return_raw_pi:
         return Y_hat, pi_hat, pi_hat_raw
     return Y_hat, pi_hat
@@ -346,36 +357,65 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
             per_trt.append((ret[0], ret[1], ret[2], ret[3] if len(ret) > 3 else None,
                             ret[4] if len(ret) > 4 else None))
 
-    frames = []
     _t_inf = phase('lfc_inference_frames')
     _t_inf.__enter__()
-    for j, (eta_est, tau_est, var_est, df_est, info) in enumerate(per_trt):
+    n_trt = A.shape[1]
+    if lfc_opts is not None and not fdx:
+        # fused path: all treatments at once (one vectorised tail-probability call, one frame)
+        tau_all = np.stack([q[1] for q in per_trt])
+        var_all = np.stack([q[2] for q in per_trt])
+        df_all = np.stack([q[3] for q in per_trt]) if per_trt[0][3] is not None else None
         with np.errstate(invalid='ignore', divide='ignore'):
-            std_est = np.sqrt(var_est)
-            tvals = tau_est / std_est
-        if fdx:
-            if eta_est is None:
-                raise NotImplementedError('fdx=True needs the dense influence values; pass a callable estimand')
-            V = fdx_control(tau_est, tvals, eta_est, std_est, fdx, fdx_B, fdx_alpha, fdx_c)
-        else:
-            V = np.zeros(tvals.shape[0])
-        tvals[np.isinf(std_est)] = np.nan
-        pv, qv, pva, qva = bh_correction(tvals, df=df_est)
-        df_res = pd.DataFrame({'gene_names': gene_names, 'tau': tau_est, 'std': std_est, 'stat': tvals, 'rej': V,
-                               'pvalue': pv, 'padj': qv, 'pvalue_emp_null_adj': pva, 'padj_emp_null_adj': qva})
-        if info is not None:
-            for name, values in info.items():
-                df_res[name] = values
-            n_bad = int(np.sum(~np.asarray(info['estimable'], dtype=bool)))
+            std_all = np.sqrt(var_all)
+            t_all = tau_all / std_all
+        t_all[np.isinf(std_all)] = np.nan
+        pv, qv, pva, qva = bh_correction_multi(t_all, df=df_all)
+        gn = np.asarray(list(gene_names))
+        cols = {'gene_names': np.tile(gn, n_trt), 'tau': tau_all.ravel(), 'std': std_all.ravel(),
+                'stat': t_all.ravel(), 'rej': np.zeros(n_trt * p), 'pvalue': pv.ravel(), 'padj': qv.ravel(),
+                'pvalue_emp_null_adj': pva.ravel(), 'padj_emp_null_adj': qva.ravel(),
+                'mean_control': np.concatenate([q[4]['mean_control'] for q in per_trt]),
+                'mean_treated': np.concatenate([q[4]['mean_treated'] for q in per_trt]),
+                'estimable': np.concatenate([q[4]['estimable'] for q in per_trt])}
+        if n_trt > 1:
+            cols['trt'] = np.repeat(np.asarray(list(trt_names), dtype=object), p)
+        df_res = pd.DataFrame(cols)
+        for j in range(n_trt):
+            n_bad = int(np.sum(~np.asarray(per_trt[j][4]['estimable'], dtype=bool)))
             if n_bad:
-                trt = trt_names[j] if A.shape[1] > 1 else 0
+                trt = trt_names[j] if n_trt > 1 else 0
                 warnings.warn(f'{n_bad} gene(s) for treatment {trt!r} have nonfinite or nonpositive AIPW '
                               'counterfactual means and are reported as non-estimable.', RuntimeWarning,
                               stacklevel=2)
-        if A.shape[1] > 1:
-            df_res['trt'] = trt_names[j]
-        frames.append(df_res)
-    df_res = pd.concat(frames, axis=0).reset_index(drop=True)
+    else:
+        frames = []
+        for j, (eta_est, tau_est, var_est, df_est, info) in enumerate(per_trt):
+            with np.errstate(invalid='ignore', divide='ignore'):
+                std_est = np.sqrt(var_est)
+                tvals = tau_est / std_est
+            if fdx:
+                if eta_est is None:
+                    raise NotImplementedError('fdx=True needs the dense influence values; pass a callable estimand')
+                V = fdx_control(tau_est, tvals, eta_est, std_est, fdx, fdx_B, fdx_alpha, fdx_c)
+            else:
+                V = np.zeros(tvals.shape[0])
+            tvals[np.isinf(std_est)] = np.nan
+            pv, qv, pva, qva = bh_correction(tvals, df=df_est)
+            df_j = pd.DataFrame({'gene_names': gene_names, 'tau': tau_est, 'std': std_est, 'stat': tvals, 'rej': V,
+                                 'pvalue': pv, 'padj': qv, 'pvalue_emp_null_adj': pva, 'padj_emp_null_adj': qva})
+            if info is not None:
+                for name, values in info.items():
+                    df_j[name] = values
+                n_bad = int(np.sum(~np.asarray(info['estimable'], dtype=bool)))
+                if n_bad:
+                    trt = trt_names[j] if n_trt > 1 else 0
+                    warnings.warn(f'{n_bad} gene(s) for treatment {trt!r} have nonfinite or nonpositive AIPW '
+                                  'counterfactual means and are reported as non-estimable.', RuntimeWarning,
+                                  stacklevel=2)
+            if n_trt > 1:
+                df_j['trt'] = trt_names[j]
+            frames.append(df_j)
+        df_res = pd.concat(frames, axis=0).reset_index(drop=True)
     _t_inf.__exit__(None, None, None)
     estimation = {**{'pi_hat': pi_hat, 'pi_hat_raw': pi_hat_raw, 'Y_hat': Y_hat, 'offset': offset,
                      'size_factors': size_factors, 'ps_class_weight': ps_class_weight}, **kwargs}

@@ -26,6 +26,9 @@ int ca_version(void);
 const char* ca_last_error(void);
 int ca_device_info(int* sm_count, int* cc_major, int* cc_minor, uint64_t* total_mem);
 int ca_set_device(int device);
+/* Device buffers of destroyed handles are cached for reuse (cudaFree of a batch costs ~0.2 s);
+ * this returns the cache to the driver.  The cache is bounded by CA_POOL_GB (default 24). */
+int ca_release_cached(void);
 
 /* ------------------------------------------------------------------------
  * S1 -- optimiser seam.  Replaces causarray/gcate_opt.py:148-206
