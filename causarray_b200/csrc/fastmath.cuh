@@ -100,9 +100,23 @@ struct NbClip {
   double u_lo, u_hi, lu_lo, lu_hi;
 };
 
-// Per-entry NB terms.  ell = y*log1p(-q) + nu*log(q),  dl = (m - y) * q.
-// The clip of q is almost never active (it needs e^xi / nu outside [1e-6, 1e6]); it is applied
-// behind a warp vote so that the common path carries no selects.
+// 1/w for w in [1, 1e6+1]: MUFU.RCP64H seed + two Newton steps (no special-case branch: the
+// libm __drcp_rn carries a slow-path CALL that splits the basic block and stops ptxas from
+// interleaving the independent per-entry chains).
+__device__ __forceinline__ double fm_rcp(double w) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  double e = fma(-w, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-w, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-w, r, 1.0);
+  return fma(r, e, r);
+}
+
+// Per-entry NB terms, branch free (straight-line code so that ptxas interleaves the four
+// independent entries a lane has in flight: every FP64 op has an 8-cycle latency).
+//   ell = y*log1p(-q) + nu*log(q),  dl = (m - y) * q.
 template <bool WANT_DL>
 __device__ __forceinline__ void fm_entry_nb(double theta, double y, double nu, double inv_nu, double log_nu,
                                             const FmTables& T, const NbClip& C, double& ell, double& dl, double& xi,
@@ -113,14 +127,14 @@ __device__ __forceinline__ void fm_entry_nb(double theta, double y, double nu, d
   double uc = m * inv_nu;
   double lu = xi - log_nu;
   const bool lo = uc < C.u_lo, hi = uc > C.u_hi;
-  if (__any_sync(0xffffffffu, lo || hi)) {
-    uc = lo ? C.u_lo : (hi ? C.u_hi : uc);
-    lu = lo ? C.lu_lo : (hi ? C.lu_hi : lu);
-  }
+  uc = lo ? C.u_lo : uc;
+  lu = lo ? C.lu_lo : lu;
+  uc = hi ? C.u_hi : uc;
+  lu = hi ? C.lu_hi : lu;
   const double w = 1.0 + uc;
   const double L = fm_log(w, T.log_t);                  // log1p(u_c) = -log(q_c)
   ell = fma(y, lu, -(y + nu) * L);                      // y (lu - L) - nu L
-  if (WANT_DL) dl = (m - y) * __drcp_rn(w);
+  if (WANT_DL) dl = (m - y) * fm_rcp(w);
 }
 
 NbClip nb_clip_constants();

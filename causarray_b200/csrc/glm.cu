@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
           if (!pois) s_log += (y + nu) * fm_log(mu + nu, FT.log_t);
           if (murow) murow[cell] = mu;
           if (!P.finalize) {
-            w = pois ? mu : mu * nu * __drcp_rn(nu + mu);
+            w = pois ? mu : mu * nu * fm_rcp(nu + mu);
             const double z = eta + (y - mu) * __drcp_rn(mu) - off;
             wz = w * z;
           }

@@ -127,38 +127,43 @@ __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, 
   return s;
 }
 
+// Stage chunk c (M rows, column parameters, the 8 rows of Y) into shared memory with bulk async
+// copies (cp.async.bulk / UBLKCP) issued by ONE thread and completed on an mbarrier: the first
+// version staged with per-thread 16-byte cp.async and spent ~40 % of the non-math instructions
+// of the kernel on address arithmetic and LDGSTS issue.
+struct Pipe {
+  unsigned long long* bar;  // two mbarriers (one per stage) in shared memory
+  unsigned phase;           // bit s = parity of the next wait on stage s
+};
+
 template <int KS>
 __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dstM, double4* dstC, double* dstY,
-                                            const int* s_rows) {
+                                            const int* s_rows, unsigned long long* bar) {
   constexpr int KPAD = 4 * KS;
   const int col0 = c * P.tc;
   const int nvalid = min(P.tc, P.ncols - col0);
-  {
-    // the 8 rows of Y for this chunk (rows of Y are padded with zeros up to ldY, a multiple of 8)
-    const int ny = round_up(nvalid, 8) / 2;  // 16-byte units per row
-    const int ldy = P.tc + 8;
-    for (int i = threadIdx.x; i < 8 * ny; i += NTHREADS) {
-      const int r = i / ny, u = i - r * ny;
+  const int npad = min(P.tc, round_up(nvalid, 8));
+  const int ldy = P.tc + 8;
+  if (threadIdx.x == 0) {
+    const unsigned bM = (unsigned)(nvalid * KPAD * sizeof(double));
+    const unsigned bC = P.colparm ? (unsigned)(nvalid * sizeof(double4)) : 0u;
+    const unsigned bY = (unsigned)(npad * sizeof(double));
+    mbar_expect_tx(bar, bM + bC + 8u * bY);
+    bulk_g2s(dstM, P.M + (size_t)col0 * KPAD, bM, bar);
+    if (P.colparm) bulk_g2s(dstC, P.colparm + col0, bC, bar);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
       const int row = s_rows[r];
-      cp_async16(dstY + r * ldy + 2 * u, P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + col0 + 2 * u);
+      bulk_g2s(dstY + r * ldy, P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + col0, bY, bar);
     }
   }
-  const int nvec = nvalid * KPAD / 2;  // 16-byte units
-  const double* src = P.M + (size_t)col0 * KPAD;
-#if CA_ABL == 2
-  if (c > 1) return;
-#endif
-  for (int i = threadIdx.x; i < nvec; i += NTHREADS) cp_async16(dstM + 2 * i, src + 2 * i);
-  if (P.colparm) {
-    const double* sc = reinterpret_cast<const double*>(P.colparm + col0);
-    double* dc = reinterpret_cast<double*>(dstC);
-    for (int i = threadIdx.x; i < nvalid * 2; i += NTHREADS) cp_async16(dc + 2 * i, sc + 2 * i);
+  // ragged tail of the last chunk: zero rows of M and neutral column parameters (generic stores
+  // to addresses the bulk copies do not touch)
+  if (npad > nvalid) {
+    for (int i = nvalid * KPAD + threadIdx.x; i < npad * KPAD; i += NTHREADS) dstM[i] = 0.0;
+    if (P.colparm)
+      for (int i = nvalid + threadIdx.x; i < npad; i += NTHREADS) dstC[i] = make_double4(1.0, 1.0, 0.0, 0.0);
   }
-  // ragged tail of the last chunk: zero rows of M and neutral column parameters
-  const int npad = min(P.tc, round_up(nvalid, 8));
-  for (int i = nvalid * KPAD + threadIdx.x; i < npad * KPAD; i += NTHREADS) dstM[i] = 0.0;
-  if (P.colparm)
-    for (int i = nvalid + threadIdx.x; i < npad; i += NTHREADS) dstC[i] = make_double4(1.0, 1.0, 0.0, 0.0);
 }
 
 enum PassMode { MODE_POIS = 0, MODE_NB_ROW = 1, MODE_NB_COL = 2 };
@@ -175,10 +180,9 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
   } else {
     double x, m;
     fm_entry_nb<GRAD>(theta, y, nu, inu, lnu, FT, clip, e, d, x, m);
-    if (__any_sync(0xffffffffu, pois)) {  // Poisson branch (nu > thres_disp): rare, behind a warp vote
-      e = pois ? fma(y, x, -m) : e;
-      if (GRAD) d = pois ? (m - y) : d;
-    }
+    // Poisson branch (nu > thres_disp), as selects: keeps the four entries in one basic block
+    e = pois ? fma(y, x, -m) : e;
+    if (GRAD) d = pois ? (m - y) : d;
   }
 }
 
@@ -192,7 +196,7 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
 // FP64 pipe (~8-10 cycles) and DMMA (~250 cycles) are latency bound with one chain per warp.
 template <int KS, bool GRAD, int NGT, int MODE>
 __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
-                                               const double* s_X, const Smem& S, int gc_lo) {
+                                               const double* s_X, const Smem& S, int gc_lo, Pipe& pipe) {
   constexpr int KPAD = 4 * KS;
   constexpr int NACC = KS < 4 ? KS : 4;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -219,18 +223,15 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
   const int nchunks = (P.ncols + tc - 1) / tc;
   const int chunk_elems = tc * KPAD;
   const int ldy = tc + 8;
-  stage_chunk<KS>(P, 0, S.M, S.cp, S.Ys, s_rows);
-  cp_async_commit();
+  stage_chunk<KS>(P, 0, S.M, S.cp, S.Ys, s_rows, pipe.bar + 0);
   for (int c = 0; c < nchunks; ++c) {
     if (c + 1 < nchunks) {
-      stage_chunk<KS>(P, c + 1, S.M + ((c + 1) & 1) * chunk_elems, S.cp + ((c + 1) & 1) * tc,
-                      S.Ys + ((c + 1) & 1) * 8 * ldy, s_rows);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+      const int sn = (c + 1) & 1;
+      stage_chunk<KS>(P, c + 1, S.M + sn * chunk_elems, S.cp + sn * tc, S.Ys + sn * 8 * ldy, s_rows, pipe.bar + sn);
     }
-    __syncthreads();
+    mbar_wait(pipe.bar + (c & 1), (pipe.phase >> (c & 1)) & 1u);
+    pipe.phase ^= 1u << (c & 1);
+    if (c == nchunks - 1) __syncthreads();  // the ragged-tail zero fill (generic stores) of the last chunk
     const double* Mb = S.M + (c & 1) * chunk_elems;
     const double4* Cb = S.cp + (c & 1) * tc;
     const double* Yb = S.Ys + (c & 1) * 8 * ldy + lr * ldy + 2 * lc;
@@ -334,13 +335,23 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
 
 template <int KS, bool GRAD, int NGT>
 __device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, const int* s_rows, const double* s_X,
-                                          const Smem& S, int gc_lo) {
+                                          const Smem& S, int gc_lo, Pipe& pipe) {
   if (P.family != CA_FAMILY_NB)
-    tile_pass_mode<KS, GRAD, NGT, MODE_POIS>(P, FT, s_rows, s_X, S, gc_lo);
+    tile_pass_mode<KS, GRAD, NGT, MODE_POIS>(P, FT, s_rows, s_X, S, gc_lo, pipe);
   else if (P.nu_per_row)
-    tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW>(P, FT, s_rows, s_X, S, gc_lo);
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW>(P, FT, s_rows, s_X, S, gc_lo, pipe);
   else
-    tile_pass_mode<KS, GRAD, NGT, MODE_NB_COL>(P, FT, s_rows, s_X, S, gc_lo);
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_COL>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+}
+
+__device__ __forceinline__ void pipe_init(Pipe& pipe, unsigned long long* bars) {
+  pipe.bar = bars;
+  pipe.phase = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_fence_init();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -357,9 +368,12 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_rowpass(PassCfg P, const 
   extern __shared__ __align__(16) double smem[];
   const Smem S = carve(smem, P.tc, KPAD, NGT * 8, false);
   __shared__ int s_rows[8];
+  __shared__ __align__(8) unsigned long long s_bars[2];
   const int total = rowlist ? *count : nrows;
   const int tile0 = blockIdx.x * TILE_ROWS;
   if (tile0 >= total) return;
+  Pipe pipe;
+  pipe_init(pipe, s_bars);
   const FmTables FT = fm_load_tables(S.tab, P.fm_tables);
   if (threadIdx.x < 8) {
     const int i = tile0 + threadIdx.x;
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_rowpass(PassCfg P, const 
     S.X[e] = (row >= 0) ? X[(size_t)row * KPAD + c] : 0.0;
   }
   __syncthreads();
-  tile_pass<KS, GRAD, NGT>(P, FT, s_rows, S.X, S, gc_lo);
+  tile_pass<KS, GRAD, NGT>(P, FT, s_rows, S.X, S, gc_lo, pipe);
   if (threadIdx.x < 8 && s_rows[threadIdx.x] >= 0) ell_out[s_rows[threadIdx.x]] = S.rowsum[threadIdx.x];
   if (GRAD) {
     for (int e = threadIdx.x; e < 8 * NGT * 8; e += NTHREADS) {
@@ -403,6 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
   extern __shared__ __align__(16) double smem[];
   const Smem S = carve(smem, P.tc, KPAD, 8, true);
   __shared__ int s_rows[8];
+  __shared__ __align__(8) unsigned long long s_bars[2];
   __shared__ double s_t[8], s_f0[8], s_ng[8], s_f01[8], s_e01[8], s_alpha[8], s_efin[8];
   __shared__ unsigned char s_done[8];
   __shared__ int s_mode[8], s_ne[8], s_alldone;
@@ -410,6 +425,8 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
   const int total = A.rowlist ? *A.count : A.nrows;
   const int tile0 = blockIdx.x * TILE_ROWS;
   if (tile0 >= total) return;
+  Pipe pipe;
+  pipe_init(pipe, s_bars);
   const FmTables FT = fm_load_tables(S.tab, P.fm_tables);
   if (tid < 8) {
     const int i = tile0 + tid;
@@ -446,7 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
       }
     }
     __syncthreads();
-    tile_pass<KS, false, 1>(P, FT, s_rows, S.X, S, 0);
+    tile_pass<KS, false, 1>(P, FT, s_rows, S.X, S, 0, pipe);
     if (tid < 8 && !s_done[tid]) {
       const int row = s_rows[tid];
       double pen = 0.0;
