@@ -106,10 +106,10 @@ struct NbClip {
 __device__ __forceinline__ double fm_rcp(double w) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(w));
+  // seed error e0 ~ 2^-20; one third-order step (r0 (1 + e + e^2)) leaves e0^3, one Newton step more
+  // takes it far below 2^-53
   double e = fma(-w, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-w, r, 1.0);
-  r = fma(r, e, r);
+  r = fma(r, fma(e, e, e), r);
   e = fma(-w, r, 1.0);
   return fma(r, e, r);
 }
