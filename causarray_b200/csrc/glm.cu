@@ -18,6 +18,7 @@
 // operand as is and, multiplied by w[cell], the A operand (DMMA m8n8k4); only
 // the upper-triangular 8x8 tiles are kept.  A second kernel solves the
 // (Jacobi-equilibrated) normal equations with a warp-level Cholesky.
+#include <algorithm>
 #include <vector>
 #include <new>
 
@@ -53,8 +54,9 @@ struct GlmPass {
   double* dev_prev;      // p
   int* status;           // p : 0 running, 1 converged, 2 numeric failure
   int* n_iter;           // p
-  double* gram;          // p x kx x kx
-  double* rhs;           // p x kx
+  double* part;          // per (slot, split): kx*kx Gram | kx rhs | 3 deviance sums  (stride part_ld)
+  int part_ld;
+  int nsplit;            // cell-range splits per gene (gridDim.y); > 1 when few genes are still running
   double* mu_t;          // p x ldn or nullptr (finalize)
   int iter;              // 1-based index of the update this pass prepares
   double tol;
@@ -111,7 +113,9 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
   for (int i = 0; i < NT; ++i) racc[i] = 0.0;
   double s_yeta = 0.0, s_mu = 0.0, s_log = 0.0;
 
-  const int nchunks = (P.n + GLM_CHUNK - 1) / GLM_CHUNK;
+  const int nchunks_all = (P.n + GLM_CHUNK - 1) / GLM_CHUNK;
+  const int c_lo = (int)((long)blockIdx.y * nchunks_all / P.nsplit);
+  const int c_hi = (int)((long)(blockIdx.y + 1) * nchunks_all / P.nsplit);
   auto stage = [&](int c, int buf) {
     const int c0 = c * GLM_CHUNK;
     const int nvalid = min(GLM_CHUNK, P.n - c0);
@@ -123,11 +127,12 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
     for (int i = tid; i < GLM_CHUNK; i += GLM_THREADS)
       offs[buf * GLM_CHUNK + i] = (P.offset && c0 + i < P.n) ? P.offset[c0 + i] : 0.0;
   };
-  stage(0, 0);
+  if (c_lo < c_hi) stage(c_lo, 0);
   cp_async_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) {
-      stage(c + 1, (c + 1) & 1);
+  for (int c = c_lo; c < c_hi; ++c) {
+    const int cb = (c - c_lo) & 1;
+    if (c + 1 < c_hi) {
+      stage(c + 1, cb ^ 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
     }
     __syncthreads();
     if (active) {
-      const double* Xc = Xs + (c & 1) * GLM_CHUNK * ldx;
-      const double* oc = offs + (c & 1) * GLM_CHUNK;
+      const double* Xc = Xs + cb * GLM_CHUNK * ldx;
+      const double* oc = offs + cb * GLM_CHUNK;
       const double* bw = betas + warp * ldx;
       for (int blk = 0; blk < GLM_CHUNK; blk += 32) {
         const int cell = c * GLM_CHUNK + blk + lane;
@@ -205,42 +210,18 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
     __syncthreads();
   }
   if (!active) return;
-  // ---- deviance at the current beta and convergence bookkeeping ----
+  // ---- partial sums of this (gene, cell range): Gram (upper tiles mirrored), rhs, deviance terms ----
   s_yeta = warp_sum(s_yeta);
   s_mu = warp_sum(s_mu);
   s_log = warp_sum(s_log);
-  const double sy = P.cst[(size_t)gene * 3 + 0], sylogy = P.cst[(size_t)gene * 3 + 1], synu = P.cst[(size_t)gene * 3 + 2];
-  double dev;
-  if (pois)
-    dev = 2.0 * ((sylogy - s_yeta) - (sy - s_mu));
-  else
-    dev = 2.0 * ((sylogy - s_yeta) - (synu - s_log));
-  bool run = true;
+  double* part = P.part + ((size_t)slot * P.nsplit + blockIdx.y) * P.part_ld;
   if (lane == 0) {
-    if (P.finalize) {
-      P.dev[gene] = dev;
-    } else {
-      const double prev = P.dev_prev[gene];
-      P.dev[gene] = dev;
-      if (!(dev == dev) || isinf(dev)) {
-        P.status[gene] = 2;
-        P.n_iter[gene] = P.iter - 1;
-        run = false;
-      } else if (!first && fabs(dev - prev) <= P.tol) {
-        P.status[gene] = 1;
-        P.n_iter[gene] = P.iter - 1;
-        run = false;
-      } else {
-        P.dev_prev[gene] = dev;
-        atomicAdd(P.n_active, 1);
-      }
-    }
+    part[kx * kx + kx + 0] = s_yeta;
+    part[kx * kx + kx + 1] = s_mu;
+    part[kx * kx + kx + 2] = s_log;
   }
   if (P.finalize) return;
-  run = __shfl_sync(0xffffffffu, run ? 1 : 0, 0) != 0;
-  if (!run) return;
-  // ---- write the Gram (upper tiles mirrored) and rhs ----
-  double* G = P.gram + (size_t)gene * kx * kx;
+  double* G = part;
   int idx = 0;
 #pragma unroll
   for (int mt = 0; mt < NT; ++mt)
@@ -264,40 +245,124 @@ __global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     const int col = lr + 8 * t;
-    if (lc == 0 && col < kx) P.rhs[(size_t)gene * kx + col] = v;
+    if (lc == 0 && col < kx) part[kx * kx + col] = v;
   }
 }
 
-// Warp-level Cholesky solve of the Jacobi-scaled normal equations, one gene per warp.
-__global__ void k_glm_solve(int p, int kx, const double* __restrict__ gram, const double* __restrict__ rhs,
-                            const double* __restrict__ ridge, int* __restrict__ status, double* __restrict__ beta,
-                            int iter, int* __restrict__ n_iter) {
+// Per running gene (one warp): combine the cell-range partials in fixed order, evaluate the
+// deviance at the current beta and the convergence test of the previous update
+// (|dev - dev_prev| <= tol), and -- if the gene keeps running -- solve the Jacobi-equilibrated
+// normal equations of the next update with a warp-level Cholesky.
+struct GlmSolve {
+  int p, kx, nslots, nsplit, part_ld;
+  const int* genelist;   // nullptr = identity
+  const double* part;
+  const double* ridge;   // kx or nullptr
+  const double* nu;
+  int family;
+  double thres;
+  const double* cst;
+  double* dev;
+  double* dev_prev;
+  int* status;
+  int* n_iter;
+  double* beta;
+  int iter;
+  double tol;
+  int finalize;          // only the deviance
+  int* n_active;
+};
+
+__global__ void k_glm_solve(GlmSolve Q) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
-  const int gene = blockIdx.x * nw + warp;
-  if (gene >= p) return;
-  if (status[gene] != 0) return;
+  const int slot = blockIdx.x * nw + warp;
+  if (slot >= Q.nslots) return;
+  const int gene = Q.genelist ? Q.genelist[slot] : slot;
+  const int kx = Q.kx;
+  if (!Q.finalize && Q.status[gene] != 0) return;
+  const double* part0 = Q.part + (size_t)slot * Q.nsplit * Q.part_ld;
+  // ---- deviance ----
+  double s_yeta = 0.0, s_mu = 0.0, s_log = 0.0;
+  for (int sp = 0; sp < Q.nsplit; ++sp) {
+    const double* ps = part0 + (size_t)sp * Q.part_ld + kx * kx + kx;
+    s_yeta += ps[0];
+    s_mu += ps[1];
+    s_log += ps[2];
+  }
+  bool pois = true;
+  if (Q.family == CA_FAMILY_NB && Q.nu) pois = Q.nu[gene] > Q.thres;
+  const double sy = Q.cst[(size_t)gene * 3 + 0], sylogy = Q.cst[(size_t)gene * 3 + 1], synu = Q.cst[(size_t)gene * 3 + 2];
+  const double dev = pois ? 2.0 * ((sylogy - s_yeta) - (sy - s_mu)) : 2.0 * ((sylogy - s_yeta) - (synu - s_log));
+  if (Q.finalize) {
+    if (lane == 0) Q.dev[gene] = dev;
+    return;
+  }
+  bool run = true;
+  {
+    const double prev = Q.dev_prev[gene];
+    if (!(dev == dev) || isinf(dev)) {
+      run = false;
+      if (lane == 0) {
+        Q.status[gene] = 2;
+        Q.n_iter[gene] = Q.iter - 1;
+      }
+    } else if (Q.iter > 1 && fabs(dev - prev) <= Q.tol) {
+      run = false;
+      if (lane == 0) {
+        Q.status[gene] = 1;
+        Q.n_iter[gene] = Q.iter - 1;
+      }
+    }
+    if (lane == 0) {
+      Q.dev[gene] = dev;
+      if (run) {
+        Q.dev_prev[gene] = dev;
+        atomicAdd(Q.n_active, 1);
+      }
+    }
+  }
+  if (!run) return;
+  // ---- normal equations ----
   const int ld = kx + 1;
   double* L = sm + (size_t)warp * (kx * ld + 2 * kx);
   double* sc = L + kx * ld;
   double* b = sc + kx;
-  const double* G = gram + (size_t)gene * kx * kx;
+  for (int e = lane; e < kx * kx; e += 32) {
+    // fixed summation order over the splits; loads issued eight at a time
+    double g = 0.0;
+    int sp = 0;
+    for (; sp + 8 <= Q.nsplit; sp += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part0[(size_t)(sp + u) * Q.part_ld + e];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) g += v[u];
+    }
+    for (; sp < Q.nsplit; ++sp) g += part0[(size_t)sp * Q.part_ld + e];
+    const int i = e / kx, j = e % kx;
+    if (Q.ridge && i == j) g += Q.ridge[i];
+    L[i * ld + j] = g;
+  }
   for (int i = lane; i < kx; i += 32) {
-    const double dgn = G[i * kx + i] + (ridge ? ridge[i] : 0.0);
-    sc[i] = dgn > 0.0 ? 1.0 / sqrt(dgn) : 0.0;
+    double r = 0.0;
+    for (int sp = 0; sp < Q.nsplit; ++sp) r += part0[(size_t)sp * Q.part_ld + kx * kx + i];
+    b[i] = r;
   }
   __syncwarp();
   bool bad = false;
+  for (int i = lane; i < kx; i += 32) {
+    const double dgn = L[i * ld + i];
+    sc[i] = dgn > 0.0 ? 1.0 / sqrt(dgn) : 0.0;
+    if (!(dgn > 0.0)) bad = true;
+  }
+  __syncwarp();
   for (int e = lane; e < kx * kx; e += 32) {
     const int i = e / kx, j = e % kx;
-    const double add = (ridge && i == j) ? ridge[i] : 0.0;
-    L[i * ld + j] = (G[e] + add) * sc[i] * sc[j];
+    L[i * ld + j] *= sc[i] * sc[j];
   }
-  for (int i = lane; i < kx; i += 32) {
-    b[i] = rhs[(size_t)gene * kx + i] * sc[i];
-    if (sc[i] == 0.0) bad = true;
-  }
+  for (int i = lane; i < kx; i += 32) b[i] *= sc[i];
   __syncwarp();
   // right-looking Cholesky, lower triangle
   for (int j = 0; j < kx; ++j) {
@@ -316,32 +381,39 @@ __global__ void k_glm_solve(int p, int kx, const double* __restrict__ gram, cons
   bad = __any_sync(0xffffffffu, bad);
   if (bad) {
     if (lane == 0) {
-      status[gene] = 2;
-      n_iter[gene] = iter;
+      Q.status[gene] = 2;
+      Q.n_iter[gene] = Q.iter;
+      atomicAdd(Q.n_active, -1);
     }
     return;
   }
-  // forward / backward substitution (lane 0; kx <= 64)
+  // forward / backward substitution: the dot product of every row is spread over the lanes and
+  // reduced with a fixed shuffle tree (kx <= 64)
+  for (int i = 0; i < kx; ++i) {
+    double s = 0.0;
+    for (int c = lane; c < i; c += 32) s += L[i * ld + c] * b[c];
+    s = warp_sum(s);
+    if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+    __syncwarp();
+  }
+  for (int i = kx - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int c = i + 1 + lane; c < kx; c += 32) s += L[c * ld + i] * b[c];
+    s = warp_sum(s);
+    if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+    __syncwarp();
+  }
   if (lane == 0) {
-    for (int i = 0; i < kx; ++i) {
-      double s = b[i];
-      for (int c = 0; c < i; ++c) s -= L[i * ld + c] * b[c];
-      b[i] = s / L[i * ld + i];
-    }
-    for (int i = kx - 1; i >= 0; --i) {
-      double s = b[i];
-      for (int c = i + 1; c < kx; ++c) s -= L[c * ld + i] * b[c];
-      b[i] = s / L[i * ld + i];
-    }
     bool fin = true;
     for (int i = 0; i < kx; ++i) {
       const double v = b[i] * sc[i];
-      beta[(size_t)gene * kx + i] = v;
+      Q.beta[(size_t)gene * kx + i] = v;
       fin = fin && (v == v) && !isinf(v);
     }
     if (!fin) {
-      status[gene] = 2;
-      n_iter[gene] = iter;
+      Q.status[gene] = 2;
+      Q.n_iter[gene] = Q.iter;
+      atomicAdd(Q.n_active, -1);
     }
   }
 }
@@ -492,7 +564,7 @@ static int launch_pass_nt(const GlmPass& P, cudaStream_t st) {
   CA_CUDA(cudaFuncSetAttribute(k_glm_pass<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int nslots = P.genelist ? P.n_list : P.p;
   if (nslots <= 0) return 0;
-  const int grid = (nslots + GLM_WARPS - 1) / GLM_WARPS;
+  const dim3 grid((nslots + GLM_WARPS - 1) / GLM_WARPS, P.nsplit);
   ProfScope prof(PROF_GLM_PASS, st);
   k_glm_pass<NT><<<grid, GLM_THREADS, sm, st>>>(P);
   CA_LAUNCH_CHECK();
@@ -581,7 +653,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   const int ldx = kpad_for(kx);
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
       h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
-      h->gram.alloc((size_t)p * kx * kx) || h->rhs.alloc((size_t)p * kx) || h->mu_t.alloc((size_t)p * h->ldn) ||
+      h->part.alloc((size_t)p * (kx * kx + kx + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
       h->counter.alloc(2) || h->offset.alloc(n) || h->nu.alloc(p) || h->ridge.alloc(kx))
     return -1;
   CA_REQUIRE(!gene_mask || h->fit_kx == kx, "gene_mask refit needs a previous fit of the same width");
@@ -636,8 +708,9 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   P.dev_prev = h->dev_prev.ptr;
   P.status = h->status.ptr;
   P.n_iter = h->n_iter.ptr;
-  P.gram = h->gram.ptr;
-  P.rhs = h->rhs.ptr;
+  P.part = h->part.ptr;
+  P.part_ld = kx * kx + kx + 4;
+  P.nsplit = 1;
   P.mu_t = nullptr;
   P.tol = tol;
   P.finalize = 0;
@@ -650,11 +723,44 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   const int solve_warps = 4;
   const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 2 * kx);
   CA_CUDA(cudaFuncSetAttribute(k_glm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_sm));
+  GlmSolve Q;
+  Q.p = p;
+  Q.kx = kx;
+  Q.part_ld = P.part_ld;
+  Q.part = h->part.ptr;
+  Q.ridge = ridge ? h->ridge.ptr : nullptr;
+  Q.nu = P.nu;
+  Q.family = family;
+  Q.thres = thres_disp;
+  Q.cst = h->cst.ptr;
+  Q.dev = h->dev.ptr;
+  Q.dev_prev = h->dev_prev.ptr;
+  Q.status = h->status.ptr;
+  Q.n_iter = h->n_iter.ptr;
+  Q.beta = h->beta.ptr;
+  Q.tol = tol;
+  Q.finalize = 0;
+  Q.n_active = h->counter.ptr;
+  int sm_count = 148;
+  {
+    int devid = 0;
+    cudaGetDevice(&devid);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, devid);
+  }
+  const int nchunks = (n + GLM_CHUNK - 1) / GLM_CHUNK;
+  auto launch_solve = [&](int nslots) -> int {
+    if (nslots <= 0) return 0;
+    ProfScope prof(PROF_GLM_SOLVE, st);
+    k_glm_solve<<<(nslots + solve_warps - 1) / solve_warps, solve_warps * 32, solve_sm, st>>>(Q);
+    CA_LAUNCH_CHECK();
+    return 0;
+  };
   int iters_done = 0;
   int nrun = p;  // genes still running (gene_mask refits start from the flagged subset)
   for (int it = 1; it <= maxiter; ++it) {
-    // pass `it` evaluates the deviance after update it-1 (convergence test of that update)
-    // and, for genes still running, accumulates the normal equations of update `it`
+    // pass `it` accumulates, per running gene, the deviance terms at the current beta and the
+    // normal equations of update `it`; the solve kernel then applies the convergence test of
+    // update it-1 and, for genes that keep running, performs update `it`
     if (it > 1 || gene_mask) {
       k_glm_active_list<<<1, 1024, 0, st>>>(h->status.ptr, p, h->genelist.ptr, h->counter.ptr + 1);
       CA_LAUNCH_CHECK();
@@ -665,31 +771,48 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
       P.genelist = h->genelist.ptr;
       P.n_list = nrun;
     }
-    CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int), st));
-    P.iter = it;
-    if (launch_pass(P, st)) return -1;
+    if (nrun <= 0) break;
+    // few running genes: split the cells of each gene over several CTAs so that the tail
+    // iterations are not bound by the latency of one CTA walking all n cells
+    const int ctas = (nrun + GLM_WARPS - 1) / GLM_WARPS;
+    int nsplit = 1;
+    if (ctas < 2 * sm_count) nsplit = std::min(std::min(nchunks, 8), std::max(1, (2 * sm_count) / ctas));
+    while (nsplit > 1 && (long)nrun * nsplit > (long)p) --nsplit;
+    P.nsplit = nsplit;
+    Q.genelist = P.genelist;
+    Q.nslots = nrun;
+    Q.nsplit = nsplit;
+    // tail (few running genes): enqueue several iterations per host synchronisation; genes that
+    // converge in between are skipped on the device through their status flag
+    const int burst = (nrun <= 64) ? std::min(8, maxiter - it + 1) : 1;
     int nact = 0;
+    for (int b = 0; b < burst; ++b) {
+      P.iter = it + b;
+      Q.iter = it + b;
+      CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int), st));
+      if (launch_pass(P, st)) return -1;
+      if (launch_solve(nrun)) return -1;
+    }
     CA_CUDA(cudaMemcpyAsync(&nact, h->counter.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     CA_CUDA(cudaStreamSynchronize(st));
-    if (nact == 0) break;
-    {
-      ProfScope prof(PROF_GLM_SOLVE, st);
-      k_glm_solve<<<(p + solve_warps - 1) / solve_warps, solve_warps * 32, solve_sm, st>>>(
-          p, kx, h->gram.ptr, h->rhs.ptr, ridge ? h->ridge.ptr : nullptr, h->status.ptr, h->beta.ptr, it,
-          h->n_iter.ptr);
-      CA_LAUNCH_CHECK();
-    }
+    it += burst - 1;
+    if (nact == 0) break;  // every gene has converged (its iteration count was recorded on the device)
     nrun = nact;
     iters_done = it;
   }
+  // finalize: fitted means + deviance at the final beta for every gene
   P.genelist = nullptr;
   P.n_list = 0;
-  // finalize: fitted means + deviance at the final beta for every gene
+  P.nsplit = 1;
   P.finalize = 1;
-  P.iter = iters_done + 1;
+  P.iter = 2;  // never "first" in finalize
   P.mu_t = h->mu_t.ptr;
-  if (iters_done == 0) P.iter = 2;  // never "first" in finalize
   if (launch_pass(P, st)) return -1;
+  Q.genelist = nullptr;
+  Q.nslots = p;
+  Q.nsplit = 1;
+  Q.finalize = 1;
+  if (launch_solve(p)) return -1;
   h->iters_done = iters_done;
   // genes still "running" after maxiter updates: n_iter = maxiter
   if (d_guard >= 0) {
@@ -705,7 +828,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   for (int j = 0; j < p; ++j) {
     int s = hs[j];
     int it = hi[j];
-    if (s == 0) it = iters_done;  // hit maxiter without meeting the tolerance
+    if (s == 0) it = maxiter;  // hit maxiter without meeting the tolerance
     // report: 0 ok (converged or maxiter), 1 guard tripped, 2 numeric failure
     int rep = (s == 3) ? 1 : (s == 2 ? 2 : 0);
     if (status) status[j] = rep;
