@@ -92,6 +92,7 @@ def gpu_step(batch, resident_ws=None):
     w = WORKLOAD
     es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
     cglm.COUNTERS["irls_gene_iters"] = 0
+    cglm.COUNTERS["gram_flops"] = 0.0
     Y, X, A, X_A = batch["Y"], batch["X"], batch["A"], batch["X_A"]
     res1, res2 = cb.fit_gcate(Y, X, A, w["r"], family=w["family"], disp_glm=batch["disp"], offset=True,
                               kwargs_es_1=dict(es), kwargs_es_2=dict(es), _ws=resident_ws)
@@ -111,6 +112,7 @@ def gpu_step(batch, resident_ws=None):
                  cell_evals=res1["line_search_evals"][0] + res2["line_search_evals"][0],
                  gene_evals=res1["line_search_evals"][1] + res2["line_search_evals"][1],
                  loop_seconds=res1["loop_seconds"] + res2["loop_seconds"], n=n, p=p,
+                 gram_flops=cglm.COUNTERS["gram_flops"],
                  n_sig=int(np.nansum(df["padj"].to_numpy() < 0.05)))
     return df, stats
 
@@ -277,7 +279,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     # per-kernel-class algorithmic bytes over the timed resident steps (rank 0)
     st_sum = {k: sum(s[k] for s in stats_res) for k in ("cell_updates", "gene_rows", "cell_evals", "gene_evals",
-                                                         "irls_gene_iters", "alt_iters")}
+                                                         "irls_gene_iters", "alt_iters", "gram_flops")}
     alg_bytes = {
         # Y read once per active row: cells x p + genes x n doubles
         "rowpass_grad": 8.0 * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
@@ -292,16 +294,30 @@ def main():
         kern[name] = {"ms": round(ms, 3), "launches": cnt, "share": round(ms / tot_ms, 4)}
         if name in alg_bytes and ms > 0:
             kern[name]["achieved_gbs"] = round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1)
+    fp64_peak_tflops = 36.5   # DMMA m8n8k4 / DFMA peak measured on this pool's B200 (tools/fp64_microbench.cu)
+    if prof.get("glm_pass", (0, 0))[0] > 0:
+        kern["glm_pass"]["achieved_tflops_fp64"] = round(st_sum["gram_flops"] / (prof["glm_pass"][0] * 1e-3) / 1e12, 2)
     dom = max((k for k in alg_bytes if prof.get(k, (0, 0))[0] > 0), key=lambda k: prof[k][0], default=None)
     roofline = None
-    if dom is not None:
+    if dom == "glm_pass":
+        ms, cnt = prof[dom]
+        ach = st_sum["gram_flops"] / (ms * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": fp64_peak_tflops,
+                    "unit": "TFLOP/s", "frac": round(ach / fp64_peak_tflops, 4), "traffic": None,
+                    "peak_source": "FP64 DMMA (mma.sync m8n8k4.f64) peak measured with tools/fp64_microbench.cu on this "
+                                   "pool's B200; MEASURED_PEAKS.json only holds the bf16 tensor and HBM figures and "
+                                   "tcgen05 has no FP64 kind",
+                    "avg_launch_ms": round(ms / max(1, cnt), 4), "launches": cnt,
+                    "algorithmic_flops_per_cell_gene_iter": "2 [kx(kx+1)/2 + 2 kx]",
+                    "hbm_view": {"achieved_gbs": round(alg_bytes[dom] / (ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak}}
+    elif dom is not None:
         ms, cnt = prof[dom]
         ach = alg_bytes[dom] / (ms * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": round(ms / max(1, cnt), 4), "launches": cnt,
-                    "note": "FP64 transcendental-bound kernel; see DESIGN.md for the FP64 (36.5 TFLOP/s measured) "
-                            "roofline of the same kernel"}
+                    "note": "FP64-pipe bound kernel (DMMA + table-driven exp/log share the FP64 units); see DESIGN.md "
+                            "section 4 for the FP64 roofline of the same kernel"}
 
     out = {"metric": "gcate_lfc_cell_gene_updates_per_s", "value": upd_res / t_res, "unit": "cell*gene updates/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -30,224 +30,9 @@
 #include "gcate_state.h"
 #include "prof.h"
 #include "fastmath.cuh"
+#include "glm_pass_impl.cuh"
 
 namespace ca {
-
-constexpr int GLM_WARPS = 8;
-constexpr int GLM_THREADS = GLM_WARPS * 32;
-constexpr int GLM_CHUNK = 128;  // cells per staged chunk
-
-struct GlmPass {
-  const double* Yt;      // p x ldn raw counts, gene-major
-  long ldn;
-  int n, p;
-  const double* X;       // n x ldx (padded, ldx % 8 == 4)
-  int kx, ldx;
-  const double* offset;  // n or nullptr
-  const double* nu;      // p or nullptr
-  int family;
-  double thres;
-  const double* beta;    // p x kx
-  const double* ybar;    // p
-  const double* cst;     // p x 3 : sum y, sum y log y, sum (y+nu) log(y+nu)
-  double* dev;           // p : deviance at the current beta
-  double* dev_prev;      // p
-  int* status;           // p : 0 running, 1 converged, 2 numeric failure
-  int* n_iter;           // p
-  double* part;          // per (slot, split): kx*kx Gram | kx rhs | 3 deviance sums  (stride part_ld)
-  int part_ld;
-  int nsplit;            // cell-range splits per gene (gridDim.y); > 1 when few genes are still running
-  double* mu_t;          // p x ldn or nullptr (finalize)
-  int iter;              // 1-based index of the update this pass prepares
-  double tol;
-  int finalize;          // 1: only deviance (+ mu_t), no Gram
-  int* n_active;         // device counter of genes still running after this pass
-  const int* genelist;   // compacted list of running genes (nullptr = all genes)
-  int n_list;            // entries of genelist
-  const double* fm_tables;
-};
-
-template <int NT>
-__global__ void __launch_bounds__(GLM_THREADS) k_glm_pass(GlmPass P) {
-  extern __shared__ __align__(16) double smem[];
-  const int ldx = P.ldx, kx = P.kx;
-  double* Xs = smem;                               // 2 * GLM_CHUNK * ldx
-  double* betas = Xs + 2 * GLM_CHUNK * ldx;        // GLM_WARPS * ldx
-  double* offs = betas + GLM_WARPS * ldx;          // 2 * GLM_CHUNK
-  double* s_tab = offs + 2 * GLM_CHUNK;            // FM_TABLE_DOUBLES
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lr = lane >> 2, lc = lane & 3;
-  const int slot = blockIdx.x * GLM_WARPS + warp;
-  const int gene = P.genelist ? (slot < P.n_list ? P.genelist[slot] : P.p) : slot;
-  const bool gene_ok = gene < P.p;
-  const FmTables FT = fm_load_tables(s_tab, P.fm_tables);
-  bool active = gene_ok && (P.finalize ? true : (P.status[gene] == 0));
-  // CTA-wide early out when nothing to do
-  {
-    __shared__ int any;
-    if (tid == 0) any = 0;
-    __syncthreads();
-    if (active && lane == 0) atomicOr(&any, 1);
-    __syncthreads();
-    if (!any) return;
-  }
-  const bool first = (P.iter == 1) && !P.finalize;
-  double nu = 1.0;
-  bool pois = true;
-  if (gene_ok && P.family == CA_FAMILY_NB && P.nu) {
-    nu = P.nu[gene];
-    pois = nu > P.thres;
-  }
-  const double ybar = gene_ok ? P.ybar[gene] : 1.0;
-  const int rot0 = lane % kx;
-  for (int c = lane; c < ldx; c += 32) betas[warp * ldx + c] = (gene_ok && c < kx && !first) ? P.beta[(size_t)gene * kx + c] : 0.0;
-  const double* yrow = P.Yt + (size_t)(gene_ok ? gene : 0) * P.ldn;
-  double* murow = (P.mu_t && gene_ok) ? P.mu_t + (size_t)gene * P.ldn : nullptr;
-
-  constexpr int NTRI = NT * (NT + 1) / 2;
-  double acc[NTRI][2];
-#pragma unroll
-  for (int i = 0; i < NTRI; ++i) acc[i][0] = acc[i][1] = 0.0;
-  double racc[NT];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) racc[i] = 0.0;
-  double s_yeta = 0.0, s_mu = 0.0, s_log = 0.0;
-
-  const int nchunks_all = (P.n + GLM_CHUNK - 1) / GLM_CHUNK;
-  const int c_lo = (int)((long)blockIdx.y * nchunks_all / P.nsplit);
-  const int c_hi = (int)((long)(blockIdx.y + 1) * nchunks_all / P.nsplit);
-  auto stage = [&](int c, int buf) {
-    const int c0 = c * GLM_CHUNK;
-    const int nvalid = min(GLM_CHUNK, P.n - c0);
-    const int nvec = nvalid * ldx / 2;
-    const double* src = P.X + (size_t)c0 * ldx;
-    double* dst = Xs + buf * GLM_CHUNK * ldx;
-    for (int i = tid; i < nvec; i += GLM_THREADS) cp_async16(dst + 2 * i, src + 2 * i);
-    for (int i = nvalid * ldx + tid; i < GLM_CHUNK * ldx; i += GLM_THREADS) dst[i] = 0.0;
-    for (int i = tid; i < GLM_CHUNK; i += GLM_THREADS)
-      offs[buf * GLM_CHUNK + i] = (P.offset && c0 + i < P.n) ? P.offset[c0 + i] : 0.0;
-  };
-  if (c_lo < c_hi) stage(c_lo, 0);
-  cp_async_commit();
-  for (int c = c_lo; c < c_hi; ++c) {
-    const int cb = (c - c_lo) & 1;
-    if (c + 1 < c_hi) {
-      stage(c + 1, cb ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    if (active) {
-      const double* Xc = Xs + cb * GLM_CHUNK * ldx;
-      const double* oc = offs + cb * GLM_CHUNK;
-      const double* bw = betas + warp * ldx;
-      for (int blk = 0; blk < GLM_CHUNK; blk += 32) {
-        const int cell = c * GLM_CHUNK + blk + lane;
-        const bool ok = cell < P.n;
-        if (c * GLM_CHUNK + blk >= P.n) break;
-        const double y = ok ? yrow[cell] : 0.0;
-        const double off = oc[blk + lane];
-        double eta, mu;
-        if (first) {
-          mu = 0.5 * (y + ybar);
-          eta = fm_log(mu, FT.log_t);
-        } else {
-          // lane-rotated column order: lane l reads column (q + l) mod kx at step q, which makes
-          // the row-strided shared-memory reads conflict free; two partial sums for ILP
-          const double* xr = Xc + (blk + lane) * ldx;
-          double ea = 0.0, eb = 0.0;
-          int idx = rot0;
-          for (int q = 0; q + 1 < kx; q += 2) {
-            ea = fma(xr[idx], bw[idx], ea);
-            idx = (idx + 1 >= kx) ? idx + 1 - kx : idx + 1;
-            eb = fma(xr[idx], bw[idx], eb);
-            idx = (idx + 1 >= kx) ? idx + 1 - kx : idx + 1;
-          }
-          if (kx & 1) ea = fma(xr[idx], bw[idx], ea);
-          eta = (ea + eb) + off;
-          mu = fm_exp(fmin(fmax(eta, -700.0), 700.0), FT.exp_t);
-        }
-        double w = 0.0, wz = 0.0;
-        if (ok) {
-          s_yeta += y * eta;  // y * log(mu): eta IS log(mu) (iteration 1: log mu0 without offset)
-          s_mu += mu;
-          if (!pois) s_log += (y + nu) * fm_log(mu + nu, FT.log_t);
-          if (murow) murow[cell] = mu;
-          if (!P.finalize) {
-            w = pois ? mu : mu * nu * fm_rcp(nu + mu);
-            const double z = eta + (y - mu) * __drcp_rn(mu) - off;
-            wz = w * z;
-          }
-        }
-        if (!P.finalize) {
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const int src = s * 4 + lc;
-            const double ws = __shfl_sync(0xffffffffu, w, src);
-            const double wzs = __shfl_sync(0xffffffffu, wz, src);
-            const double* xp = Xc + (blk + src) * ldx + lr;
-            double xv[NT], av[NT];
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-              xv[t] = xp[8 * t];
-              av[t] = ws * xv[t];
-              racc[t] = fma(wzs, xv[t], racc[t]);
-            }
-            int idx = 0;
-#pragma unroll
-            for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-              for (int nt = mt; nt < NT; ++nt) {
-                dmma884(acc[idx][0], acc[idx][1], av[mt], xv[nt]);
-                ++idx;
-              }
-          }
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (!active) return;
-  // ---- partial sums of this (gene, cell range): Gram (upper tiles mirrored), rhs, deviance terms ----
-  s_yeta = warp_sum(s_yeta);
-  s_mu = warp_sum(s_mu);
-  s_log = warp_sum(s_log);
-  double* part = P.part + ((size_t)slot * P.nsplit + blockIdx.y) * P.part_ld;
-  if (lane == 0) {
-    part[kx * kx + kx + 0] = s_yeta;
-    part[kx * kx + kx + 1] = s_mu;
-    part[kx * kx + kx + 2] = s_log;
-  }
-  if (P.finalize) return;
-  double* G = part;
-  int idx = 0;
-#pragma unroll
-  for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-    for (int nt = mt; nt < NT; ++nt) {
-      const int m = 8 * mt + lr;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int nn = 8 * nt + 2 * lc + i;
-        if (m < kx && nn < kx) {
-          G[m * kx + nn] = acc[idx][i];
-          if (nt != mt) G[nn * kx + m] = acc[idx][i];
-        }
-      }
-      ++idx;
-    }
-  // rhs: lane holds partial over its cells (lc) for column lr + 8t -> reduce over lc
-#pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    double v = racc[t];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    const int col = lr + 8 * t;
-    if (lc == 0 && col < kx) part[kx * kx + col] = v;
-  }
-}
 
 // Per running gene (one warp): combine the cell-range partials in fixed order, evaluate the
 // deviance at the current beta and the convergence test of the previous update
@@ -558,30 +343,17 @@ __global__ void k_disp_moments(const double* __restrict__ Yt, const double* __re
   }
 }
 
-template <int NT>
-static int launch_pass_nt(const GlmPass& P, cudaStream_t st) {
-  const size_t sm = sizeof(double) * ((size_t)2 * GLM_CHUNK * P.ldx + GLM_WARPS * P.ldx + 2 * GLM_CHUNK + FM_TABLE_DOUBLES);
-  CA_CUDA(cudaFuncSetAttribute(k_glm_pass<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  const int nslots = P.genelist ? P.n_list : P.p;
-  if (nslots <= 0) return 0;
-  const dim3 grid((nslots + GLM_WARPS - 1) / GLM_WARPS, P.nsplit);
-  ProfScope prof(PROF_GLM_PASS, st);
-  k_glm_pass<NT><<<grid, GLM_THREADS, sm, st>>>(P);
-  CA_LAUNCH_CHECK();
-  return 0;
-}
-
 static int launch_pass(const GlmPass& P, cudaStream_t st) {
   const int nt = (P.kx + 7) / 8;
   switch (nt) {
-    case 1: return launch_pass_nt<1>(P, st);
-    case 2: return launch_pass_nt<2>(P, st);
-    case 3: return launch_pass_nt<3>(P, st);
-    case 4: return launch_pass_nt<4>(P, st);
-    case 5: return launch_pass_nt<5>(P, st);
-    case 6: return launch_pass_nt<6>(P, st);
-    case 7: return launch_pass_nt<7>(P, st);
-    case 8: return launch_pass_nt<8>(P, st);
+    case 1: return launch_glm_pass_nt<1>(P, st);
+    case 2: return launch_glm_pass_nt<2>(P, st);
+    case 3: return launch_glm_pass_nt<3>(P, st);
+    case 4: return launch_glm_pass_nt<4>(P, st);
+    case 5: return launch_glm_pass_nt<5>(P, st);
+    case 6: return launch_glm_pass_nt<6>(P, st);
+    case 7: return launch_glm_pass_nt<7>(P, st);
+    case 8: return launch_glm_pass_nt<8>(P, st);
   }
   set_error("design wider than 64 columns");
   return -2;
@@ -650,17 +422,18 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
   const int n = h->n, p = h->p;
   cudaStream_t st = h->st;
-  const int ldx = kpad_for(kx);
+  const int ldx = 8 * ((kx + 7) / 8) + 4;
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
       h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
       h->part.alloc((size_t)p * (kx * kx + kx + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
-      h->counter.alloc(2) || h->offset.alloc(n) || h->nu.alloc(p) || h->ridge.alloc(kx))
+      h->counter.alloc(2) || h->offset.alloc((size_t)n + 8) || h->nu.alloc(p) || h->ridge.alloc(kx))
     return -1;
   CA_REQUIRE(!gene_mask || h->fit_kx == kx, "gene_mask refit needs a previous fit of the same width");
   h->fit_kx = kx;
   CA_CUDA(cudaMemsetAsync(h->X.ptr, 0, h->X.bytes(), st));
   CA_CUDA(cudaMemcpy2DAsync(h->X.ptr, sizeof(double) * ldx, X, sizeof(double) * kx, sizeof(double) * kx, n,
                             cudaMemcpyHostToDevice, st));
+  CA_CUDA(cudaMemsetAsync(h->offset.ptr, 0, h->offset.bytes(), st));
   if (offset) CA_CUDA(cudaMemcpyAsync(h->offset.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   if (nu) CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu, sizeof(double) * p, cudaMemcpyHostToDevice, st));
   if (ridge) CA_CUDA(cudaMemcpyAsync(h->ridge.ptr, ridge, sizeof(double) * kx, cudaMemcpyHostToDevice, st));
@@ -697,24 +470,18 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   P.X = h->X.ptr;
   P.kx = kx;
   P.ldx = ldx;
-  P.offset = offset ? h->offset.ptr : nullptr;
+  P.offset = h->offset.ptr;
   P.nu = h->has_nu ? h->nu.ptr : nullptr;
   P.family = family;
   P.thres = thres_disp;
   P.beta = h->beta.ptr;
   P.ybar = h->ybar.ptr;
-  P.cst = h->cst.ptr;
-  P.dev = h->dev.ptr;
-  P.dev_prev = h->dev_prev.ptr;
   P.status = h->status.ptr;
-  P.n_iter = h->n_iter.ptr;
   P.part = h->part.ptr;
   P.part_ld = kx * kx + kx + 4;
   P.nsplit = 1;
   P.mu_t = nullptr;
-  P.tol = tol;
   P.finalize = 0;
-  P.n_active = h->counter.ptr;
   P.genelist = nullptr;
   P.n_list = 0;
   P.fm_tables = fastmath_tables();

@@ -32,7 +32,7 @@ _FAST_MAX_COEF = 1e4
 _CRISPYX_AVAILABLE = False   # the device backend replaces crispyx; kept for API compatibility
 
 last_fit_info = {}
-COUNTERS = {'irls_gene_iters': 0, 'fits': 0}
+COUNTERS = {'irls_gene_iters': 0, 'fits': 0, 'gram_flops': 0.0}
 
 
 @contextlib.contextmanager
@@ -86,6 +86,9 @@ def _device_fit(dev, Xf, family, offsets, disp, thres_disp, maxiter, d_guard, al
                 pprint.pprint('Fitting GLM for {} columns does not converge.'.format(int(still.sum())))
     COUNTERS['irls_gene_iters'] += int(n_iter.sum())
     COUNTERS['fits'] += 1
+    _kx = Xf.shape[1]
+    # algorithmic FLOPs of the IRLS passes: 2 n [kx(kx+1)/2 + 2 kx] per gene and iteration
+    COUNTERS['gram_flops'] += 2.0 * n * float(n_iter.sum()) * (_kx * (_kx + 1) / 2 + 2 * _kx)
     last_fit_info.update(n_genes=int(B.shape[0]), n_refit=int(bad.sum()), max_iter=int(n_iter.max(initial=0)),
                          irls_gene_iters=int(n_iter.sum()))
     return GlmFit(dev, B, dv, n_iter, status, bad)
