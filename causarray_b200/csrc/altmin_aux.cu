@@ -244,6 +244,63 @@ int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream
   return 0;
 }
 
+// ---- mask compaction ordered by a small integer key (deterministic, single CTA) ----
+// The gene line search walks its 8 rows of a tile in lockstep, so a tile costs as many row
+// passes as its slowest row.  Listing the active rows by the number of candidates each needed in
+// the previous alternating iteration (descending: long tiles are scheduled first) groups rows of
+// similar cost; the per-row results do not depend on which tile a row sits in.
+constexpr int CK_BINS = 16;
+__global__ void __launch_bounds__(1024) k_compact_by_key(const uint8_t* __restrict__ mask, const int* __restrict__ key,
+                                                         int n, int* __restrict__ list, int* __restrict__ count) {
+  __shared__ int s_cnt[CK_BINS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = (n + 31) / 32;
+  const int lo = warp * seg, hi = min(n, lo + seg);
+  int cnt[CK_BINS];
+#pragma unroll
+  for (int b = 0; b < CK_BINS; ++b) cnt[b] = 0;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const int kb = (i < hi && mask[i]) ? min(max(key[i], 0), CK_BINS - 1) : -1;
+#pragma unroll
+    for (int b = 0; b < CK_BINS; ++b) cnt[b] += __popc(__ballot_sync(0xffffffffu, kb == b));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int b = 0; b < CK_BINS; ++b) s_cnt[b][warp] = cnt[b];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = CK_BINS - 1; b >= 0; --b)
+      for (int w = 0; w < 32; ++w) {
+        const int c = s_cnt[b][w];
+        s_cnt[b][w] = run;
+        run += c;
+      }
+    *count = run;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < CK_BINS; ++b) cnt[b] = s_cnt[b][warp];
+  const unsigned lt = (1u << lane) - 1u;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    const int kb = (i < hi && mask[i]) ? min(max(key[i], 0), CK_BINS - 1) : -1;
+#pragma unroll
+    for (int b = 0; b < CK_BINS; ++b) {
+      const unsigned bal = __ballot_sync(0xffffffffu, kb == b);
+      if (kb == b) list[cnt[b] + __popc(bal & lt)] = i;
+      cnt[b] += __popc(bal);
+    }
+  }
+}
+int launch_compact_by_key(const uint8_t* mask, const int* key, int n, int* list, int* count, cudaStream_t st) {
+  k_compact_by_key<<<1, 1024, 0, st>>>(mask, key, n, list, count);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- clip (records rows that changed) --------------------------------------
 __global__ void k_clip(double* X, int rows, int kpad, int lo, int hi, double bound, int* list, int* count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -114,25 +114,58 @@ __device__ __forceinline__ double fm_rcp(double w) {
   return fma(r, e, r);
 }
 
+// Comparisons against a constant of known sign done on the integer pipe (IEEE-754 doubles of one
+// sign order like their bit patterns): a DSETP costs a slot on the FP64 pipe, which is the pipe the
+// likelihood kernels are bound by; ISETP pairs run on the ALU.  Exact for every non-NaN input.
+__device__ __forceinline__ bool fm_lt_pos(double a, double c) {  // a < c, c > 0
+#ifdef CA_NO_ICMP
+  return a < c;
+#else
+  return __double_as_longlong(a) < __double_as_longlong(c);
+#endif
+}
+__device__ __forceinline__ bool fm_gt_pos(double a, double c) {  // a > c, a >= 0, c > 0
+#ifdef CA_NO_ICMP
+  return a > c;
+#else
+  return __double_as_longlong(a) > __double_as_longlong(c);
+#endif
+}
+__device__ __forceinline__ bool fm_gt_neg(double a, double c) {  // a > c, c < 0
+#ifdef CA_NO_ICMP
+  return a > c;
+#else
+  return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(c);
+#endif
+}
+
 // Per-entry NB terms, branch free (straight-line code so that ptxas interleaves the four
 // independent entries a lane has in flight: every FP64 op has an 8-cycle latency).
-//   ell = y*log1p(-q) + nu*log(q),  dl = (m - y) * q.
-template <bool WANT_DL>
-__device__ __forceinline__ void fm_entry_nb(double theta, double y, double nu, double inv_nu, double log_nu,
-                                            const FmTables& T, const NbClip& C, double& ell, double& dl, double& xi,
-                                            double& m) {
-  xi = theta < 100.0 ? theta : 100.0;                   // the reference clips from above only
-  const double xe = xi > -700.0 ? xi : -700.0;          // exp(-700) ~ 1e-304 stands in for the underflow to 0
+//   lu = log(u_c), L = log1p(u_c), w = 1 + u_c, m = e^xi:
+//   ell = y*log1p(-q) + nu*log(q) = y*lu - (y + nu)*L,   dl = (m - y) * q = (m - y) / w.
+__device__ __forceinline__ void fm_terms_nb(double theta, double inv_nu, double log_nu, const FmTables& T,
+                                            const NbClip& C, double& xi, double& m, double& lu, double& L,
+                                            double& w) {
+  xi = fm_lt_pos(theta, 100.0) ? theta : 100.0;         // the reference clips from above only
+  const double xe = fm_gt_neg(xi, -700.0) ? xi : -700.0;  // exp(-700) ~ 1e-304 stands in for the underflow to 0
   m = fm_exp(xe, T.exp_t);
   double uc = m * inv_nu;
-  double lu = xi - log_nu;
-  const bool lo = uc < C.u_lo, hi = uc > C.u_hi;
+  lu = xi - log_nu;
+  const bool lo = fm_lt_pos(uc, C.u_lo), hi = fm_gt_pos(uc, C.u_hi);
   uc = lo ? C.u_lo : uc;
   lu = lo ? C.lu_lo : lu;
   uc = hi ? C.u_hi : uc;
   lu = hi ? C.lu_hi : lu;
-  const double w = 1.0 + uc;
-  const double L = fm_log(w, T.log_t);                  // log1p(u_c) = -log(q_c)
+  w = 1.0 + uc;
+  L = fm_log(w, T.log_t);                               // log1p(u_c) = -log(q_c)
+}
+
+template <bool WANT_DL>
+__device__ __forceinline__ void fm_entry_nb(double theta, double y, double nu, double inv_nu, double log_nu,
+                                            const FmTables& T, const NbClip& C, double& ell, double& dl, double& xi,
+                                            double& m) {
+  double lu, L, w;
+  fm_terms_nb(theta, inv_nu, log_nu, T, C, xi, m, lu, L, w);
   ell = fma(y, lu, -(y + nu) * L);                      // y (lu - L) - nu L
   if (WANT_DL) dl = (m - y) * fm_rcp(w);
 }

@@ -57,13 +57,14 @@ static int gcate_alloc(ca_gcate* h) {
   if (h->ell_c.alloc(n) || h->ell_g.alloc(p) || h->ellfin_c.alloc(n) || h->ellfin_g.alloc(p) ||
       h->Graw_c.alloc((size_t)n * h->ldG) || h->Graw_g.alloc((size_t)p * h->ldG) || h->g_c.alloc((size_t)n * kp) ||
       h->g_g.alloc((size_t)p * kp) || h->f0_c.alloc(n) || h->f0_g.alloc(p) || h->ng_c.alloc(n) || h->ng_g.alloc(p) ||
-      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(2) || h->alpha_gene.alloc(p))
+      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(4) || h->neval_g.alloc(p) || h->alpha_gene.alloc(p))
     return -1;
   CA_CUDA(cudaMemsetAsync(h->Yn.ptr, 0, h->Yn.bytes(), h->st));
   CA_CUDA(cudaMemsetAsync(h->Ynt.ptr, 0, h->Ynt.bytes(), h->st));
   CA_CUDA(cudaMemsetAsync(h->A.ptr, 0, h->A.bytes(), h->st));
   CA_CUDA(cudaMemsetAsync(h->B.ptr, 0, h->B.bytes(), h->st));
   CA_CUDA(cudaMemsetAsync(h->evals.ptr, 0, h->evals.bytes(), h->st));
+  CA_CUDA(cudaMemsetAsync(h->neval_g.ptr, 0, h->neval_g.bytes(), h->st));
   if (launch_fill_u8(h->gene_active.ptr, p, 1, h->st) || launch_fill_u8(h->cell_active.ptr, n, 1, h->st)) return -1;
   return 0;
 }
@@ -451,7 +452,10 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
         if (launch_pt_v(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
         if (launch_sub_p_w(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
       }
-      if (launch_compact(h->gene_active.ptr, p, h->list_g.ptr, cnt + 1, st)) return -1;
+      static const bool nosort = getenv("CA_NOSORT") != nullptr;
+      if (nosort ? launch_compact(h->gene_active.ptr, p, h->list_g.ptr, cnt + 1, st)
+                 : launch_compact_by_key(h->gene_active.ptr, h->neval_g.ptr, p, h->list_g.ptr, cnt + 1, st))
+        return -1;
       PrepArgs pa;
       pa.nrows = p;
       pa.rowlist = h->list_g.ptr;
@@ -495,7 +499,7 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       s.count = cnt + 1;
       s.nrows = p;
       s.ell_fin = h->ellfin_g.ptr;
-      s.neval = nullptr;
+      s.neval = h->neval_g.ptr;
       s.eval_total = h->evals.ptr + 1;
       if (launch_search(rp, s, st)) return -1;
     }
@@ -705,7 +709,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   }
   if (t == prm->es_max_iters) t = prm->es_max_iters - 1;  // python's loop variable after exhaustion
   auto t1 = std::chrono::steady_clock::now();
-  unsigned long long ev[2];
+  unsigned long long ev[4];
   CA_CUDA(cudaMemcpy(ev, h->evals.ptr, sizeof ev, cudaMemcpyDeviceToHost));
   res->n_iter = t;
   res->func_val = f;
@@ -715,6 +719,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   res->total_cell_updates = tot_c;
   res->cell_evals = (int64_t)ev[0];
   res->gene_evals = (int64_t)ev[1];
+  if (getenv("CA_TIMING")) fprintf(stderr, "[ca] line search: cell evals %llu (tile-lockstep %llu), gene evals %llu (tile-lockstep %llu)\n", ev[0], ev[2], ev[1], ev[3]);
   res->loop_seconds = std::chrono::duration<double>(t1 - t0).count();
   return 0;
 }

@@ -20,7 +20,8 @@ struct ca_gcate {
   DevBuf<uint8_t> gene_active, cell_active;
   DevBuf<int> list_c, list_g, list_clip, counts;  // counts: [0] cells, [1] genes, [2] clip, [3] n_act_c, [4] n_act_g
   DevBuf<double> ell_c, ell_g, ellfin_c, ellfin_g, Graw_c, Graw_g, g_c, g_g, f0_c, f0_g, ng_c, ng_g, W, scal;
-  DevBuf<unsigned long long> evals;  // [0] cell evals, [1] gene evals
+  DevBuf<unsigned long long> evals;  // [0] cell evals, [1] gene evals, [2]/[3] cell / gene tile passes x 8
+  DevBuf<int> neval_g;               // candidates each gene needed in its last line search (list ordering key)
   int ldG = 64;
   bool counts_loaded = false, factors_set = false;
   // raw counts kept for the GLM / AIPW handles that share them

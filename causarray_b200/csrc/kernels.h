@@ -86,6 +86,7 @@ struct PrepArgs {
 int launch_prep_search(const PrepArgs& a, cudaStream_t st);
 
 int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream_t st);
+int launch_compact_by_key(const uint8_t* mask, const int* key, int n, int* list, int* count, cudaStream_t st);
 // clip X[:, lo:hi) to [-bound, bound]; rows where something changed are appended to list/count
 int launch_clip(double* X, int rows, int kpad, int lo, int hi, double bound, int* list, int* count, cudaStream_t st);
 // mask[i] = || X[i, lo:hi) - Xprev[i, lo:hi) ||_2 > tol ; n_active written to count

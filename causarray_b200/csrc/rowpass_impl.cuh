@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace ca {
 
@@ -38,6 +39,9 @@ constexpr int NTHREADS = NWARPS * 32;
 #endif
 #ifndef CA_ABL
 #define CA_ABL 0
+#endif
+#ifndef CA_NACC
+#define CA_NACC 2
 #endif
 
 struct PassCfg {
@@ -168,21 +172,40 @@ __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst
 
 enum PassMode { MODE_POIS = 0, MODE_NB_ROW = 1, MODE_NB_COL = 2 };
 
-// Likelihood terms of one matrix entry (branch free).
-template <int MODE, bool GRAD>
+// Likelihood terms of one matrix entry (branch free), accumulated straight into `acc`:
+//   acc += ell(y, theta);   d = -d ell / d theta (GRAD).
+// The last operations of ell are fused multiply-adds into the running sum (y*a - c*b with
+// (a, b, c) = (log u, log1p u, y + nu) for NB and (xi, m, 1) on the Poisson branch), which saves
+// the separate product, the Poisson alternative and the add into the row sum of the first version.
+// VALID = false (ragged last tile only) removes the entry from the sums.
+template <int MODE, bool GRAD, bool RAGGED>
 __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& clip, double theta, double y, double nu,
-                                           double inu, double lnu, bool pois, double& e, double& d) {
+                                           double inu, double lnu, bool pois, bool valid, double& acc, double& d) {
   if (MODE == MODE_POIS) {
-    const double x = theta < 100.0 ? theta : 100.0;
-    const double m = fm_exp(x > -700.0 ? x : -700.0, FT.exp_t);
-    e = fma(y, x, -m);
+    const double x = fm_lt_pos(theta, 100.0) ? theta : 100.0;
+    double m = fm_exp(fm_gt_neg(x, -700.0) ? x : -700.0, FT.exp_t);
+    if (RAGGED) {
+      y = valid ? y : 0.0;
+      m = valid ? m : 0.0;
+    }
+    acc = fma(y, x, acc) - m;
     if (GRAD) d = m - y;
   } else {
-    double x, m;
-    fm_entry_nb<GRAD>(theta, y, nu, inu, lnu, FT, clip, e, d, x, m);
-    // Poisson branch (nu > thres_disp), as selects: keeps the four entries in one basic block
-    e = pois ? fma(y, x, -m) : e;
-    if (GRAD) d = pois ? (m - y) : d;
+    double x, m, lu, L, w;
+    fm_terms_nb(theta, inu, lnu, FT, clip, x, m, lu, L, w);
+    const double a = pois ? x : lu;
+    const double b = pois ? m : L;
+    double c = pois ? 1.0 : y + nu;
+    if (GRAD) {
+      const double q = pois ? 1.0 : fm_rcp(w);
+      d = (m - y) * q;
+      if (RAGGED) d = valid ? d : 0.0;
+    }
+    if (RAGGED) {
+      y = valid ? y : 0.0;
+      c = valid ? c : 0.0;
+    }
+    acc = fma(-c, b, fma(y, a, acc));
   }
 }
 
@@ -198,7 +221,7 @@ template <int KS, bool GRAD, int NGT, int MODE>
 __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
                                                const double* s_X, const Smem& S, int gc_lo, Pipe& pipe) {
   constexpr int KPAD = 4 * KS;
-  constexpr int NACC = KS < 4 ? KS : 4;
+  constexpr int NACC = KS < CA_NACC ? KS : CA_NACC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
   const int tc = P.tc;
@@ -215,7 +238,7 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
   double afrag[KS];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) afrag[ks] = s_X[lr * KPAD + ks * 4 + lc];
-  double ellsum = 0.0;
+  double ellA = 0.0, ellB = 0.0;  // running row sums of the two tiles of an iteration
   double gacc[NGT][2], gacb[NGT][2];  // two accumulator sets (the two tiles of an iteration)
 #pragma unroll
   for (int j = 0; j < NGT; ++j) gacc[j][0] = gacc[j][1] = gacb[j][0] = gacb[j][1] = 0.0;
@@ -238,10 +261,8 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
     const int col0 = c * tc;
     const int nrem = P.ncols - col0;
     const int ntile = min(tc, round_up(nrem, 8)) >> 3;
-#pragma unroll 1
-    for (int t = warp; t < ntile; t += 2 * NWARPS) {
-      const bool hasB = t + NWARPS < ntile;            // warp uniform
-      const int tA = t, tB = hasB ? t + NWARPS : t;
+    auto pair_body = [&](auto ragged_tag, int tA, int tB, bool hasB) {
+      constexpr bool RAGGED = decltype(ragged_tag)::value;
       const int clA = tA * 8 + 2 * lc, clB = tB * 8 + 2 * lc;  // columns within the chunk
       const double2 yA = *reinterpret_cast<const double2*>(Yb + tA * 8);
       const double2 yB = *reinterpret_cast<const double2*>(Yb + tB * 8);
@@ -275,20 +296,18 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
         cB0 = Cb[clB];
         cB1 = Cb[clB + 1];
       }
-      double eA0, eA1, eB0, eB1, dA0 = 0.0, dA1 = 0.0, dB0 = 0.0, dB1 = 0.0;
-      eval_entry<MODE, GRAD>(FT, clip, pa[0][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, eA0, dA0);
-      eval_entry<MODE, GRAD>(FT, clip, pa[0][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, eA1, dA1);
-      eval_entry<MODE, GRAD>(FT, clip, pb[0][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, eB0, dB0);
-      eval_entry<MODE, GRAD>(FT, clip, pb[0][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, eB1, dB1);
-      if (!hasB || tB * 8 + 8 > nrem) {  // missing / ragged second tile (warp uniform)
-        if (!hasB || clB >= nrem) eB0 = dB0 = 0.0;
-        if (!hasB || clB + 1 >= nrem) eB1 = dB1 = 0.0;
+      bool vA0 = true, vA1 = true, vB0 = true, vB1 = true;
+      if (RAGGED) {  // missing second tile / columns past the end
+        vA0 = clA < nrem;
+        vA1 = clA + 1 < nrem;
+        vB0 = hasB && clB < nrem;
+        vB1 = hasB && clB + 1 < nrem;
       }
-      if (tA * 8 + 8 > nrem) {
-        if (clA >= nrem) eA0 = dA0 = 0.0;
-        if (clA + 1 >= nrem) eA1 = dA1 = 0.0;
-      }
-      ellsum += (eA0 + eA1) + (eB0 + eB1);
+      double dA0 = 0.0, dA1 = 0.0, dB0 = 0.0, dB1 = 0.0;
+      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, ellA, dA0);
+      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, ellB, dB0);
+      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, ellA, dA1);
+      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, ellB, dB1);
       if (GRAD) {
         const double* gA = Mb + (tA * 8 + 2 * lc) * KPAD + gc_lo + lr;
         const double* gB = Mb + (tB * 8 + 2 * lc) * KPAD + gc_lo + lr;
@@ -300,10 +319,20 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
           dmma884(gacb[j][0], gacb[j][1], dB1, gB[KPAD + 8 * j]);
         }
       }
+    };
+#pragma unroll 1
+    for (int t = warp; t < ntile; t += 2 * NWARPS) {
+      const bool hasB = t + NWARPS < ntile;            // warp uniform
+      const int tB = hasB ? t + NWARPS : t;
+      if (!hasB || tB * 8 + 8 > nrem)
+        pair_body(std::true_type{}, t, tB, hasB);
+      else
+        pair_body(std::false_type{}, t, tB, hasB);
     }
     __syncthreads();
   }
   // fixed-order reduction: 4 lanes of a row, then the 8 warps
+  double ellsum = ellA + ellB;
   ellsum += __shfl_xor_sync(0xffffffffu, ellsum, 1);
   ellsum += __shfl_xor_sync(0xffffffffu, ellsum, 2);
   if (lc == 0) S.red[warp * 8 + lr] = ellsum;
@@ -518,6 +547,11 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
     A.ell_fin[s_rows[tid]] = s_efin[tid];
     if (A.neval) A.neval[s_rows[tid]] = s_ne[tid];
     if (A.eval_total) atomicAdd(A.eval_total, (unsigned long long)s_ne[tid]);
+  }
+  if (tid == 0 && A.eval_total) {  // lockstep cost of the tile: rows x the slowest row's candidates
+    int mx = 0;
+    for (int r = 0; r < 8; ++r) mx = max(mx, s_ne[r]);
+    atomicAdd(A.eval_total + 2, (unsigned long long)(8 * mx));
   }
 }
 
