@@ -18,6 +18,8 @@
 // operand as is and, multiplied by w[cell], the A operand (DMMA m8n8k4); only
 // the upper-triangular 8x8 tiles are kept.  A second kernel solves the
 // (Jacobi-equilibrated) normal equations with a warp-level Cholesky.
+#include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 #include <new>
@@ -40,6 +42,8 @@ namespace ca {
 // normal equations of the next update with a warp-level Cholesky.
 struct GlmSolve {
   int p, kx, nslots, nsplit, part_ld;
+  int kxi;               // width of the pass kernel's internal column layout
+  signed char emap[64];  // caller's column -> internal column
   const int* genelist;   // nullptr = identity
   const double* part;
   const double* ridge;   // kx or nullptr
@@ -65,13 +69,13 @@ __global__ void k_glm_solve(GlmSolve Q) {
   const int slot = blockIdx.x * nw + warp;
   if (slot >= Q.nslots) return;
   const int gene = Q.genelist ? Q.genelist[slot] : slot;
-  const int kx = Q.kx;
+  const int kx = Q.kx, kxi = Q.kxi;
   if (!Q.finalize && Q.status[gene] != 0) return;
   const double* part0 = Q.part + (size_t)slot * Q.nsplit * Q.part_ld;
   // ---- deviance ----
   double s_yeta = 0.0, s_mu = 0.0, s_log = 0.0;
   for (int sp = 0; sp < Q.nsplit; ++sp) {
-    const double* ps = part0 + (size_t)sp * Q.part_ld + kx * kx + kx;
+    const double* ps = part0 + (size_t)sp * Q.part_ld + kxi * kxi + kxi;
     s_yeta += ps[0];
     s_mu += ps[1];
     s_log += ps[2];
@@ -116,23 +120,24 @@ __global__ void k_glm_solve(GlmSolve Q) {
   double* b = sc + kx;
   for (int e = lane; e < kx * kx; e += 32) {
     // fixed summation order over the splits; loads issued eight at a time
+    const int i = e / kx, j = e % kx;
+    const int ei = (int)Q.emap[i] * kxi + (int)Q.emap[j];
     double g = 0.0;
     int sp = 0;
     for (; sp + 8 <= Q.nsplit; sp += 8) {
       double v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = part0[(size_t)(sp + u) * Q.part_ld + e];
+      for (int u = 0; u < 8; ++u) v[u] = part0[(size_t)(sp + u) * Q.part_ld + ei];
 #pragma unroll
       for (int u = 0; u < 8; ++u) g += v[u];
     }
-    for (; sp < Q.nsplit; ++sp) g += part0[(size_t)sp * Q.part_ld + e];
-    const int i = e / kx, j = e % kx;
+    for (; sp < Q.nsplit; ++sp) g += part0[(size_t)sp * Q.part_ld + ei];
     if (Q.ridge && i == j) g += Q.ridge[i];
     L[i * ld + j] = g;
   }
   for (int i = lane; i < kx; i += 32) {
     double r = 0.0;
-    for (int sp = 0; sp < Q.nsplit; ++sp) r += part0[(size_t)sp * Q.part_ld + kx * kx + i];
+    for (int sp = 0; sp < Q.nsplit; ++sp) r += part0[(size_t)sp * Q.part_ld + kxi * kxi + (int)Q.emap[i]];
     b[i] = r;
   }
   __syncwarp();
@@ -344,7 +349,7 @@ __global__ void k_disp_moments(const double* __restrict__ Yt, const double* __re
 }
 
 static int launch_pass(const GlmPass& P, cudaStream_t st) {
-  const int nt = (P.kx + 7) / 8;
+  const int nt = (P.kxi + 7) / 8;
   switch (nt) {
     case 1: return launch_glm_pass_nt<1>(P, st);
     case 2: return launch_glm_pass_nt<2>(P, st);
@@ -360,6 +365,72 @@ static int launch_pass(const GlmPass& P, cudaStream_t st) {
 }
 
 int kpad_for(int k);
+
+// Internal column layout of the pass kernel.  A contiguous block of design columns of which every
+// cell has at most one non-zero entry (one-hot treatment indicators, causarray/DR_learner.py builds
+// the design as [W, A]) has a diagonal weighted Gram block whatever the IRLS weights are.  Moving
+// that block behind the other ("dense") columns, aligned to an 8-column tile, lets the kernel skip
+// the DMMA tiles that lie inside it (3 of 10 for [1, U(10) | A(15)]).  The layout is used only when
+// it lowers the number of tiles.
+struct GlmLayout {
+  int kxi;
+  signed char cmap[64];  // internal -> caller (-1: padding)
+  signed char emap[64];  // caller -> internal
+  int t0;                // first tile of the orthogonal block (= number of tiles: none)
+};
+
+static int tri_tiles(int nt) { return nt * (nt + 1) / 2; }
+
+static GlmLayout plan_layout(const double* X, int n, int kx) {
+  GlmLayout L;
+  L.kxi = kx;
+  L.t0 = (kx + 7) / 8;
+  for (int c = 0; c < 64; ++c) L.cmap[c] = L.emap[c] = (signed char)(c < kx ? c : -1);
+  if (kx < 9 || getenv("CA_GLM_NO_ORTHO")) return L;
+  // conflict[i] bit j: some cell has columns i and j both non-zero
+  unsigned long long conflict[64] = {0};
+  for (int i = 0; i < n; ++i) {
+    const double* x = X + (size_t)i * kx;
+    unsigned long long m = 0;
+    for (int c = 0; c < kx; ++c)
+      if (x[c] != 0.0) m |= 1ull << c;
+    for (unsigned long long r = m; r; r &= r - 1) conflict[__builtin_ctzll(r)] |= m;
+  }
+  // longest contiguous range [lo, hi) without a conflict between two distinct columns
+  int best_lo = 0, best_n = 0;
+  for (int lo = 0; lo < kx; ++lo) {
+    unsigned long long in = 0;
+    int hi = lo;
+    while (hi < kx && !(conflict[hi] & in & ~(1ull << hi))) {
+      in |= 1ull << hi;
+      ++hi;
+    }
+    if (hi - lo > best_n) {
+      best_n = hi - lo;
+      best_lo = lo;
+    }
+  }
+  if (best_n < 9) return L;  // at least one full tile pair inside the block is needed to skip anything
+  const int n_dense = kx - best_n;
+  const int o0 = round_up(n_dense, 8);
+  const int kxi = o0 + best_n;
+  if (kxi > 64) return L;
+  const int nt_i = (kxi + 7) / 8, nt_e = (kx + 7) / 8, t0 = o0 / 8;
+  const int tiles_i = tri_tiles(nt_i) - tri_tiles(nt_i - t0);
+  if (tiles_i >= tri_tiles(nt_e)) return L;
+  if (t0 < 1 || t0 > 2 || nt_i - t0 < 2) return L;  // variants built in glm_pass_inst.cu
+  L.kxi = kxi;
+  for (int c = 0; c < 64; ++c) L.cmap[c] = -1;
+  int di = 0;
+  for (int c = 0; c < kx; ++c) {
+    const bool ortho = c >= best_lo && c < best_lo + best_n;
+    const int ci = ortho ? o0 + (c - best_lo) : di++;
+    L.cmap[ci] = (signed char)c;
+    L.emap[c] = (signed char)ci;
+  }
+  L.t0 = t0;
+  return L;
+}
 
 }  // namespace ca
 
@@ -422,17 +493,24 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
   const int n = h->n, p = h->p;
   cudaStream_t st = h->st;
-  const int ldx = 8 * ((kx + 7) / 8) + 4;
+  const GlmLayout lay = plan_layout(X, n, kx);
+  const int kxi = lay.kxi;
+  const int ldx = 8 * ((kxi + 7) / 8) + 4;
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
       h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
-      h->part.alloc((size_t)p * (kx * kx + kx + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
+      h->part.alloc((size_t)p * (kxi * kxi + kxi + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
       h->counter.alloc(2) || h->offset.alloc((size_t)n + 8) || h->nu.alloc(p) || h->ridge.alloc(kx))
     return -1;
   CA_REQUIRE(!gene_mask || h->fit_kx == kx, "gene_mask refit needs a previous fit of the same width");
   h->fit_kx = kx;
-  CA_CUDA(cudaMemsetAsync(h->X.ptr, 0, h->X.bytes(), st));
-  CA_CUDA(cudaMemcpy2DAsync(h->X.ptr, sizeof(double) * ldx, X, sizeof(double) * kx, sizeof(double) * kx, n,
-                            cudaMemcpyHostToDevice, st));
+  {
+    // design in the internal column layout, zero padded to ldx
+    std::vector<double> xi((size_t)n * ldx, 0.0);
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < kx; ++c) xi[(size_t)i * ldx + lay.emap[c]] = X[(size_t)i * kx + c];
+    CA_CUDA(cudaMemcpyAsync(h->X.ptr, xi.data(), sizeof(double) * xi.size(), cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+  }
   CA_CUDA(cudaMemsetAsync(h->offset.ptr, 0, h->offset.bytes(), st));
   if (offset) CA_CUDA(cudaMemcpyAsync(h->offset.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   if (nu) CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu, sizeof(double) * p, cudaMemcpyHostToDevice, st));
@@ -470,6 +548,9 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   P.X = h->X.ptr;
   P.kx = kx;
   P.ldx = ldx;
+  P.kxi = kxi;
+  memcpy(P.cmap, lay.cmap, sizeof P.cmap);
+  P.t0 = lay.t0;
   P.offset = h->offset.ptr;
   P.nu = h->has_nu ? h->nu.ptr : nullptr;
   P.family = family;
@@ -478,7 +559,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   P.ybar = h->ybar.ptr;
   P.status = h->status.ptr;
   P.part = h->part.ptr;
-  P.part_ld = kx * kx + kx + 4;
+  P.part_ld = kxi * kxi + kxi + 4;
   P.nsplit = 1;
   P.mu_t = nullptr;
   P.finalize = 0;
@@ -493,6 +574,8 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   GlmSolve Q;
   Q.p = p;
   Q.kx = kx;
+  Q.kxi = kxi;
+  memcpy(Q.emap, lay.emap, sizeof Q.emap);
   Q.part_ld = P.part_ld;
   Q.part = h->part.ptr;
   Q.ridge = ridge ? h->ridge.ptr : nullptr;

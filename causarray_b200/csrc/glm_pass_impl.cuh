@@ -11,7 +11,8 @@
 // eta / mu / w / z for ONE cell (straight-line code, table-driven exp / log), software-pipelined
 // one block ahead of the Gram accumulation: for a 4-cell step the fragment
 // X[cell = lane%4][col = lane/4 + 8t] is the DMMA B operand as is and, times w[cell], the A operand;
-// only the upper-triangular 8x8 tiles are kept.
+// only the upper-triangular 8x8 tiles are kept.  T0 < NT: the tiles from T0 on hold mutually
+// orthogonal columns (GlmLayout in glm.cu) and the DMMAs between them are skipped.
 #pragma once
 #include "common.cuh"
 #include "fastmath.cuh"
@@ -26,8 +27,12 @@ struct GlmPass {
   const double* Yt;      // p x ldn raw counts, gene-major
   long ldn;
   int n, p;
-  const double* X;       // n x ldx, ldx = 8 * ceil(kx / 8) + 4, zero padded
-  int kx, ldx;
+  const double* X;       // n x ldx in the INTERNAL column layout, ldx = 8 * ceil(kxi / 8) + 4, zero padded
+  int kx, ldx;           // kx: width of the caller's design (layout of beta)
+  int kxi;               // width of the internal layout (see GlmLayout in glm.cu)
+  signed char cmap[64];  // internal column -> caller's column, -1 for a padding column
+  int t0;                // tiles >= t0 hold mutually orthogonal columns: a tile (mt, nt) with both
+                         // indices >= t0 has only its diagonal (mt == nt) non-zero (t0 = NT: none)
   const double* offset;  // n (zeros when the model has no offset)
   const double* nu;      // p or nullptr
   int family;
@@ -51,7 +56,7 @@ inline size_t glm_pass_smem_bytes(int nt) {
   return sizeof(double) * ((size_t)2 * GLM_CHUNK * ldx + 2 * GLM_CHUNK + GLM_WARPS * nt8 + FM_TABLE_DOUBLES);
 }
 
-template <int NT, bool FIRST, bool FIN, bool NB>
+template <int NT, int T0, bool FIRST, bool FIN, bool NB>
 __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(GlmPass P) {
   constexpr int NT8 = NT * 8, LDX = NT8 + 4;
   constexpr int NTRI = NT * (NT + 1) / 2;
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
   __shared__ int s_any;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
-  const int kx = P.kx;
+  const int kx = P.kx, kxi = P.kxi;
   const int slot = blockIdx.x * GLM_WARPS + warp;
   const int gene = P.genelist ? (slot < P.n_list ? P.genelist[slot] : P.p) : slot;
   const bool gene_ok = gene < P.p;
@@ -82,8 +87,10 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
   const FmTables FT = fm_load_tables(s_tab, P.fm_tables);
   for (int i = tid; i < 2 * GLM_CHUNK * LDX; i += GLM_THREADS) Xs[i] = 0.0;  // rows past n stay finite
   for (int i = tid; i < 2 * GLM_CHUNK; i += GLM_THREADS) offs[i] = 0.0;
-  for (int c = lane; c < NT8; c += 32)
-    betas[warp * NT8 + c] = (gene_ok && c < kx && !FIRST) ? P.beta[(size_t)gene * kx + c] : 0.0;
+  for (int c = lane; c < NT8; c += 32) {
+    const int ce = c < kxi ? (int)P.cmap[c] : -1;
+    betas[warp * NT8 + c] = (gene_ok && ce >= 0 && !FIRST) ? P.beta[(size_t)gene * kx + ce] : 0.0;
+  }
   if (tid == 0) {
     mbar_init(bars + 0, 1);
     mbar_init(bars + 1, 1);
@@ -208,7 +215,12 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
           for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
             for (int nt = mt; nt < NT; ++nt) {
-              dmma884(acc[idx][0], acc[idx][1], av[mt], xv[nt]);
+              // tiles between mutually orthogonal columns (one-hot treatment indicators): every
+              // cross product vanishes whatever the weights, so only the diagonal is accumulated
+              if (!(mt >= T0 && nt >= T0))
+                dmma884(acc[idx][0], acc[idx][1], av[mt], xv[nt]);
+              else if (mt == nt)
+                acc[idx][0] = fma(av[mt], xv[mt], acc[idx][0]);
               ++idx;
             }
         }
@@ -240,9 +252,9 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
   s_log = warp_sum(s_log);
   double* part = P.part + ((size_t)slot * P.nsplit + blockIdx.y) * P.part_ld;
   if (lane == 0) {
-    part[kx * kx + kx + 0] = s_yeta;
-    part[kx * kx + kx + 1] = s_mu;
-    part[kx * kx + kx + 2] = s_log;
+    part[kxi * kxi + kxi + 0] = s_yeta;
+    part[kxi * kxi + kxi + 1] = s_mu;
+    part[kxi * kxi + kxi + 2] = s_log;
   }
   if (FIN) return;
   double* G = part;
@@ -252,12 +264,20 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
 #pragma unroll
     for (int nt = mt; nt < NT; ++nt) {
       const int m = 8 * mt + lr;
+      const bool sk = mt >= T0 && nt >= T0;
+      double dg = 0.0;
+      if (sk && mt == nt) {  // diagonal of a skipped tile: column m, partial sums over the 4 cell lanes
+        dg = acc[idx][0];
+        dg += __shfl_xor_sync(0xffffffffu, dg, 1);
+        dg += __shfl_xor_sync(0xffffffffu, dg, 2);
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int nn = 8 * nt + 2 * lc + i;
-        if (m < kx && nn < kx) {
-          G[m * kx + nn] = acc[idx][i];
-          if (nt != mt) G[nn * kx + m] = acc[idx][i];
+        if (m < kxi && nn < kxi) {
+          const double v = sk ? ((mt == nt && nn == m) ? dg : 0.0) : acc[idx][i];
+          G[m * kxi + nn] = v;
+          if (nt != mt) G[nn * kxi + m] = v;
         }
       }
       ++idx;
@@ -269,7 +289,7 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     const int col = lr + 8 * t;
-    if (lc == 0 && col < kx) part[kx * kx + col] = v;
+    if (lc == 0 && col < kxi) part[kxi * kxi + col] = v;
   }
 }
 

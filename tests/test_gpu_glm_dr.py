@@ -47,6 +47,42 @@ def test_glm_fit_vs_oracle(fam):
     np.testing.assert_allclose(dm, dm_ref, rtol=1e-9)
 
 
+@pytest.mark.parametrize("fam,d_cov,r", [("nb", 2, 4), ("poisson", 3, 8)])
+def test_glm_orthogonal_block_layout(fam, d_cov, r):
+    """One-hot treatment block: the tile-skipping internal layout (dense part of one / two tiles)
+    against the plain layout and the oracle."""
+    from causarray_b200.device import GlmDevice
+    from causarray_b200.synth import simulate_screen
+    sim = simulate_screen(n_ctrl=150, n_perts=12, cells_per_pert=25, p=70, r=r, d_cov=d_cov, family=fam, seed=11,
+                          base_lo=0.0, base_hi=2.5)
+    Y = sim["Y"]
+    X = np.c_[sim["X"], sim["U"] * 0.3, sim["A"]]
+    assert X.shape[1] >= 17 and set(np.unique(sim["A"])) <= {0.0, 1.0}
+    n, p = Y.shape
+    off = np.random.default_rng(5).standard_normal(n) * 0.2
+    disp = sim["disp"] if fam == "nb" else None
+    dev = GlmDevice(n, p)
+    dev.load_counts(Y)
+    out = {}
+    for tag in ("ortho", "plain"):
+        if tag == "plain":
+            os.environ["CA_GLM_NO_ORTHO"] = "1"
+        try:
+            B, dv, n_iter, status = dev.fit(fam, X, off, disp, maxiter=100, tol=1e-8, d_guard=2)
+            out[tag] = (B.copy(), dv.copy(), n_iter.copy(), status.copy(), dev.fitted())
+        finally:
+            os.environ.pop("CA_GLM_NO_ORTHO", None)
+    ok = (out["ortho"][3] == 0) & (out["plain"][3] == 0)
+    assert ok.sum() >= p - 2
+    np.testing.assert_allclose(out["ortho"][0][ok], out["plain"][0][ok], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(out["ortho"][1][ok], out["plain"][1][ok], rtol=1e-10)
+    assert (out["ortho"][2][ok] != out["plain"][2][ok]).sum() <= 1
+    np.testing.assert_allclose(out["ortho"][4][:, ok], out["plain"][4][:, ok], rtol=1e-9)
+    B_ref, _, _, _, _, status_ref, _ = og.fit_glm_original(Y, X, None, family=fam, disp_glm=disp, offset=off, maxiter=100)
+    ok &= status_ref == 0
+    np.testing.assert_allclose(out["ortho"][0][ok], B_ref[ok], rtol=1e-7, atol=1e-8)
+
+
 def test_glm_golden_helpers(golden_dir):
     """MoM dispersion against the reference's own estimate_disp (golden)."""
     g = np.load(os.path.join(golden_dir, "misc.npz"))
