@@ -131,6 +131,13 @@ __device__ __forceinline__ bool fm_gt_pos(double a, double c) {  // a > c, a >= 
   return __double_as_longlong(a) > __double_as_longlong(c);
 #endif
 }
+__device__ __forceinline__ bool fm_lt_neg(double a, double c) {  // a < c, c < 0
+#ifdef CA_NO_ICMP
+  return a < c;
+#else
+  return (unsigned long long)__double_as_longlong(a) > (unsigned long long)__double_as_longlong(c);
+#endif
+}
 __device__ __forceinline__ bool fm_gt_neg(double a, double c) {  // a > c, c < 0
 #ifdef CA_NO_ICMP
   return a > c;

@@ -130,6 +130,7 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
     nu_host = ones.data();
   }
   std::vector<double> hin(p), hln(p), hcp((size_t)4 * p);
+  h->any_pois = 0;
   for (int j = 0; j < p; ++j) {
     hin[j] = 1.0 / nu_host[j];
     hln[j] = std::log(nu_host[j]);
@@ -137,6 +138,7 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
     hcp[4 * j + 1] = hin[j];
     hcp[4 * j + 2] = hln[j];
     hcp[4 * j + 3] = (nu_host[j] > h->thres) ? 1.0 : 0.0;
+    if (nu_host[j] > h->thres) h->any_pois = 1;
   }
   CA_CUDA(cudaMemcpyAsync(h->colparm.ptr, hcp.data(), sizeof(double) * 4 * p, cudaMemcpyHostToDevice, h->st));
   CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu_host, sizeof(double) * p, cudaMemcpyHostToDevice, h->st));
@@ -337,6 +339,7 @@ static RowProblem cell_problem(ca_gcate* h) {
   rp.log_nu = h->log_nu.ptr;
   rp.colparm = h->colparm.ptr;
   rp.nu_per_row = 0;
+  rp.any_pois = h->any_pois;
   rp.family = h->family;
   rp.thres_disp = h->thres;
   return rp;
@@ -353,6 +356,7 @@ static RowProblem gene_problem(ca_gcate* h) {
   rp.log_nu = h->log_nu.ptr;
   rp.colparm = nullptr;
   rp.nu_per_row = 1;
+  rp.any_pois = h->any_pois;
   rp.family = h->family;
   rp.thres_disp = h->thres;
   return rp;

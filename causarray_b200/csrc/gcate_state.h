@@ -23,6 +23,7 @@ struct ca_gcate {
   DevBuf<unsigned long long> evals;  // [0] cell evals, [1] gene evals, [2]/[3] cell / gene tile passes x 8
   DevBuf<int> neval_g;               // candidates each gene needed in its last line search (list ordering key)
   int ldG = 64;
+  int any_pois = 0;                  // some nu exceeds thres (the NB kernels then keep their Poisson switch)
   bool counts_loaded = false, factors_set = false;
   // raw counts kept for the GLM / AIPW handles that share them
   DevBuf<double> Yraw, Yraw_t;

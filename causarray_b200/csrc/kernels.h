@@ -19,6 +19,7 @@ struct RowProblem {
   const double* log_nu;  // log(nu)
   const void* colparm;   // per column (nu, 1/nu, log nu, poisson flag) as double4, for nu_per_row = 0
   int nu_per_row;
+  int any_pois;      // some nu exceeds thres_disp
   int family;
   double thres_disp;
 };

@@ -25,6 +25,7 @@ static int make_cfg(const RowProblem& rp, PassCfg& P) {
   P.colparm = (!rp.nu_per_row && rp.family == CA_FAMILY_NB) ? reinterpret_cast<const double4*>(rp.colparm) : nullptr;
   CA_REQUIRE(rp.nu_per_row || rp.family != CA_FAMILY_NB || rp.colparm, "column parameters missing");
   P.nu_per_row = rp.nu_per_row;
+  P.any_pois = rp.any_pois;
   P.family = rp.family;
   P.thres = rp.thres_disp;
   P.tc = pick_tc(rp.kpad);

@@ -54,6 +54,7 @@ struct PassCfg {
   const double* log_nu;
   const double4* colparm; // per column (!nu_per_row): (nu, 1/nu, log nu, pois)
   int nu_per_row;
+  int any_pois;  // some nu exceeds thres (NB entries of those rows / columns take the Poisson branch)
   int family;
   double thres;
   int tc;  // columns per staged chunk (multiple of 8)
@@ -170,7 +171,13 @@ __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst
   }
 }
 
-enum PassMode { MODE_POIS = 0, MODE_NB_ROW = 1, MODE_NB_COL = 2 };
+// *_F: NB without the Poisson switch -- no nu exceeds thres_disp (always the case for
+// method-of-moments dispersions, which are clipped to [0.01, 100]); the per-entry Poisson selects
+// drop out and the log-likelihood-only pass needs a single clamp of log u.
+enum PassMode { MODE_POIS = 0, MODE_NB_ROW = 1, MODE_NB_COL = 2, MODE_NB_ROW_F = 3, MODE_NB_COL_F = 4 };
+__host__ __device__ constexpr bool mode_row(int m) { return m == MODE_NB_ROW || m == MODE_NB_ROW_F; }
+__host__ __device__ constexpr bool mode_col(int m) { return m == MODE_NB_COL || m == MODE_NB_COL_F; }
+__host__ __device__ constexpr bool mode_fast(int m) { return m == MODE_NB_ROW_F || m == MODE_NB_COL_F; }
 
 // Likelihood terms of one matrix entry (branch free), accumulated straight into `acc`:
 //   acc += ell(y, theta);   d = -d ell / d theta (GRAD).
@@ -190,6 +197,32 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
     }
     acc = fma(y, x, acc) - m;
     if (GRAD) d = m - y;
+  } else if (mode_fast(MODE) && !GRAD) {
+    // ell = y log u_c - (y + nu) log1p(u_c) with log u_c = clamp(xi - log nu) and u_c = exp(log u_c):
+    // one clamp instead of the paired clamps of u and log u, and no range guard on the exponential
+    const double x = fm_lt_pos(theta, 100.0) ? theta : 100.0;
+    double lu = x - lnu;
+    lu = fm_lt_neg(lu, clip.lu_lo) ? clip.lu_lo : lu;
+    lu = fm_gt_pos(lu, clip.lu_hi) ? clip.lu_hi : lu;
+    const double u = fm_exp(lu, FT.exp_t);
+    const double L = fm_log(1.0 + u, FT.log_t);
+    double c = y + nu;
+    if (RAGGED) {
+      y = valid ? y : 0.0;
+      c = valid ? c : 0.0;
+    }
+    acc = fma(-c, L, fma(y, lu, acc));
+  } else if (mode_fast(MODE)) {
+    double x, m, lu, L, w;
+    fm_terms_nb(theta, inu, lnu, FT, clip, x, m, lu, L, w);
+    d = (m - y) * fm_rcp(w);
+    double c = y + nu;
+    if (RAGGED) {
+      d = valid ? d : 0.0;
+      y = valid ? y : 0.0;
+      c = valid ? c : 0.0;
+    }
+    acc = fma(-c, L, fma(y, lu, acc));
   } else {
     double x, m, lu, L, w;
     fm_terms_nb(theta, inu, lnu, FT, clip, x, m, lu, L, w);
@@ -228,7 +261,7 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
   const int row = s_rows[lr];
   double nu_r = 1.0, inu_r = 1.0, lnu_r = 0.0;
   bool pois_r = false;
-  if (MODE == MODE_NB_ROW && row >= 0) {
+  if (mode_row(MODE) && row >= 0) {
     nu_r = P.nu[row];
     inu_r = P.inv_nu[row];
     lnu_r = P.log_nu[row];
@@ -290,7 +323,7 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
           pb[i][1] += pb[i + st][1];
         }
       double4 cA0 = make_double4(nu_r, inu_r, lnu_r, pois_r ? 1.0 : 0.0), cA1 = cA0, cB0 = cA0, cB1 = cA0;
-      if (MODE == MODE_NB_COL) {
+      if (mode_col(MODE)) {
         cA0 = Cb[clA];
         cA1 = Cb[clA + 1];
         cB0 = Cb[clB];
@@ -367,10 +400,14 @@ __device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, 
                                           const Smem& S, int gc_lo, Pipe& pipe) {
   if (P.family != CA_FAMILY_NB)
     tile_pass_mode<KS, GRAD, NGT, MODE_POIS>(P, FT, s_rows, s_X, S, gc_lo, pipe);
-  else if (P.nu_per_row)
+  else if (P.nu_per_row && P.any_pois)
     tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW>(P, FT, s_rows, s_X, S, gc_lo, pipe);
-  else
+  else if (P.nu_per_row)
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW_F>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+  else if (P.any_pois)
     tile_pass_mode<KS, GRAD, NGT, MODE_NB_COL>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+  else
+    tile_pass_mode<KS, GRAD, NGT, MODE_NB_COL_F>(P, FT, s_rows, s_X, S, gc_lo, pipe);
 }
 
 __device__ __forceinline__ void pipe_init(Pipe& pipe, unsigned long long* bars) {

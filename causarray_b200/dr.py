@@ -17,6 +17,7 @@ lbfgs, as in the reference -- SURVEY.md section 2, row 7).
 """
 import contextlib
 import gc
+import os
 import warnings
 from typing import Literal
 
@@ -35,6 +36,7 @@ __version__ = "0.1.0"
 
 import concurrent.futures as _cf
 _PS_POOL = _cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix='causarray_ps')
+_PS_FIT_POOL = _cf.ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1))), thread_name_prefix='causarray_psfit')
 
 
 class YhatFactors:
@@ -128,7 +130,7 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
     for tr, te in folds:
         A_tr, X_tr, X_te = A[tr], X_A[tr], X_A[te]
         ctrl = np.sum(A_tr, axis=1) == 0
-        for j in range(A.shape[1]):
+        def fit_one(j):
             elig = mask[tr, j] if mask is not None else (ctrl | (A_tr[:, j] == 1))
             y = A_tr[elig, j]
             if y.size == 0 or np.unique(y).size != 2:
@@ -137,14 +139,19 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
             x = X_tr[elig]
             if np.all(np.ptp(x, axis=0) == 0):
                 if class_weight == 'balanced':
-                    pi_hat[te, j] = 0.5
-                elif isinstance(class_weight, dict):
+                    return 0.5
+                if isinstance(class_weight, dict):
                     sw = np.asarray([class_weight.get(int(v), 1.0) for v in y])
-                    pi_hat[te, j] = np.average(y, weights=sw)
-                else:
-                    pi_hat[te, j] = np.mean(y)
-            else:
-                pi_hat[te, j] = LogisticRegression(**lr_kw).fit(x, y).predict_proba(X_te)[:, 1]
+                    return np.average(y, weights=sw)
+                return np.mean(y)
+            return LogisticRegression(**lr_kw).fit(x, y).predict_proba(X_te)[:, 1]
+
+        # the per-treatment fits are independent (shared controls, own cases): fan them out over host
+        # threads; results are collected in treatment order
+        n_trt = A.shape[1]
+        fits = list(_PS_FIT_POOL.map(fit_one, range(n_trt))) if n_trt > 2 else [fit_one(j) for j in range(n_trt)]
+        for j in range(n_trt):
+            pi_hat[te, j] = fits[j]
     if clip is not None:
         lo, hi = _validate_clip(clip)
         pi_hat = np.clip(pi_hat, lo, hi)
