@@ -367,23 +367,27 @@ int launch_fill_u8(uint8_t* v, int n, uint8_t val, cudaStream_t st) {
 }
 
 // ---- L1 term and adaptive weights -------------------------------------------
+// two deterministic steps: one partial per block of 64 rows, then the fixed-order sum of the partials
+constexpr int L1_ROWS = 64;
 __global__ void k_l1_penalty(const double* __restrict__ X, int rows, int kpad, int lo, int hi,
-                             const double* __restrict__ lam, int ldlam, double* __restrict__ out) {
+                             const double* __restrict__ lam, int ldlam, double* __restrict__ partial) {
   __shared__ double scratch[32];
   const int w = hi - lo;
+  const int r0 = blockIdx.x * L1_ROWS, r1 = min(rows, r0 + L1_ROWS);
   double s = 0.0;
-  for (long e = threadIdx.x; e < (long)rows * w; e += blockDim.x) {
-    const int i = (int)(e / w), c = (int)(e % w);
-    s += fabs(X[(size_t)i * kpad + lo + c]) * lam[(size_t)i * ldlam + c];
-  }
+  for (int i = r0 + (threadIdx.x >> 4); i < r1; i += blockDim.x >> 4)
+    for (int c = threadIdx.x & 15; c < w; c += 16)
+      s += fabs(X[(size_t)i * kpad + lo + c]) * lam[(size_t)i * ldlam + c];
   s = block_sum(s, scratch);
-  if (threadIdx.x == 0) out[0] = s;
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
-int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const double* lam, int ldlam, double* out,
-                      cudaStream_t st) {
-  k_l1_penalty<<<1, 1024, 0, st>>>(X, rows, kpad, lo, hi, lam, ldlam, out);
+int l1_penalty_blocks(int rows) { return (rows + L1_ROWS - 1) / L1_ROWS; }
+int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const double* lam, int ldlam,
+                      double* partial, double* out, cudaStream_t st) {
+  const int nb = l1_penalty_blocks(rows);
+  k_l1_penalty<<<nb, 256, 0, st>>>(X, rows, kpad, lo, hi, lam, ldlam, partial);
   CA_LAUNCH_CHECK();
-  return 0;
+  return launch_sum(partial, nb, out, st);
 }
 
 __global__ void k_adaptive_weights(const double* __restrict__ X, int rows, int kpad, int lo, int hi, double lam0,

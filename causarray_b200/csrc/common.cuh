@@ -109,6 +109,9 @@ __device__ __forceinline__ unsigned mbar_try_wait(unsigned long long* bar, unsig
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   while (!mbar_try_wait(bar, parity)) {
+#ifdef CA_WAIT_SLEEP
+    __nanosleep(CA_WAIT_SLEEP);
+#endif
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {

@@ -579,7 +579,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   // adaptive lasso weights (gcate_opt.py:352-353)
   h->has_lam = false;
   if (a > 0) {
-    if (h->lam.alloc((size_t)p * a)) return -1;
+    if (h->lam.alloc((size_t)p * a) || h->l1part.alloc(l1_penalty_blocks(p))) return -1;
     if (launch_adaptive_weights(h->B.ptr, p, kp, d - a, d, prm->lam, h->lam.ptr, a, st)) return -1;
     h->has_lam = prm->lam != 0.0;
   }
@@ -603,7 +603,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   CA_CUDA(cudaMemcpyAsync(&tys_total, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, st));
   auto objective = [&](double ell_sum, double pen) { return (nll_from_sum(h, ell_sum, tys_total) + pen) / (double)p; };
   auto penalty_async = [&]() -> int {
-    if (a > 0 && h->has_lam) return launch_l1_penalty(h->B.ptr, p, kp, d - a, d, h->lam.ptr, a, h->scal.ptr + 2, st);
+    if (a > 0 && h->has_lam) return launch_l1_penalty(h->B.ptr, p, kp, d - a, d, h->lam.ptr, a, h->l1part.ptr, h->scal.ptr + 2, st);
     CA_CUDA(cudaMemsetAsync(h->scal.ptr + 2, 0, sizeof(double), st));
     return 0;
   };

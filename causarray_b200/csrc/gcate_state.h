@@ -14,7 +14,7 @@ struct ca_gcate {
   cudaStream_t st;
   DevBuf<double> Yn, Ynt, nu, inv_nu, log_nu, colparm, tys_row, tys_col, tys_total, sparsity;
   DevBuf<double> A, B, Aprev, Bprev;
-  DevBuf<double> P1, P2, lam, alpha_gene;
+  DevBuf<double> P1, P2, lam, alpha_gene, l1part;
   int d1 = 0, r2 = 0, a = 0;
   bool has_P1 = false, has_P2 = false, has_lam = false, has_alpha_gene = false;
   DevBuf<uint8_t> gene_active, cell_active;

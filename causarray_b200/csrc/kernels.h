@@ -95,8 +95,9 @@ int launch_step_mask(const double* X, const double* Xprev, int rows, int kpad, i
                      uint8_t* mask, int* count, cudaStream_t st);
 int launch_fill_u8(uint8_t* v, int n, uint8_t val, cudaStream_t st);
 // out = sum_{i, c in [lo,hi)} |X[i,c]| * lam[i*ldlam + c-lo]
+int l1_penalty_blocks(int rows);
 int launch_l1_penalty(const double* X, int rows, int kpad, int lo, int hi, const double* lam, int ldlam,
-                      double* out, cudaStream_t st);
+                      double* partial, double* out, cudaStream_t st);
 // lam[i, c] = lam0 / (|X[i, lo + c]| + 1e-6)
 int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi, double lam0, double* lam,
                             int ldlam, cudaStream_t st);
