@@ -19,6 +19,10 @@ alternating iteration + numpy IRLS over all host cores) on a bounded gene subsam
 import argparse
 import json
 import os
+
+# keep stdout to the single JSON line: a box-level NCCL_DEBUG=VERSION makes NCCL print its banner there
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION",):
+    os.environ["NCCL_DEBUG"] = "WARN"
 import subprocess
 import sys
 import threading
@@ -133,6 +137,7 @@ def run_reference(args, rank, world):
         return
     from oracle import cport
     cores = os.cpu_count() or 1
+    cport.set_threads(cores)
     p_s = args.cpu_genes
     times, upd = [], []
     stats = None
@@ -339,6 +344,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         from oracle import cport
         cores = os.cpu_count() or 1
+        cport.set_threads(cores)
         b = make_batch(1000, p=args.cpu_genes)
         t0 = time.perf_counter()
         st = cpu_step(b, cores)

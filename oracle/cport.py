@@ -43,6 +43,15 @@ def threads():
     return load().gcate_oracle_threads()
 
 
+def set_threads(n):
+    """Number of OpenMP threads of the C restatement (torchrun exports OMP_NUM_THREADS=1)."""
+    lib = load()
+    lib.gcate_oracle_set_threads.argtypes = [ctypes.c_int]
+    lib.gcate_oracle_set_threads.restype = None
+    lib.gcate_oracle_set_threads(int(n))
+    return lib.gcate_oracle_threads()
+
+
 def _d(a):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 

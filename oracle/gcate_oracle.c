@@ -209,6 +209,15 @@ double gcate_update_with_mask(int n, int p, int k, int d, int a, const double* Y
   return -total / (double)n;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is entitled to all host cores */
+void gcate_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int gcate_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
