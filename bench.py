@@ -303,26 +303,45 @@ def main():
     if prof.get("glm_pass", (0, 0))[0] > 0:
         kern["glm_pass"]["achieved_tflops_fp64"] = round(st_sum["gram_flops"] / (prof["glm_pass"][0] * 1e-3) / 1e12, 2)
     dom = max((k for k in alg_bytes if prof.get(k, (0, 0))[0] > 0), key=lambda k: prof[k][0], default=None)
+    # DRAM bytes of one captured launch per kernel class (ncu --set full, committed next to its summary)
+    traffic = {}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        pass
+
+    def kernel_roofline(name):
+        ms, cnt = prof[name]
+        tr = traffic.get(name)
+        if name == "glm_pass":
+            ach = st_sum["gram_flops"] / (ms * 1e-3) / 1e12
+            r = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": fp64_peak_tflops,
+                 "unit": "TFLOP/s", "frac": round(ach / fp64_peak_tflops, 4),
+                 "peak_source": "FP64 DMMA (mma.sync m8n8k4.f64) peak measured with tools/fp64_microbench.cu on this "
+                                "pool's B200; MEASURED_PEAKS.json only holds the bf16 tensor and HBM figures and "
+                                "tcgen05 has no FP64 kind",
+                 "algorithmic_flops_per_cell_gene_iter": "2 [kx(kx+1)/2 + 2 kx]",
+                 "hbm_view": {"achieved_gbs": round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak}}
+        else:
+            ach = alg_bytes[name] / (ms * 1e-3) / 1e9
+            r = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
+                 "frac": round(ach / hbm_peak, 4), "peak_source": peak_src,
+                 "note": "FP64-pipe / latency bound kernel (DMMA + table-driven exp/log share the FP64 units, ncu: "
+                         "~50 % of that pipe); see DESIGN.md section 4"}
+        r["avg_launch_ms"] = round(ms / max(1, cnt), 4)
+        r["launches"] = cnt
+        r["traffic"] = tr["dram_bytes"] if tr else None
+        if tr:
+            r["traffic_note"] = "DRAM read+write bytes of one captured launch (%s); algorithmic bytes of that launch %d" \
+                                % (tr["capture"], tr["algorithmic_bytes"])
+        return r
+
     roofline = None
-    if dom == "glm_pass":
-        ms, cnt = prof[dom]
-        ach = st_sum["gram_flops"] / (ms * 1e-3) / 1e12
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": fp64_peak_tflops,
-                    "unit": "TFLOP/s", "frac": round(ach / fp64_peak_tflops, 4), "traffic": None,
-                    "peak_source": "FP64 DMMA (mma.sync m8n8k4.f64) peak measured with tools/fp64_microbench.cu on this "
-                                   "pool's B200; MEASURED_PEAKS.json only holds the bf16 tensor and HBM figures and "
-                                   "tcgen05 has no FP64 kind",
-                    "avg_launch_ms": round(ms / max(1, cnt), 4), "launches": cnt,
-                    "algorithmic_flops_per_cell_gene_iter": "2 [kx(kx+1)/2 + 2 kx]",
-                    "hbm_view": {"achieved_gbs": round(alg_bytes[dom] / (ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak}}
-    elif dom is not None:
-        ms, cnt = prof[dom]
-        ach = alg_bytes[dom] / (ms * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                    "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": round(ms / max(1, cnt), 4), "launches": cnt,
-                    "note": "FP64-pipe bound kernel (DMMA + table-driven exp/log share the FP64 units); see DESIGN.md "
-                            "section 4 for the FP64 roofline of the same kernel"}
+    if dom is not None:
+        roofline = kernel_roofline(dom)
+        roofline["others"] = [kernel_roofline(k) for k in ("search", "glm_pass", "rowpass_grad")
+                              if k != dom and prof.get(k, (0, 0))[0] > 0]
 
     out = {"metric": "gcate_lfc_cell_gene_updates_per_s", "value": upd_res / t_res, "unit": "cell*gene updates/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
