@@ -3,6 +3,7 @@
 // of the optimiser loop (alter_min, causarray/gcate_opt.py:337-458).
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <new>
@@ -57,7 +58,8 @@ static int gcate_alloc(ca_gcate* h) {
   if (h->ell_c.alloc(n) || h->ell_g.alloc(p) || h->ellfin_c.alloc(n) || h->ellfin_g.alloc(p) ||
       h->Graw_c.alloc((size_t)n * h->ldG) || h->Graw_g.alloc((size_t)p * h->ldG) || h->g_c.alloc((size_t)n * kp) ||
       h->g_g.alloc((size_t)p * kp) || h->f0_c.alloc(n) || h->f0_g.alloc(p) || h->ng_c.alloc(n) || h->ng_g.alloc(p) ||
-      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(4) || h->neval_g.alloc(p) || h->alpha_gene.alloc(p))
+      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(4) || h->neval_g.alloc(p) || h->alpha_gene.alloc(p) || h->ls_pend.alloc(std::max(n, p)) ||
+      h->ls_f01.alloc(std::max(n, p)) || h->ls_e01.alloc(std::max(n, p)) || h->ls_list2.alloc(std::max(n, p)))
     return -1;
   CA_CUDA(cudaMemsetAsync(h->Yn.ptr, 0, h->Yn.bytes(), h->st));
   CA_CUDA(cudaMemsetAsync(h->Ynt.ptr, 0, h->Ynt.bytes(), h->st));
@@ -418,6 +420,11 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
     s.ell_fin = h->ellfin_c.ptr;
     s.neval = nullptr;
     s.eval_total = h->evals.ptr + 0;
+    s.pend = h->ls_pend.ptr;
+    s.f01s = h->ls_f01.ptr;
+    s.e01s = h->ls_e01.ptr;
+    s.list2 = h->ls_list2.ptr;
+    s.count2 = cnt + 5;
     if (launch_search(rp, s, st)) return -1;
     if (h->has_P1) {
       if (launch_pt_v(h->P1.ptr, h->d1, h->d1, h->A.ptr + d, kp, r, n, h->W.ptr, st)) return -1;
@@ -505,6 +512,11 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       s.ell_fin = h->ellfin_g.ptr;
       s.neval = h->neval_g.ptr;
       s.eval_total = h->evals.ptr + 1;
+      s.pend = h->ls_pend.ptr;
+      s.f01s = h->ls_f01.ptr;
+      s.e01s = h->ls_e01.ptr;
+      s.list2 = h->ls_list2.ptr;
+      s.count2 = cnt + 6;
       if (launch_search(rp, s, st)) return -1;
     }
     if (!h->has_P2 && r > 0) {
@@ -723,6 +735,16 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   res->total_cell_updates = tot_c;
   res->cell_evals = (int64_t)ev[0];
   res->gene_evals = (int64_t)ev[1];
+  if (getenv("CA_TIMING")) {
+    std::vector<int> ne(p);
+    CA_CUDA(cudaMemcpy(ne.data(), h->neval_g.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost));
+    int hist[32] = {0};
+    for (int j = 0; j < p; ++j) hist[ne[j] < 0 ? 0 : (ne[j] > 31 ? 31 : ne[j])]++;
+    fprintf(stderr, "[ca] candidates per gene in the last line search:");
+    for (int b = 0; b < 32; ++b)
+      if (hist[b]) fprintf(stderr, " %d:%d", b, hist[b]);
+    fprintf(stderr, "\n");
+  }
   if (getenv("CA_TIMING")) fprintf(stderr, "[ca] line search: cell evals %llu (tile-lockstep %llu), gene evals %llu (tile-lockstep %llu)\n", ev[0], ev[2], ev[1], ev[3]);
   res->loop_seconds = std::chrono::duration<double>(t1 - t0).count();
   return 0;

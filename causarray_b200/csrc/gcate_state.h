@@ -21,6 +21,9 @@ struct ca_gcate {
   DevBuf<int> list_c, list_g, list_clip, counts;  // counts: [0] cells, [1] genes, [2] clip, [3] n_act_c, [4] n_act_g
   DevBuf<double> ell_c, ell_g, ellfin_c, ellfin_g, Graw_c, Graw_g, g_c, g_g, f0_c, f0_g, ng_c, ng_g, W, scal;
   DevBuf<unsigned long long> evals;  // [0] cell evals, [1] gene evals, [2]/[3] cell / gene tile passes x 8
+  DevBuf<uint8_t> ls_pend;           // two-phase line search scratch, max(n, p) entries each
+  DevBuf<double> ls_f01, ls_e01;
+  DevBuf<int> ls_list2;
   DevBuf<int> neval_g;               // candidates each gene needed in its last line search (list ordering key)
   int ldG = 64;
   int any_pois = 0;                  // some nu exceeds thres (the NB kernels then keep their Poisson switch)

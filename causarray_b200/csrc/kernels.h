@@ -42,6 +42,14 @@ struct SearchLaunch {
   double* ell_fin;
   int* neval;
   unsigned long long* eval_total;  // optional device counter of candidate evaluations
+  // two-phase search (all four set, or all null for the single-kernel sequential walk): rows that
+  // fail their first candidate are listed (ordered by `neval` of their previous search when given)
+  // and finished by the multi-candidate kernel
+  unsigned char* pend;   // nrows
+  double* f01s;          // nrows
+  double* e01s;          // nrows
+  int* list2;            // nrows
+  int* count2;
 };
 
 int launch_rowpass(const RowProblem& rp, const double* X, const int* rowlist, const int* count, int nrows,

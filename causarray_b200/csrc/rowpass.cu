@@ -65,6 +65,21 @@ int launch_rowpass(const RowProblem& rp, const double* X, const int* rowlist, co
   return -2;
 }
 
+static int dispatch_search(int ks, const PassCfg& P, const SearchArgs& A, cudaStream_t st) {
+#define CALL_LS(K) launch_search_ks<K>(P, A, st)
+  CA_DISPATCH_KS(ks, CALL_LS)
+#undef CALL_LS
+  set_error("unsupported kpad %d", 4 * ks);
+  return -2;
+}
+static int dispatch_search_multi(int ks, const PassCfg& P, const SearchArgs& A, cudaStream_t st) {
+#define CALL_LM(K) launch_search_multi_ks<K>(P, A, st)
+  CA_DISPATCH_KS(ks, CALL_LM)
+#undef CALL_LM
+  set_error("unsupported kpad %d", 4 * ks);
+  return -2;
+}
+
 int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st) {
   if (s.nrows <= 0) return 0;
   PassCfg P;
@@ -90,11 +105,23 @@ int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st) 
   A.ell_fin = s.ell_fin;
   A.neval = s.neval;
   A.eval_total = s.eval_total;
-#define CALL_LS(K) launch_search_ks<K>(P, A, st)
-  CA_DISPATCH_KS(rp.kpad / 4, CALL_LS)
-#undef CALL_LS
-  set_error("unsupported kpad %d", rp.kpad);
-  return -2;
+  A.pend = s.pend;
+  A.f01s = s.f01s;
+  A.e01s = s.e01s;
+  if (s.pend) {
+    CA_REQUIRE(s.f01s && s.e01s && s.list2 && s.count2, "two-phase search needs all of its buffers");
+    CA_CUDA(cudaMemsetAsync(s.pend, 0, (size_t)s.nrows, st));
+  }
+  int rc = dispatch_search(rp.kpad / 4, P, A, st);
+  if (rc || !s.pend) return rc;
+  // phase B over the rows phase A left pending
+  if (s.neval ? launch_compact_by_key(s.pend, s.neval, s.nrows, s.list2, s.count2, st)
+              : launch_compact(s.pend, s.nrows, s.list2, s.count2, st))
+    return -1;
+  A.rowlist = s.list2;
+  A.count = s.count2;
+  A.pend = nullptr;
+  return dispatch_search_multi(rp.kpad / 4, P, A, st);
 }
 
 }  // namespace ca

@@ -80,6 +80,11 @@ struct SearchArgs {
   double* ell_fin;
   int* neval;
   unsigned long long* eval_total;
+  // two-phase search: phase A (k_search with pend != nullptr) evaluates the first candidate only and
+  // hands the rows that neither accepted nor terminated to phase B (k_search_multi)
+  unsigned char* pend;   // per row: 1 = continue in phase B
+  double* f01s;          // per row: objective / log-likelihood sum of the first candidate
+  double* e01s;
 };
 
 template <int KS>
@@ -102,12 +107,13 @@ struct Smem {
   double* G;       // 8 * NGT*8
 };
 
-__host__ __device__ inline size_t smem_doubles(int tc, int kpad, int ngt, bool search) {
-  return FM_TABLE_DOUBLES + 2 * (size_t)tc * kpad + 64 + 2 * (size_t)tc * 4 + 2 * 8 * ((size_t)tc + 8) + 8 * kpad + (search ? 16 * kpad : 0) + 64 +
+// nx: number of (8 x kpad) row blocks: 1 row pass, 3 line search (X, X0, g), NC + 3 multi-candidate search
+__host__ __device__ inline size_t smem_doubles(int tc, int kpad, int ngt, int nx) {
+  return FM_TABLE_DOUBLES + 2 * (size_t)tc * kpad + 64 + 2 * (size_t)tc * 4 + 2 * 8 * ((size_t)tc + 8) + (size_t)nx * 8 * kpad + 64 +
          8 + 64 * (size_t)ngt * 8 + 8 * (size_t)ngt * 8;
 }
 
-__device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, bool search) {
+__device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, int nx) {
   Smem s;
   s.tab = base;
   base += FM_TABLE_DOUBLES;
@@ -118,10 +124,9 @@ __device__ __forceinline__ Smem carve(double* base, int tc, int kpad, int ngt8, 
   s.Ys = base;
   base += 2 * 8 * (tc + 8);
   s.X = base;
-  base += 8 * kpad;
-  s.X0 = base;
-  s.Gd = base + 8 * kpad;
-  if (search) base += 16 * kpad;
+  s.X0 = base + 8 * kpad;
+  s.Gd = base + 16 * kpad;
+  base += nx * 8 * kpad;
   s.red = base;
   base += 64;
   s.rowsum = base;
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_rowpass(PassCfg P, const 
                                                        double* ell_out, double* G_out, int ldG) {
   constexpr int KPAD = 4 * KS;
   extern __shared__ __align__(16) double smem[];
-  const Smem S = carve(smem, P.tc, KPAD, NGT * 8, false);
+  const Smem S = carve(smem, P.tc, KPAD, NGT * 8, 1);
   __shared__ int s_rows[8];
   __shared__ __align__(8) unsigned long long s_bars[2];
   const int total = rowlist ? *count : nrows;
@@ -481,11 +486,11 @@ template <int KS>
 __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchArgs A) {
   constexpr int KPAD = 4 * KS;
   extern __shared__ __align__(16) double smem[];
-  const Smem S = carve(smem, P.tc, KPAD, 8, true);
+  const Smem S = carve(smem, P.tc, KPAD, 8, 3);
   __shared__ int s_rows[8];
   __shared__ __align__(8) unsigned long long s_bars[2];
   __shared__ double s_t[8], s_f0[8], s_ng[8], s_f01[8], s_e01[8], s_alpha[8], s_efin[8];
-  __shared__ unsigned char s_done[8];
+  __shared__ unsigned char s_done[8], s_pend[8];
   __shared__ int s_mode[8], s_ne[8], s_alldone;
   const int tid = threadIdx.x;
   const int total = A.rowlist ? *A.count : A.nrows;
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
     const int row = (i < total) ? (A.rowlist ? A.rowlist[i] : i) : -1;
     s_rows[tid] = row;
     s_done[tid] = row < 0;
+    s_pend[tid] = 0;
     s_mode[tid] = 0;
     s_ne[tid] = 0;
     if (row >= 0) {
@@ -557,6 +563,11 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
         } else {
           s_efin[tid] = ell;
         }
+      } else if (A.pend) {  // phase A: the remaining candidates of this row are evaluated together in phase B
+        s_done[tid] = 1;
+        s_pend[tid] = 1;
+        A.f01s[row] = f1;
+        A.e01s[row] = ell;
       } else {
         s_t[tid] = t * A.beta;
       }
@@ -572,7 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
   }
   for (int e = tid; e < 8 * KPAD; e += NTHREADS) {
     const int r = e / KPAD, c = e % KPAD, row = s_rows[r];
-    if (row < 0) continue;
+    if (row < 0 || s_pend[r]) continue;
     double v = S.X[e];
     if (s_mode[r] == 1) {
       v = S.X0[e] - s_alpha[r] * S.Gd[e];
@@ -581,8 +592,11 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
     A.X[(size_t)row * KPAD + c] = v;
   }
   if (tid < 8 && s_rows[tid] >= 0) {
-    A.ell_fin[s_rows[tid]] = s_efin[tid];
-    if (A.neval) A.neval[s_rows[tid]] = s_ne[tid];
+    if (A.pend) A.pend[s_rows[tid]] = s_pend[tid];
+    if (!s_pend[tid]) {
+      A.ell_fin[s_rows[tid]] = s_efin[tid];
+      if (A.neval) A.neval[s_rows[tid]] = s_ne[tid];
+    }
     if (A.eval_total) atomicAdd(A.eval_total, (unsigned long long)s_ne[tid]);
   }
   if (tid == 0 && A.eval_total) {  // lockstep cost of the tile: rows x the slowest row's candidates
@@ -592,11 +606,303 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
   }
 }
 
+// ---------------------------------------------------------------------------
+// Phase B of the line search: NC candidates per pass over the data.
+//
+// In stage 2 most genes fail the Armijo test for every candidate (the histogram of candidates per
+// gene is 1 | 11-13, nothing in between), so walking the candidates one pass at a time re-stages
+// M and Y a dozen times and gives a lane only four dependency chains.  Here a warp keeps the two
+// tiles of Y and the B fragments of a k-step in registers and runs NC candidate rows (A fragments
+// from shared memory) against them: 2 NC independent DMMA chains and 4 NC independent epilogues per
+// lane.  The accept / stop / fallback rule is then applied to the NC objectives in candidate order,
+// exactly as the sequential walk does.
+// ---------------------------------------------------------------------------
+template <int KS, int MODE, int NC>
+__device__ __forceinline__ void tile_pass_multi_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
+                                                     const double* s_Xc, const Smem& S, Pipe& pipe) {
+  constexpr int KPAD = 4 * KS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lr = lane >> 2, lc = lane & 3;
+  const int tc = P.tc;
+  const int row = s_rows[lr];
+  double nu_r = 1.0, inu_r = 1.0, lnu_r = 0.0;
+  bool pois_r = false;
+  if (mode_row(MODE) && row >= 0) {
+    nu_r = P.nu[row];
+    inu_r = P.inv_nu[row];
+    lnu_r = P.log_nu[row];
+    pois_r = nu_r > P.thres;
+  }
+  const NbClip clip = P.clip;
+  const double* ap = s_Xc + lr * KPAD + lc;  // A fragment of candidate c, k-step ks: ap[c * 8 * KPAD + 4 * ks]
+  double accA[NC], accB[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) accA[c] = accB[c] = 0.0;
+
+  const int nchunks = (P.ncols + tc - 1) / tc;
+  const int chunk_elems = tc * KPAD;
+  const int ldy = tc + 8;
+  stage_chunk<KS>(P, 0, S.M, S.cp, S.Ys, s_rows, pipe.bar + 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) {
+      const int sn = (ch + 1) & 1;
+      stage_chunk<KS>(P, ch + 1, S.M + sn * chunk_elems, S.cp + sn * tc, S.Ys + sn * 8 * ldy, s_rows, pipe.bar + sn);
+    }
+    mbar_wait(pipe.bar + (ch & 1), (pipe.phase >> (ch & 1)) & 1u);
+    pipe.phase ^= 1u << (ch & 1);
+    if (ch == nchunks - 1) __syncthreads();  // the ragged-tail zero fill (generic stores) of the last chunk
+    const double* Mb = S.M + (ch & 1) * chunk_elems;
+    const double4* Cb = S.cp + (ch & 1) * tc;
+    const double* Yb = S.Ys + (ch & 1) * 8 * ldy + lr * ldy + 2 * lc;
+    const int nrem = P.ncols - ch * tc;
+    const int ntile = min(tc, round_up(nrem, 8)) >> 3;
+    auto pair_body = [&](auto ragged_tag, int tA, int tB, bool hasB) {
+      constexpr bool RAGGED = decltype(ragged_tag)::value;
+      const int clA = tA * 8 + 2 * lc, clB = tB * 8 + 2 * lc;
+      const double2 yA = *reinterpret_cast<const double2*>(Yb + tA * 8);
+      const double2 yB = *reinterpret_cast<const double2*>(Yb + tB * 8);
+      const double* bpA = Mb + (tA * 8 + lr) * KPAD + lc;
+      const double* bpB = Mb + (tB * 8 + lr) * KPAD + lc;
+      double pa[NC][2], pb[NC][2];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) pa[c][0] = pa[c][1] = pb[c][0] = pb[c][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double bA = bpA[ks * 4], bB = bpB[ks * 4];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const double a = ap[c * 8 * KPAD + ks * 4];
+          dmma884(pa[c][0], pa[c][1], a, bA);
+          dmma884(pb[c][0], pb[c][1], a, bB);
+        }
+      }
+      double4 cA0 = make_double4(nu_r, inu_r, lnu_r, pois_r ? 1.0 : 0.0), cA1 = cA0, cB0 = cA0, cB1 = cA0;
+      if (mode_col(MODE)) {
+        cA0 = Cb[clA];
+        cA1 = Cb[clA + 1];
+        cB0 = Cb[clB];
+        cB1 = Cb[clB + 1];
+      }
+      bool vA0 = true, vA1 = true, vB0 = true, vB1 = true;
+      if (RAGGED) {
+        vA0 = clA < nrem;
+        vA1 = clA + 1 < nrem;
+        vB0 = hasB && clB < nrem;
+        vB1 = hasB && clB + 1 < nrem;
+      }
+      double dummy = 0.0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, accA[c], dummy);
+        eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, accB[c], dummy);
+        eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, accA[c], dummy);
+        eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, accB[c], dummy);
+      }
+    };
+#pragma unroll 1
+    for (int t = warp; t < ntile; t += 2 * NWARPS) {
+      const bool hasB = t + NWARPS < ntile;
+      const int tB = hasB ? t + NWARPS : t;
+      if (!hasB || tB * 8 + 8 > nrem)
+        pair_body(std::true_type{}, t, tB, hasB);
+      else
+        pair_body(std::false_type{}, t, tB, hasB);
+    }
+    __syncthreads();
+  }
+  // fixed-order reduction per candidate: 4 lanes of a row, then the 8 warps (scratch: S.Gred / S.G)
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double e = accA[c] + accB[c];
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    if (lc == 0) S.Gred[(c * NWARPS + warp) * 8 + lr] = e;
+  }
+  __syncthreads();
+  if (tid < 8 * NC) {
+    const int c = tid >> 3, r = tid & 7;
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) sum += S.Gred[(c * NWARPS + w) * 8 + r];
+    S.G[c * 8 + r] = sum;
+  }
+  __syncthreads();
+}
+
+template <int KS, int NC>
+__device__ __forceinline__ void tile_pass_multi(const PassCfg& P, const FmTables& FT, const int* s_rows,
+                                                const double* s_Xc, const Smem& S, Pipe& pipe) {
+  if (P.family != CA_FAMILY_NB)
+    tile_pass_multi_mode<KS, MODE_POIS, NC>(P, FT, s_rows, s_Xc, S, pipe);
+  else if (P.nu_per_row && P.any_pois)
+    tile_pass_multi_mode<KS, MODE_NB_ROW, NC>(P, FT, s_rows, s_Xc, S, pipe);
+  else if (P.nu_per_row)
+    tile_pass_multi_mode<KS, MODE_NB_ROW_F, NC>(P, FT, s_rows, s_Xc, S, pipe);
+  else if (P.any_pois)
+    tile_pass_multi_mode<KS, MODE_NB_COL, NC>(P, FT, s_rows, s_Xc, S, pipe);
+  else
+    tile_pass_multi_mode<KS, MODE_NB_COL_F, NC>(P, FT, s_rows, s_Xc, S, pipe);
+}
+
+#ifndef CA_SEARCH_NC
+#define CA_SEARCH_NC 4
+#endif
+constexpr int SEARCH_NC = CA_SEARCH_NC;  // candidates per pass in phase B
+
+// Rows listed in A.rowlist failed their first candidate in phase A (A.f01s / A.e01s hold its
+// objective and log-likelihood sum; X is untouched).  Candidates j = 1, 2, ... are evaluated NC at a
+// time; per row the walk of causarray/gcate_opt.py:60-82 is replayed over the objectives in order.
+template <int KS, int NC>
+__global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search_multi(PassCfg P, SearchArgs A) {
+  constexpr int KPAD = 4 * KS;
+  extern __shared__ __align__(16) double smem[];
+  const Smem S = carve(smem, P.tc, KPAD, 8, NC + 3);
+  double* Xc = S.X;                        // NC x 8 x KPAD candidate rows
+  double* X0 = S.X + NC * 8 * KPAD;
+  double* Gd = X0 + 8 * KPAD;
+  double* Xfin = Gd + 8 * KPAD;
+  __shared__ int s_rows[8];
+  __shared__ __align__(8) unsigned long long s_bars[2];
+  __shared__ double s_tlast[8], s_tc[NC][8], s_f0[8], s_ng[8], s_f01[8], s_e01[8], s_alpha[8], s_efin[8];
+  __shared__ unsigned char s_done[8];
+  __shared__ int s_mode[8], s_ne[8], s_sel[8], s_alldone;
+  const int tid = threadIdx.x;
+  const int total = A.rowlist ? *A.count : A.nrows;
+  const int tile0 = blockIdx.x * TILE_ROWS;
+  if (tile0 >= total) return;
+  Pipe pipe;
+  pipe_init(pipe, s_bars);
+  const FmTables FT = fm_load_tables(S.tab, P.fm_tables);
+  if (tid < 8) {
+    const int i = tile0 + tid;
+    const int row = (i < total) ? (A.rowlist ? A.rowlist[i] : i) : -1;
+    s_rows[tid] = row;
+    s_done[tid] = row < 0;
+    s_mode[tid] = 0;
+    s_ne[tid] = 1;  // the first candidate was evaluated in phase A
+    s_sel[tid] = -1;
+    if (row >= 0) {
+      s_alpha[tid] = A.alpha_row ? A.alpha_row[row] : A.alpha;
+      s_tlast[tid] = s_alpha[tid];
+      s_f0[tid] = A.f0[row];
+      s_ng[tid] = A.normg[row];
+      s_f01[tid] = A.f01s[row];
+      s_e01[tid] = A.e01s[row];
+    } else {
+      s_tlast[tid] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 8 * KPAD; e += NTHREADS) {
+    const int r = e / KPAD, c = e % KPAD, row = s_rows[r];
+    X0[e] = (row >= 0) ? A.X[(size_t)row * KPAD + c] : 0.0;
+    Gd[e] = (row >= 0) ? A.g[(size_t)row * KPAD + c] : 0.0;
+    Xfin[e] = X0[e];
+  }
+  const double ncols_d = (double)P.ncols;
+  const int nprox = A.prox_hi - A.prox_lo;
+  int groups = 0;
+  for (int j0 = 1; j0 < A.max_iters; j0 += NC) {
+    ++groups;
+    if (tid < 8) {
+      double t = s_tlast[tid];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        t = t * A.beta;
+        s_tc[c][tid] = t;
+      }
+      s_tlast[tid] = t;
+    }
+    __syncthreads();
+    for (int e = tid; e < NC * 8 * KPAD; e += NTHREADS) {
+      const int c = e / (8 * KPAD), rc = e % (8 * KPAD), r = rc / KPAD, col = rc % KPAD;
+      double v = X0[rc] - s_tc[c][r] * Gd[rc];
+      if (A.lam && col >= A.prox_lo && col < A.prox_hi && s_rows[r] >= 0)
+        v = soft_thr(v, A.lam[(size_t)s_rows[r] * A.ldlam + (col - A.prox_lo)]);
+      Xc[e] = v;
+    }
+    __syncthreads();
+    tile_pass_multi<KS, NC>(P, FT, s_rows, Xc, S, pipe);
+    if (tid < 8 && !s_done[tid]) {
+      const int row = s_rows[tid];
+      for (int c = 0; c < NC; ++c) {
+        const int it = j0 + c;  // iteration index of the reference's loop
+        if (it >= A.max_iters) break;
+        double pen = 0.0;
+        if (A.lam && nprox > 0) {
+          for (int q = 0; q < nprox; ++q)
+            pen += A.lam[(size_t)row * A.ldlam + q] * fabs(Xc[(c * 8 + tid) * KPAD + A.prox_lo + q]);
+          pen /= (double)nprox;
+        }
+        const double ell = S.G[c * 8 + tid];
+        const double f1 = -(ell + A.tys[row]) / ncols_d + pen;
+        const double t = s_tc[c][tid];
+        s_ne[tid] += 1;
+        if (f1 < s_f0[tid] - A.tol * t * s_ng[tid]) {
+          s_done[tid] = 1;
+          s_sel[tid] = c;
+          s_efin[tid] = ell;
+          break;
+        } else if (t < 1e-4 || it == A.max_iters - 1) {
+          s_done[tid] = 1;
+          if (s_f01[tid] < 1.1 * f1) {
+            s_mode[tid] = 1;  // fall back to the full initial step
+            s_sel[tid] = NC;
+            s_efin[tid] = s_e01[tid];
+          } else {
+            s_sel[tid] = c;
+            s_efin[tid] = ell;
+          }
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    // keep the chosen point of rows that finished in this group (Xc is overwritten by the next group)
+    for (int e = tid; e < 8 * KPAD; e += NTHREADS) {
+      const int r = e / KPAD, col = e % KPAD, sel = s_sel[r];
+      if (sel < 0) continue;
+      double v;
+      if (sel == NC) {
+        v = X0[e] - s_alpha[r] * Gd[e];
+        if (A.lam && col >= A.prox_lo && col < A.prox_hi)
+          v = soft_thr(v, A.lam[(size_t)s_rows[r] * A.ldlam + (col - A.prox_lo)]);
+      } else {
+        v = Xc[(sel * 8 + r) * KPAD + col];
+      }
+      Xfin[e] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int all = 1;
+      for (int r = 0; r < 8; ++r) {
+        all &= (int)s_done[r];
+        s_sel[r] = -1;
+      }
+      s_alldone = all;
+    }
+    __syncthreads();
+    if (s_alldone) break;
+  }
+  for (int e = tid; e < 8 * KPAD; e += NTHREADS) {
+    const int r = e / KPAD, c = e % KPAD, row = s_rows[r];
+    if (row >= 0) A.X[(size_t)row * KPAD + c] = Xfin[e];
+  }
+  if (tid < 8 && s_rows[tid] >= 0) {
+    A.ell_fin[s_rows[tid]] = s_efin[tid];
+    if (A.neval) A.neval[s_rows[tid]] = s_ne[tid];
+    if (A.eval_total) atomicAdd(A.eval_total, (unsigned long long)(s_ne[tid] - 1));
+  }
+  if (tid == 0 && A.eval_total) atomicAdd(A.eval_total + 2, (unsigned long long)(8 * NC * groups));
+}
+
 // per-KS launchers (explicitly instantiated in rowpass_inst.cu, one object file per KS)
 template <int KS>
 int launch_rowpass_ks(const PassCfg& P, const double* X, const int* rowlist, const int* count, int nrows,
                       bool want_grad, int gc_lo, int gc_n, double* ell_out, double* G_out, int ldG, cudaStream_t st);
 template <int KS>
 int launch_search_ks(const PassCfg& P, const SearchArgs& A, cudaStream_t st);
+template <int KS>
+int launch_search_multi_ks(const PassCfg& P, const SearchArgs& A, cudaStream_t st);
 
 }  // namespace ca
