@@ -115,25 +115,57 @@ __global__ void k_glm_solve(GlmSolve Q) {
   if (!run) return;
   // ---- normal equations ----
   const int ld = kx + 1;
-  double* L = sm + (size_t)warp * (kx * ld + 2 * kx);
+  double* L = sm + (size_t)warp * (kx * ld + 3 * kx);
   double* sc = L + kx * ld;
   double* b = sc + kx;
-  for (int e = lane; e < kx * kx; e += 32) {
-    // fixed summation order over the splits; loads issued eight at a time
-    const int i = e / kx, j = e % kx;
-    const int ei = (int)Q.emap[i] * kxi + (int)Q.emap[j];
-    double g = 0.0;
-    int sp = 0;
-    for (; sp + 8 <= Q.nsplit; sp += 8) {
-      double v[8];
+  double* invd = b + kx;  // reciprocals of the Cholesky diagonal
+  {
+    // fixed summation order over the splits; a lane walks the flat index e = i * kx + j in steps of
+    // 32 (row / column tracked incrementally: no division) and keeps 2 x nsplit loads in flight
+    int i0 = lane / kx, j0 = lane - i0 * kx;
+    const int di = 32 / kx, dj = 32 - di * kx;
+    for (int e = lane; e < kx * kx; e += 64) {
+      int i1 = i0 + di, j1 = j0 + dj;
+      if (j1 >= kx) {
+        j1 -= kx;
+        ++i1;
+      }
+      const bool two = e + 32 < kx * kx;
+      const int ea = (int)Q.emap[i0] * kxi + (int)Q.emap[j0];
+      const int eb = two ? (int)Q.emap[i1] * kxi + (int)Q.emap[j1] : ea;
+      double ga = 0.0, gb = 0.0;
+      int sp = 0;
+      for (; sp + 8 <= Q.nsplit; sp += 8) {
+        double va[8], vb[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = part0[(size_t)(sp + u) * Q.part_ld + ei];
+        for (int u = 0; u < 8; ++u) {
+          va[u] = part0[(size_t)(sp + u) * Q.part_ld + ea];
+          vb[u] = part0[(size_t)(sp + u) * Q.part_ld + eb];
+        }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) g += v[u];
+        for (int u = 0; u < 8; ++u) {
+          ga += va[u];
+          gb += vb[u];
+        }
+      }
+      for (; sp < Q.nsplit; ++sp) {
+        ga += part0[(size_t)sp * Q.part_ld + ea];
+        gb += part0[(size_t)sp * Q.part_ld + eb];
+      }
+      if (Q.ridge && i0 == j0) ga += Q.ridge[i0];
+      L[i0 * ld + j0] = ga;
+      if (two) {
+        if (Q.ridge && i1 == j1) gb += Q.ridge[i1];
+        L[i1 * ld + j1] = gb;
+      }
+      // advance both cursors by 64
+      i0 = i1 + di;
+      j0 = j1 + dj;
+      if (j0 >= kx) {
+        j0 -= kx;
+        ++i0;
+      }
     }
-    for (; sp < Q.nsplit; ++sp) g += part0[(size_t)sp * Q.part_ld + ei];
-    if (Q.ridge && i == j) g += Q.ridge[i];
-    L[i * ld + j] = g;
   }
   for (int i = lane; i < kx; i += 32) {
     double r = 0.0;
@@ -144,28 +176,46 @@ __global__ void k_glm_solve(GlmSolve Q) {
   bool bad = false;
   for (int i = lane; i < kx; i += 32) {
     const double dgn = L[i * ld + i];
-    sc[i] = dgn > 0.0 ? 1.0 / sqrt(dgn) : 0.0;
+    sc[i] = dgn > 0.0 ? rsqrt(dgn) : 0.0;
     if (!(dgn > 0.0)) bad = true;
   }
   __syncwarp();
-  for (int e = lane; e < kx * kx; e += 32) {
-    const int i = e / kx, j = e % kx;
-    L[i * ld + j] *= sc[i] * sc[j];
+  // Jacobi scaling, one matrix row per lane
+  for (int i = lane; i < kx; i += 32) {
+    const double si = sc[i];
+    for (int j = 0; j <= i; ++j) L[i * ld + j] *= si * sc[j];
+    b[i] *= si;
   }
-  for (int i = lane; i < kx; i += 32) b[i] *= sc[i];
   __syncwarp();
-  // right-looking Cholesky, lower triangle
+  // Right-looking Cholesky of the lower triangle, one matrix ROW per lane (rows lane and lane + 32):
+  // the trailing update of row i is a run of FMAs over its columns with no index arithmetic (the
+  // first version walked the trailing block as a flat index with a division and a modulo per
+  // element and took 80 us per 26 x 26 system -- most of an IRLS tail iteration).
+  // ld = kx + 1 is odd, so the row-per-lane accesses are bank-conflict free.
   for (int j = 0; j < kx; ++j) {
     const double djj = L[j * ld + j];
     if (!(djj > 1e-13)) bad = true;
-    const double inv = 1.0 / sqrt(djj > 1e-300 ? djj : 1e-300);
+    const double inv = rsqrt(djj > 1e-300 ? djj : 1e-300);
+    if (lane == 0) invd[j] = inv;
+    for (int i = lane; i < kx; i += 32)
+      if (i >= j) L[i * ld + j] *= inv;
     __syncwarp();
-    for (int i = j + lane; i < kx; i += 32) L[i * ld + j] *= inv;
-    __syncwarp();
-    for (int e = lane; e < (kx - j - 1) * (kx - j - 1); e += 32) {
-      const int i = j + 1 + e / (kx - j - 1), c = j + 1 + e % (kx - j - 1);
-      if (c <= i) L[i * ld + c] -= L[i * ld + j] * L[c * ld + j];
-    }
+    for (int i = lane; i < kx; i += 32)
+      if (i > j) {
+        const double lij = L[i * ld + j];
+        double* Li = L + i * ld;
+        const double* Lj = L + j;
+        int c = j + 1;
+        for (; c + 3 <= i; c += 4) {  // four independent updates in flight
+          const double a0 = Lj[c * ld], a1 = Lj[(c + 1) * ld], a2 = Lj[(c + 2) * ld], a3 = Lj[(c + 3) * ld];
+          const double r0 = Li[c], r1 = Li[c + 1], r2 = Li[c + 2], r3 = Li[c + 3];
+          Li[c] = fma(-lij, a0, r0);
+          Li[c + 1] = fma(-lij, a1, r1);
+          Li[c + 2] = fma(-lij, a2, r2);
+          Li[c + 3] = fma(-lij, a3, r3);
+        }
+        for (; c <= i; ++c) Li[c] = fma(-lij, Lj[c * ld], Li[c]);
+      }
     __syncwarp();
   }
   bad = __any_sync(0xffffffffu, bad);
@@ -177,34 +227,41 @@ __global__ void k_glm_solve(GlmSolve Q) {
     }
     return;
   }
-  // forward / backward substitution: the dot product of every row is spread over the lanes and
-  // reduced with a fixed shuffle tree (kx <= 64)
-  for (int i = 0; i < kx; ++i) {
-    double s = 0.0;
-    for (int c = lane; c < i; c += 32) s += L[i * ld + c] * b[c];
-    s = warp_sum(s);
-    if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+  // column-oriented forward / backward substitution: lane i owns b[i]; the diagonal enters through
+  // its stored reciprocal (after the scaled column the diagonal entry of L is djj * inv = 1 / inv)
+  for (int j = 0; j < kx; ++j) {
+    const double yj = b[j] * invd[j];
+    __syncwarp();
+    for (int i = lane; i < kx; i += 32) {
+      if (i > j)
+        b[i] = fma(-L[i * ld + j], yj, b[i]);
+      else if (i == j)
+        b[i] = yj;
+    }
     __syncwarp();
   }
-  for (int i = kx - 1; i >= 0; --i) {
-    double s = 0.0;
-    for (int c = i + 1 + lane; c < kx; c += 32) s += L[c * ld + i] * b[c];
-    s = warp_sum(s);
-    if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+  for (int j = kx - 1; j >= 0; --j) {
+    const double xj = b[j] * invd[j];
+    __syncwarp();
+    for (int i = lane; i < kx; i += 32) {
+      if (i < j)
+        b[i] = fma(-L[j * ld + i], xj, b[i]);
+      else if (i == j)
+        b[i] = xj;
+    }
     __syncwarp();
   }
-  if (lane == 0) {
-    bool fin = true;
-    for (int i = 0; i < kx; ++i) {
-      const double v = b[i] * sc[i];
-      Q.beta[(size_t)gene * kx + i] = v;
-      fin = fin && (v == v) && !isinf(v);
-    }
-    if (!fin) {
-      Q.status[gene] = 2;
-      Q.n_iter[gene] = Q.iter;
-      atomicAdd(Q.n_active, -1);
-    }
+  bool fin = true;
+  for (int i = lane; i < kx; i += 32) {
+    const double v = b[i] * sc[i];
+    Q.beta[(size_t)gene * kx + i] = v;
+    fin = fin && (v == v) && !isinf(v);
+  }
+  fin = __all_sync(0xffffffffu, fin);
+  if (!fin && lane == 0) {
+    Q.status[gene] = 2;
+    Q.n_iter[gene] = Q.iter;
+    atomicAdd(Q.n_active, -1);
   }
 }
 
@@ -569,7 +626,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   if (h->genelist.alloc(p)) return -1;
   const int solve_warps = 4;
-  const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 2 * kx);
+  const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 3 * kx);
   CA_CUDA(cudaFuncSetAttribute(k_glm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_sm));
   GlmSolve Q;
   Q.p = p;

@@ -233,6 +233,19 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
     return Y_hat, pi_hat
 
 
+def _repeated_labels(labels, idx):
+    """Column ``labels[idx]`` for the result frame.  For string labels the (short) label array is
+    converted to pandas' string dtype once and then gathered -- building the 120 000-row column from
+    Python objects and letting the DataFrame constructor infer its dtype cost 20 ms per batch."""
+    labels = np.asarray(labels)
+    if labels.dtype.kind in 'OU' and all(isinstance(v, str) for v in labels.tolist()):
+        try:
+            return pd.array(labels, dtype='str').take(idx)
+        except (TypeError, ValueError):      # pandas without the 'str' dtype alias
+            pass
+    return labels[idx]
+
+
 def _add_log2fc_columns(df_res):
     """(Re)compute ``log2fc`` / ``log2fc_se`` right after ``std`` as exact rescalings of ``tau`` / ``std``."""
     ln2 = np.log(2.0)
@@ -378,14 +391,15 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         t_all[np.isinf(std_all)] = np.nan
         pv, qv, pva, qva = bh_correction_multi(t_all, df=df_all)
         gn = np.asarray(list(gene_names))
-        cols = {'gene_names': np.tile(gn, n_trt), 'tau': tau_all.ravel(), 'std': std_all.ravel(),
+        cols = {'gene_names': _repeated_labels(gn, np.tile(np.arange(p), n_trt)), 'tau': tau_all.ravel(),
+                'std': std_all.ravel(),
                 'stat': t_all.ravel(), 'rej': np.zeros(n_trt * p), 'pvalue': pv.ravel(), 'padj': qv.ravel(),
                 'pvalue_emp_null_adj': pva.ravel(), 'padj_emp_null_adj': qva.ravel(),
                 'mean_control': np.concatenate([q[4]['mean_control'] for q in per_trt]),
                 'mean_treated': np.concatenate([q[4]['mean_treated'] for q in per_trt]),
                 'estimable': np.concatenate([q[4]['estimable'] for q in per_trt])}
         if n_trt > 1:
-            cols['trt'] = np.repeat(np.asarray(list(trt_names), dtype=object), p)
+            cols['trt'] = _repeated_labels(np.asarray(list(trt_names), dtype=object), np.repeat(np.arange(n_trt), p))
         df_res = pd.DataFrame(cols)
         for j in range(n_trt):
             n_bad = int(np.sum(~np.asarray(per_trt[j][4]['estimable'], dtype=bool)))

@@ -26,3 +26,5 @@ for fam, nu in (("poisson", None), ("nb", b["disp"])):
     L.profile_enable(False)
     print(fam, "fit %.1f ms" % (dt * 1e3), "gene-iters", int(it.sum()), "max it", int(it.max()), "bad", int((st != 0).sum()),
           {k: (round(v[0], 2), v[1]) for k, v in prof.items() if v[1]})
+    h = np.bincount(np.minimum(it, 100))
+    print("   iterations histogram:", {int(k): int(v) for k, v in enumerate(h) if v})
