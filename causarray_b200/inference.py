@@ -52,23 +52,8 @@ _POOL = _cf.ThreadPoolExecutor(max_workers=_N_THREADS, thread_name_prefix='causa
 _MAD_NORMAL = 0.6744897501960817   # scipy's scale="normal": Phi^{-1}(3/4)
 
 
-def _bh_rows(p):
-    """Row-wise Benjamini-Hochberg with NaN entries left out of each family; the rows (one family
-    per treatment) are fanned out over host threads -- the sort dominates and releases the GIL."""
-    a = p.shape[0]
-    if a < 2 or p.size < 20000:
-        return _bh_rows_block(p)
-    out = np.empty_like(p)
-    rows = np.array_split(np.arange(a), min(a, _N_THREADS))
-
-    def work(idx):
-        if idx.size:
-            out[idx] = _bh_rows_block(p[idx])
-    list(_POOL.map(work, rows))
-    return out
-
-
 def _bh_rows_block(p):
+    """Row-wise Benjamini-Hochberg with NaN entries left out of each family (vectorised)."""
     a, m = p.shape
     order = np.argsort(p, axis=1)                      # NaNs sort last
     ps = np.take_along_axis(p, order, axis=1)
@@ -84,32 +69,39 @@ def _bh_rows_block(p):
     return out
 
 
+def _tail_parallel(x, dfa):
+    """Two-sided tail probabilities of ``x`` (any shape), Student-t with ``dfa`` or normal, with the
+    flat array cut into one contiguous piece per host thread (scipy.special ufuncs release the GIL;
+    the Student-t tail -- an incomplete beta -- costs ~0.2 us per value)."""
+    import scipy.special as sc
+    xf = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    out = np.empty_like(xf)
+    if dfa is None:
+        np.multiply(sc.ndtr(-np.abs(xf)), 2.0, out=out)
+        return out.reshape(np.shape(x))
+    df_f = np.ascontiguousarray(np.broadcast_to(dfa, np.shape(x)), dtype=np.float64).ravel()
+    cuts = np.linspace(0, xf.size, _N_THREADS + 1).astype(int)
+
+    def work(i):
+        lo, hi = cuts[i], cuts[i + 1]
+        if hi > lo:
+            sc.stdtr(df_f[lo:hi], -np.abs(xf[lo:hi]), out=out[lo:hi])
+            out[lo:hi] *= 2.0
+    list(_POOL.map(work, range(_N_THREADS)))
+    return out.reshape(np.shape(x))
+
+
 def bh_correction_multi(tvalues, df=None):
     """``bh_correction`` applied to every row of ``tvalues (a, p)`` (one BH family per treatment, as
-    the reference loops over treatments), vectorised over the rows.  The tail probabilities call
-    ``scipy.special.stdtr`` / ``ndtr`` directly -- the functions behind ``scipy.stats.t.sf`` /
-    ``norm.sf`` -- without the distribution-object overhead."""
-    import scipy.special as sc
+    the reference loops over treatments).  The tail probabilities call ``scipy.special.stdtr`` /
+    ``ndtr`` directly -- the functions behind ``scipy.stats.t.sf`` / ``norm.sf`` -- without the
+    distribution-object overhead, fanned out over host threads."""
     t = np.asarray(tvalues, dtype=np.float64)
+    a = t.shape[0]
     keep = ~np.isnan(t)
-
-    def tail(x):
-        if df is None:
-            return sc.ndtr(-np.abs(x)) * 2
-        # the Student-t tail (incomplete beta) costs ~0.3 us per value: fan the rows out over host
-        # threads (scipy.special ufuncs release the GIL)
-        dfa = np.asarray(df, dtype=np.float64)
-        out = np.empty_like(x)
-        rows = np.array_split(np.arange(x.shape[0]), min(x.shape[0], _N_THREADS))
-
-        def work(idx):
-            if idx.size:
-                out[idx] = sc.stdtr(dfa[idx], -np.abs(x[idx])) * 2
-        list(_POOL.map(work, rows))
-        return out
+    dfa = None if df is None else np.asarray(df, dtype=np.float64)
     with np.errstate(invalid='ignore'):
-        pv = np.where(keep, tail(t), np.nan)
-        qv = _bh_rows(pv)
+        pv = np.where(keep, _tail_parallel(t, dfa), np.nan)
         tm = np.where(keep, t, np.nan)
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
@@ -118,8 +110,11 @@ def bh_correction_multi(tvalues, df=None):
         ok = mad > 0
         t_adj = (t - med[:, None]) / np.where(ok, mad, 1.0)[:, None]
         keep_adj = keep & ok[:, None]
-        pva = np.where(keep_adj, tail(t_adj), np.nan)
-        qva = _bh_rows(pva)
+        pva = np.where(keep_adj, _tail_parallel(t_adj, dfa), np.nan)
+        # (the row-wise sorts are many small numpy calls: fanning them out over threads only adds
+        # GIL contention -- measured slower than the vectorised form)
+        qv = _bh_rows_block(pv)
+        qva = _bh_rows_block(pva)
     return pv, qv, pva, qva
 
 
