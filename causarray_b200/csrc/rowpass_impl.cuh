@@ -154,18 +154,22 @@ __device__ __forceinline__ void stage_chunk(const PassCfg& P, int c, double* dst
   const int nvalid = min(P.tc, P.ncols - col0);
   const int npad = min(P.tc, round_up(nvalid, 8));
   const int ldy = P.tc + 8;
-  if (threadIdx.x == 0) {
+  // The ten copies of a chunk are issued by ten different lanes: lane 0 of warp w requests row w of
+  // Y, warp 0 also arms the barrier and requests M, warp 1 the column parameters.  (With one thread
+  // issuing everything its warp was ~200 cycles late at every per-chunk CTA barrier.)  A copy that
+  // completes before the expect_tx is harmless: the phase cannot complete before warp 0's arrive.
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
     const unsigned bM = (unsigned)(nvalid * KPAD * sizeof(double));
     const unsigned bC = P.colparm ? (unsigned)(nvalid * sizeof(double4)) : 0u;
     const unsigned bY = (unsigned)(npad * sizeof(double));
-    mbar_expect_tx(bar, bM + bC + 8u * bY);
-    bulk_g2s(dstM, P.M + (size_t)col0 * KPAD, bM, bar);
-    if (P.colparm) bulk_g2s(dstC, P.colparm + col0, bC, bar);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int row = s_rows[r];
-      bulk_g2s(dstY + r * ldy, P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + col0, bY, bar);
+    if (w == 0) {
+      mbar_expect_tx(bar, bM + bC + 8u * bY);
+      bulk_g2s(dstM, P.M + (size_t)col0 * KPAD, bM, bar);
     }
+    if (w == 1 && P.colparm) bulk_g2s(dstC, P.colparm + col0, bC, bar);
+    const int row = s_rows[w];
+    bulk_g2s(dstY + w * ldy, P.Y + (size_t)(row >= 0 ? row : 0) * P.ldY + col0, bY, bar);
   }
   // ragged tail of the last chunk: zero rows of M and neutral column parameters (generic stores
   // to addresses the bulk copies do not touch)
