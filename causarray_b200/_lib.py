@@ -99,6 +99,8 @@ _SIGNATURES = {
     "ca_profile_get": [_c_int, _D, ctypes.POINTER(ctypes.c_int64)],
     "ca_launch_count": [],
     "ca_test_fastmath": [_D, _c_int, _c_int, _D],
+    "ca_host_bh_rows": [_D, _c_int, _c_int, _D],
+    "ca_host_median_mad_rows": [_D, _c_int, _c_int, _D, _D],
 }
 _RESTYPE = {"ca_last_error": ctypes.c_char_p, "ca_profile_class_name": ctypes.c_char_p,
             "ca_launch_count": ctypes.c_int64}

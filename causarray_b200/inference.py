@@ -52,8 +52,44 @@ _POOL = _cf.ThreadPoolExecutor(max_workers=_N_THREADS, thread_name_prefix='causa
 _MAD_NORMAL = 0.6744897501960817   # scipy's scale="normal": Phi^{-1}(3/4)
 
 
+def _host_lib():
+    """The shared library's host-side helpers (no GPU needed); ``None`` when it has not been built."""
+    try:
+        from . import _lib as L
+        return L.load(require_gpu=False), L
+    except Exception:
+        return None, None
+
+
+def _bh_rows(p):
+    """Row-wise Benjamini-Hochberg, NaN entries left out of each family: ``ca_host_bh_rows`` (one host
+    thread per row) when the library is built, else the numpy form below (same arithmetic)."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    lib, L = _host_lib()
+    if lib is None or p.ndim != 2:
+        return _bh_rows_block(p)
+    q = np.empty_like(p)
+    L.check(lib.ca_host_bh_rows(L.dptr(p), p.shape[0], p.shape[1], L.dptr(q)))
+    return q
+
+
+def _median_mad_rows(t):
+    """NaN-skipping per-row median and MAD / Phi^{-1}(3/4) (scipy's ``scale='normal'``)."""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    lib, L = _host_lib()
+    if lib is None:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            med = np.nanmedian(t, axis=1)
+            mad = np.nanmedian(np.abs(t - med[:, None]), axis=1)
+        return med, mad / _MAD_NORMAL
+    med, mad = np.empty(t.shape[0]), np.empty(t.shape[0])
+    L.check(lib.ca_host_median_mad_rows(L.dptr(t), t.shape[0], t.shape[1], L.dptr(med), L.dptr(mad)))
+    return med, mad / _MAD_NORMAL
+
+
 def _bh_rows_block(p):
-    """Row-wise Benjamini-Hochberg with NaN entries left out of each family (vectorised)."""
+    """Row-wise Benjamini-Hochberg with NaN entries left out of each family (vectorised numpy)."""
     a, m = p.shape
     order = np.argsort(p, axis=1)                      # NaNs sort last
     ps = np.take_along_axis(p, order, axis=1)
@@ -102,19 +138,13 @@ def bh_correction_multi(tvalues, df=None):
     dfa = None if df is None else np.asarray(df, dtype=np.float64)
     with np.errstate(invalid='ignore'):
         pv = np.where(keep, _tail_parallel(t, dfa), np.nan)
-        tm = np.where(keep, t, np.nan)
-        with warnings.catch_warnings():
-            warnings.simplefilter('ignore')
-            med = np.nanmedian(tm, axis=1)
-            mad = np.nanmedian(np.abs(tm - med[:, None]), axis=1) / _MAD_NORMAL
+        med, mad = _median_mad_rows(np.where(keep, t, np.nan))
         ok = mad > 0
         t_adj = (t - med[:, None]) / np.where(ok, mad, 1.0)[:, None]
         keep_adj = keep & ok[:, None]
         pva = np.where(keep_adj, _tail_parallel(t_adj, dfa), np.nan)
-        # (the row-wise sorts are many small numpy calls: fanning them out over threads only adds
-        # GIL contention -- measured slower than the vectorised form)
-        qv = _bh_rows_block(pv)
-        qva = _bh_rows_block(pva)
+        qv = _bh_rows(pv)
+        qva = _bh_rows(pva)
     return pv, qv, pva, qva
 
 

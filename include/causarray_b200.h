@@ -200,6 +200,15 @@ int ca_aipw_lfc_yhat(int n, int p, int a, const double* Y, const double* Yhat, c
                      const double* A, const double* pi, const uint8_t* cell_mask, const ca_lfc_params* prm,
                      double* mean0, double* mean1, double* tau, double* var, double* df, uint8_t* estimable);
 
+/* ---- host-side helpers of the inference tail (CPU, no device work) ------------------------------
+ * Replace the per-treatment loop around statsmodels multipletests(method='fdr_bh') and the
+ * median / MAD of the empirical-null standardisation in bh_correction
+ * (causarray/DR_inference.py:153-201).  p, q, t: (a, m) row-major host arrays, one BH family per row;
+ * NaN entries are left out of a family and come back as NaN.  mad is the raw median absolute
+ * deviation (the caller divides by Phi^{-1}(3/4)). */
+int ca_host_bh_rows(const double* p, int a, int m, double* q);
+int ca_host_median_mad_rows(const double* t, int a, int m, double* med, double* mad);
+
 /* ------------------------------------------------------------------------
  * Measurement hooks (bench.py): per-kernel-class device time from CUDA events
  * recorded on the launching stream, and the number of kernels launched so far.

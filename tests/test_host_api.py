@@ -163,3 +163,23 @@ def test_lowrank_product_svd():
     np.testing.assert_allclose((u * s) @ vt, U @ G.T, atol=1e-10)
     s_ref = np.linalg.svd(U @ G.T, compute_uv=False)[:3]
     np.testing.assert_allclose(s, s_ref, rtol=1e-10)
+
+
+def test_host_inference_helpers_match_numpy():
+    """ca_host_bh_rows / ca_host_median_mad_rows (CPU code in the shared library) against the numpy
+    forms, with NaNs, ties, an all-NaN family and an even / odd number of kept entries."""
+    from causarray_b200 import inference as inf
+    rng = np.random.default_rng(4)
+    p = rng.random((6, 501))
+    p[1, 3:40] = np.nan
+    p[2] = np.nan
+    p[3, :50] = p[3, 60]
+    p[4, ::2] = np.nan
+    q = inf._bh_rows(p)
+    np.testing.assert_array_equal(q, inf._bh_rows_block(p))
+    t = rng.standard_normal((6, 501))
+    t[1, 3:40] = np.nan
+    t[4, ::7] = np.nan
+    med, mad = inf._median_mad_rows(t)
+    np.testing.assert_allclose(med, np.nanmedian(t, axis=1), rtol=0, atol=0)
+    np.testing.assert_allclose(mad, np.nanmedian(np.abs(t - med[:, None]), axis=1) / inf._MAD_NORMAL, rtol=1e-15)
