@@ -47,6 +47,7 @@ struct GlmSolve {
   const int* genelist;   // nullptr = identity
   const double* part;
   const double* ridge;   // kx or nullptr
+  const double* l1;      // kx or nullptr: L1 weights n * alpha_k of the lasso refit (caller's column order)
   const double* nu;
   int family;
   double thres;
@@ -83,7 +84,14 @@ __global__ void k_glm_solve(GlmSolve Q) {
   bool pois = true;
   if (Q.family == CA_FAMILY_NB && Q.nu) pois = Q.nu[gene] > Q.thres;
   const double sy = Q.cst[(size_t)gene * 3 + 0], sylogy = Q.cst[(size_t)gene * 3 + 1], synu = Q.cst[(size_t)gene * 3 + 2];
-  const double dev = pois ? 2.0 * ((sylogy - s_yeta) - (sy - s_mu)) : 2.0 * ((sylogy - s_yeta) - (synu - s_log));
+  double dev = pois ? 2.0 * ((sylogy - s_yeta) - (sy - s_mu)) : 2.0 * ((sylogy - s_yeta) - (synu - s_log));
+  if (Q.l1 && !Q.finalize) {
+    // lasso refit: the convergence test runs on the penalised objective dev + 2 sum_k l1_k |beta_k|
+    // (= 2 n times statsmodels' -loglike / n + sum_k alpha_k |beta_k|, up to a constant)
+    double pen = 0.0;
+    for (int i = 0; i < kx; ++i) pen += Q.l1[i] * fabs(Q.beta[(size_t)gene * kx + i]);
+    dev += 2.0 * pen;
+  }
   if (Q.finalize) {
     if (lane == 0) Q.dev[gene] = dev;
     return;
@@ -115,10 +123,15 @@ __global__ void k_glm_solve(GlmSolve Q) {
   if (!run) return;
   // ---- normal equations ----
   const int ld = kx + 1;
-  double* L = sm + (size_t)warp * (kx * ld + 3 * kx);
+  // (the lasso refit keeps a second copy of the system; plain fits do not pay its shared memory)
+  double* L = sm + (size_t)warp * (kx * ld + 3 * kx + (Q.l1 ? kx * ld + 3 * kx : 0));
   double* sc = L + kx * ld;
   double* b = sc + kx;
   double* invd = b + kx;  // reciprocals of the Cholesky diagonal
+  double* Gc = invd + kx; // lasso refit: copy of the scaled Gram matrix (the factorisation is in place)
+  double* b0 = Gc + kx * ld;
+  double* t2 = b0 + kx;
+  double* zf = t2 + kx;   // 1.0 where the coefficient is held at zero
   {
     // fixed summation order over the splits; a lane walks the flat index e = i * kx + j in steps of
     // 32 (row / column tracked incrementally: no division) and keeps 2 x nsplit loads in flight
@@ -185,39 +198,53 @@ __global__ void k_glm_solve(GlmSolve Q) {
     const double si = sc[i];
     for (int j = 0; j <= i; ++j) L[i * ld + j] *= si * sc[j];
     b[i] *= si;
+    if (Q.l1) {
+      for (int j = 0; j <= i; ++j) Gc[i * ld + j] = L[i * ld + j];
+      b0[i] = b[i];
+    }
   }
   __syncwarp();
+  if (Q.l1) {  // mirror: the coordinate descent below reads full rows
+    for (int i = lane; i < kx; i += 32)
+      for (int j = 0; j < i; ++j) Gc[j * ld + i] = Gc[i * ld + j];
+    __syncwarp();
+  }
   // Right-looking Cholesky of the lower triangle, one matrix ROW per lane (rows lane and lane + 32):
   // the trailing update of row i is a run of FMAs over its columns with no index arithmetic (the
   // first version walked the trailing block as a flat index with a division and a modulo per
   // element and took 80 us per 26 x 26 system -- most of an IRLS tail iteration).
   // ld = kx + 1 is odd, so the row-per-lane accesses are bank-conflict free.
-  for (int j = 0; j < kx; ++j) {
-    const double djj = L[j * ld + j];
-    if (!(djj > 1e-13)) bad = true;
-    const double inv = rsqrt(djj > 1e-300 ? djj : 1e-300);
-    if (lane == 0) invd[j] = inv;
-    for (int i = lane; i < kx; i += 32)
-      if (i >= j) L[i * ld + j] *= inv;
-    __syncwarp();
-    for (int i = lane; i < kx; i += 32)
-      if (i > j) {
-        const double lij = L[i * ld + j];
-        double* Li = L + i * ld;
-        const double* Lj = L + j;
-        int c = j + 1;
-        for (; c + 3 <= i; c += 4) {  // four independent updates in flight
-          const double a0 = Lj[c * ld], a1 = Lj[(c + 1) * ld], a2 = Lj[(c + 2) * ld], a3 = Lj[(c + 3) * ld];
-          const double r0 = Li[c], r1 = Li[c + 1], r2 = Li[c + 2], r3 = Li[c + 3];
-          Li[c] = fma(-lij, a0, r0);
-          Li[c + 1] = fma(-lij, a1, r1);
-          Li[c + 2] = fma(-lij, a2, r2);
-          Li[c + 3] = fma(-lij, a3, r3);
+  auto factor = [&]() {
+    bool sing = false;
+    for (int j = 0; j < kx; ++j) {
+      const double djj = L[j * ld + j];
+      if (!(djj > 1e-13)) sing = true;
+      const double inv = rsqrt(djj > 1e-300 ? djj : 1e-300);
+      if (lane == 0) invd[j] = inv;
+      for (int i = lane; i < kx; i += 32)
+        if (i >= j) L[i * ld + j] *= inv;
+      __syncwarp();
+      for (int i = lane; i < kx; i += 32)
+        if (i > j) {
+          const double lij = L[i * ld + j];
+          double* Li = L + i * ld;
+          const double* Lj = L + j;
+          int c = j + 1;
+          for (; c + 3 <= i; c += 4) {  // four independent updates in flight
+            const double a0 = Lj[c * ld], a1 = Lj[(c + 1) * ld], a2 = Lj[(c + 2) * ld], a3 = Lj[(c + 3) * ld];
+            const double r0 = Li[c], r1 = Li[c + 1], r2 = Li[c + 2], r3 = Li[c + 3];
+            Li[c] = fma(-lij, a0, r0);
+            Li[c + 1] = fma(-lij, a1, r1);
+            Li[c + 2] = fma(-lij, a2, r2);
+            Li[c + 3] = fma(-lij, a3, r3);
+          }
+          for (; c <= i; ++c) Li[c] = fma(-lij, Lj[c * ld], Li[c]);
         }
-        for (; c <= i; ++c) Li[c] = fma(-lij, Lj[c * ld], Li[c]);
-      }
-    __syncwarp();
-  }
+      __syncwarp();
+    }
+    return sing;
+  };
+  if (factor()) bad = true;
   bad = __any_sync(0xffffffffu, bad);
   if (bad) {
     if (lane == 0) {
@@ -227,29 +254,109 @@ __global__ void k_glm_solve(GlmSolve Q) {
     }
     return;
   }
-  // column-oriented forward / backward substitution: lane i owns b[i]; the diagonal enters through
+  // column-oriented forward / backward substitution: lane i owns v[i]; the diagonal enters through
   // its stored reciprocal (after the scaled column the diagonal entry of L is djj * inv = 1 / inv)
-  for (int j = 0; j < kx; ++j) {
-    const double yj = b[j] * invd[j];
-    __syncwarp();
-    for (int i = lane; i < kx; i += 32) {
-      if (i > j)
-        b[i] = fma(-L[i * ld + j], yj, b[i]);
-      else if (i == j)
-        b[i] = yj;
+  auto substitute = [&](double* v) {
+    for (int j = 0; j < kx; ++j) {
+      const double yj = v[j] * invd[j];
+      __syncwarp();
+      for (int i = lane; i < kx; i += 32) {
+        if (i > j)
+          v[i] = fma(-L[i * ld + j], yj, v[i]);
+        else if (i == j)
+          v[i] = yj;
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  for (int j = kx - 1; j >= 0; --j) {
-    const double xj = b[j] * invd[j];
-    __syncwarp();
-    for (int i = lane; i < kx; i += 32) {
-      if (i < j)
-        b[i] = fma(-L[j * ld + i], xj, b[i]);
-      else if (i == j)
-        b[i] = xj;
+    for (int j = kx - 1; j >= 0; --j) {
+      const double xj = v[j] * invd[j];
+      __syncwarp();
+      for (int i = lane; i < kx; i += 32) {
+        if (i < j)
+          v[i] = fma(-L[j * ld + i], xj, v[i]);
+        else if (i == j)
+          v[i] = xj;
+      }
+      __syncwarp();
     }
+  };
+  substitute(b);
+  if (Q.l1) {
+    // Lasso step of the penalised IRLS (glmnet form): minimise the quadratic model
+    //   1/2 b^T G b - r^T b + sum_k l1_k |b_k|
+    // on the (scaled) kx x kx system.  Its fixed point over the IRLS iterations is the minimiser of
+    // -loglike / n + sum_k alpha_k |beta_k|, the objective of statsmodels' fit_regularized
+    // (elastic net with L1_wt = 1) that causarray/gcate_glm.py:209 falls back to.
+    // Active-set rounds: with a sign pattern s (0 = coefficient held at zero) the optimality system is
+    //   G_AA b_A = r_A - l1_A s_A,  b_Z = 0;
+    // it is solved with the rows / columns of Z replaced by the identity, then checked: an active
+    // coefficient whose sign came out wrong joins Z, a zero coefficient whose gradient exceeds its
+    // weight rejoins A.  The unpenalised solution supplies the first pattern; one or two rounds
+    // settle it.  Fallback (pattern still moving after 6 rounds): cyclic coordinate descent.
+    double sg[2] = {0.0, 0.0};   // pattern of the (up to two) coordinates this lane owns
+    for (int i = lane, q = 0; i < kx; i += 32, ++q) {
+      const double lam = Q.l1[i] * sc[i];
+      sg[q] = b[i] > 0.0 ? 1.0 : (b[i] < 0.0 ? -1.0 : 0.0);
+      if (lam == 0.0) sg[q] = 2.0;  // unpenalised coordinate: always active, no sign constraint
+    }
+    bool settled = false;
+    for (int round = 0; round < 6 && !settled; ++round) {
+      for (int i = lane, q = 0; i < kx; i += 32, ++q) {
+        const double lam = Q.l1[i] * sc[i];
+        zf[i] = sg[q] == 0.0 ? 1.0 : 0.0;
+        t2[i] = sg[q] == 0.0 ? 0.0 : b0[i] - (sg[q] == 2.0 ? 0.0 : lam * sg[q]);
+      }
+      __syncwarp();
+      for (int i = lane; i < kx; i += 32)
+        for (int j = 0; j <= i; ++j)
+          L[i * ld + j] = (zf[i] != 0.0 || zf[j] != 0.0) ? (i == j ? 1.0 : 0.0) : Gc[i * ld + j];
+      __syncwarp();
+      factor();
+      substitute(t2);
+      bool chg = false;
+      for (int i = lane, q = 0; i < kx; i += 32, ++q) {
+        const double lam = Q.l1[i] * sc[i];
+        if (sg[q] == 2.0) continue;
+        if (sg[q] != 0.0) {
+          if (!((t2[i] > 0.0 && sg[q] > 0.0) || (t2[i] < 0.0 && sg[q] < 0.0))) {
+            sg[q] = 0.0;
+            chg = true;
+          }
+        } else {
+          double gdot = 0.0;
+          for (int j = 0; j < kx; ++j) gdot += Gc[i * ld + j] * t2[j];
+          const double res = b0[i] - gdot;
+          if (fabs(res) > lam * (1.0 + 1e-12)) {
+            sg[q] = res > 0.0 ? 1.0 : -1.0;
+            chg = true;
+          }
+        }
+      }
+      settled = !__any_sync(0xffffffffu, chg);
+    }
+    for (int i = lane; i < kx; i += 32) b[i] = t2[i];
     __syncwarp();
+    if (!settled) {
+      for (int sweep = 0; sweep < 2000; ++sweep) {
+        double maxchg = 0.0, maxabs = 0.0;
+        for (int k = 0; k < kx; ++k) {
+          double part = 0.0;
+          for (int j = lane; j < kx; j += 32) part += Gc[k * ld + j] * b[j];
+          part = warp_sum(part);
+          const double gkk = Gc[k * ld + k], old = b[k];
+          const double r = b0[k] - (part - gkk * old);
+          const double lam = Q.l1[k] * sc[k];
+          const double mag = fabs(r) - lam;
+          const double nw = mag > 0.0 ? (r > 0.0 ? mag : -mag) / gkk : 0.0;
+          __syncwarp();
+          if (lane == 0) b[k] = nw;
+          __syncwarp();
+          maxchg = fmax(maxchg, fabs(nw - old));
+          maxabs = fmax(maxabs, fabs(nw));
+        }
+        if (maxchg <= 1e-11 * (1.0 + maxabs)) break;
+      }
+    }
   }
   bool fin = true;
   for (int i = lane; i < kx; i += 32) {
@@ -542,9 +649,28 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
                        status);
 }
 
+static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                        double thres_disp, int maxiter, double tol, int d_guard, const double* ridge, const double* l1,
+                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status);
+
 extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                              double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
                              const uint8_t* gene_mask, double* B, double* dev, int32_t* n_iter, int32_t* status) {
+  return glm_fit_impl(h, family, X, kx, offset, nu, thres_disp, maxiter, tol, d_guard, ridge, nullptr, gene_mask, false, B,
+                      dev, n_iter, status);
+}
+
+extern "C" int ca_glm_refit_l1(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                               double thres_disp, int maxiter, double tol, const double* l1, const uint8_t* gene_mask,
+                               double* B, double* dev, int32_t* n_iter, int32_t* status) {
+  CA_REQUIRE(l1 && gene_mask, "the lasso refit needs its weights and the gene subset");
+  return glm_fit_impl(h, family, X, kx, offset, nu, thres_disp, maxiter, tol, -1, nullptr, l1, gene_mask, true, B, dev,
+                      n_iter, status);
+}
+
+static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                        double thres_disp, int maxiter, double tol, int d_guard, const double* ridge, const double* l1,
+                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status) {
   CA_REQUIRE(h && h->Yt && X && B, "load counts first");
   CA_REQUIRE(kx > 0 && kx <= 64, "design width must be in [1, 64]");
   CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
@@ -556,7 +682,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
       h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
       h->part.alloc((size_t)p * (kxi * kxi + kxi + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
-      h->counter.alloc(2) || h->offset.alloc((size_t)n + 8) || h->nu.alloc(p) || h->ridge.alloc(kx))
+      h->counter.alloc(2) || h->offset.alloc((size_t)n + 8) || h->nu.alloc(p) || h->ridge.alloc(2 * kx))
     return -1;
   CA_REQUIRE(!gene_mask || h->fit_kx == kx, "gene_mask refit needs a previous fit of the same width");
   h->fit_kx = kx;
@@ -572,6 +698,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   if (offset) CA_CUDA(cudaMemcpyAsync(h->offset.ptr, offset, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   if (nu) CA_CUDA(cudaMemcpyAsync(h->nu.ptr, nu, sizeof(double) * p, cudaMemcpyHostToDevice, st));
   if (ridge) CA_CUDA(cudaMemcpyAsync(h->ridge.ptr, ridge, sizeof(double) * kx, cudaMemcpyHostToDevice, st));
+  if (l1) CA_CUDA(cudaMemcpyAsync(h->ridge.ptr + kx, l1, sizeof(double) * kx, cudaMemcpyHostToDevice, st));
   if (gene_mask) {
     // refit only the flagged genes; the others keep their coefficients and are frozen
     std::vector<int> st0(p);
@@ -579,7 +706,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
     CA_CUDA(cudaMemcpy(hb.data(), h->beta.ptr, sizeof(double) * (size_t)p * kx, cudaMemcpyDeviceToHost));
     for (int j = 0; j < p; ++j) {
       st0[j] = gene_mask[j] ? 0 : 1;
-      if (gene_mask[j])
+      if (gene_mask[j] && !warm)  // (a warm refit starts from the coefficients of the previous fit)
         for (int c = 0; c < kx; ++c) hb[(size_t)j * kx + c] = 0.0;
     }
     CA_CUDA(cudaMemcpy(h->beta.ptr, hb.data(), sizeof(double) * (size_t)p * kx, cudaMemcpyHostToDevice));
@@ -626,7 +753,8 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   if (h->genelist.alloc(p)) return -1;
   const int solve_warps = 4;
-  const size_t solve_sm = sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 3 * kx);
+  const size_t solve_sm =
+      sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 3 * kx + (l1 ? (size_t)kx * (kx + 1) + 3 * kx : 0));
   CA_CUDA(cudaFuncSetAttribute(k_glm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_sm));
   GlmSolve Q;
   Q.p = p;
@@ -636,6 +764,7 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
   Q.part_ld = P.part_ld;
   Q.part = h->part.ptr;
   Q.ridge = ridge ? h->ridge.ptr : nullptr;
+  Q.l1 = l1 ? h->ridge.ptr + kx : nullptr;
   Q.nu = P.nu;
   Q.family = family;
   Q.thres = thres_disp;
@@ -694,8 +823,8 @@ extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, co
     const int burst = (nrun <= 64) ? std::min(8, maxiter - it + 1) : 1;
     int nact = 0;
     for (int b = 0; b < burst; ++b) {
-      P.iter = it + b;
-      Q.iter = it + b;
+      P.iter = it + b + (warm ? 1 : 0);  // a warm refit has no "first" pass from mu0 = (y + ybar) / 2
+      Q.iter = it + b + (warm ? 1 : 0);
       CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int), st));
       if (launch_pass(P, st)) return -1;
       if (launch_solve(nrun)) return -1;

@@ -183,6 +183,24 @@ class GlmDevice:
                                        L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
         return B, dev, n_iter, status
 
+    def refit_l1(self, family, X, l1, gene_mask, offset=None, nu=None, thres_disp=100.0, maxiter=100, tol=1e-8):
+        """Lasso refit (``ca_glm_refit_l1``) of the genes flagged in ``gene_mask``, warm-started from the
+        previous fit; ``l1`` (kx,) = n * alpha_k."""
+        X = L.f64(X)
+        kx = X.shape[1]
+        off = None if offset is None else L.f64(np.ravel(offset))
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        l1 = L.f64(np.ravel(l1))
+        gm = np.ascontiguousarray(gene_mask, dtype=np.uint8)
+        B = np.zeros((self.p, kx))
+        dev = np.zeros(self.p)
+        n_iter = np.zeros(self.p, dtype=np.int32)
+        status = np.zeros(self.p, dtype=np.int32)
+        L.check(self.lib.ca_glm_refit_l1(self.h, L.FAMILY[family], L.dptr(X), kx, L.dptr(off), L.dptr(nu),
+                                         float(thres_disp), int(maxiter), float(tol), L.dptr(l1), L.u8ptr(gm),
+                                         L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
+        return B, dev, n_iter, status
+
     def resid_device_ptr(self):
         ptr = ctypes.c_void_p()
         L.check(self.lib.ca_glm_resid_device(self.h, ctypes.byref(ptr)))

@@ -12,9 +12,12 @@ approximation is an un-vendored third-party algorithm and is not imitated:
 
 Genes whose unpenalised fit trips the reference's guards (non-finite
 coefficients, |beta_cov| > 50, |beta_trt| > 10; ``gcate_glm.py:205``) are refitted
-on the device with a small ridge term (the reference falls back to a
-statsmodels lasso there, which cannot be matched); their deviance residuals
-are zero, as in the reference (``:210``).  The number of such genes is
+on the device by a lasso-penalised IRLS whose fixed point minimises
+``-loglike / n + sum_k alpha_k |beta_k|`` -- the objective of the statsmodels
+``fit_regularized(alpha=1e-4 on non-constant columns, L1_wt=1)`` call the
+reference falls back to (``:209``; statsmodels stops its coordinate descent
+at ``cnvrg_tol=1e-5``, the device solves to 1e-8 in the penalised deviance);
+their deviance residuals are zero, as in the reference (``:210``).  The number of such genes is
 reported in ``last_fit_info``.
 """
 import contextlib
@@ -65,7 +68,9 @@ class GlmFit:
 
 
 def _device_fit(dev, Xf, family, offsets, disp, thres_disp, maxiter, d_guard, alpha=1e-4, verbose=False):
-    """Unpenalised IRLS for all genes, then the ridge refit of guard failures."""
+    """Unpenalised IRLS for all genes, then the lasso refit of the genes that trip the reference's
+    coefficient guards (``causarray/gcate_glm.py:205-209``: ``fit_regularized(alpha)``, an L1
+    penalty ``alpha = 1e-4`` on every non-constant column)."""
     n = Xf.shape[0]
     fam = 'poisson' if family == 'poisson' else 'nb'
     nu = None if fam == 'poisson' else np.asarray(disp, dtype=np.float64)
@@ -74,9 +79,9 @@ def _device_fit(dev, Xf, family, offsets, disp, thres_disp, maxiter, d_guard, al
     bad = status != 0
     if bad.any():
         const = np.all(Xf == Xf[0, :], axis=0)
-        ridge = np.where(const, 0.0, alpha * n)
-        B2, dv2, it2, st2 = dev.fit(fam, Xf, offsets, nu, thres_disp=thres_disp, maxiter=50, tol=1e-8, d_guard=-1,
-                                    ridge=ridge, gene_mask=bad)
+        l1 = np.where(const, 0.0, alpha * n)
+        B2, dv2, it2, st2 = dev.refit_l1(fam, Xf, l1, bad, offset=offsets, nu=nu, thres_disp=thres_disp, maxiter=100,
+                                         tol=1e-8)
         still = bad & (st2 != 0)
         B = B2
         dv = dv2

@@ -154,6 +154,16 @@ int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* of
 int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                   double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
                   const uint8_t* gene_mask, double* B, double* dev, int32_t* n_iter, int32_t* status);
+/* Lasso refit of the genes flagged in gene_mask (p, uint8), warm-started from the coefficients of
+ * the previous fit of the same width: penalised IRLS whose fixed point minimises
+ *   -loglike(beta) / n + sum_k alpha_k |beta_k|,   l1[k] = n * alpha_k  (kx entries, caller's order),
+ * the objective of the statsmodels fit_regularized(alpha, L1_wt = 1) call the reference falls back
+ * to when a gene trips its coefficient guards (causarray/gcate_glm.py:205-209).  Each IRLS step
+ * solves its quadratic model by coordinate descent on the kx x kx normal equations.  The other
+ * genes keep their coefficients.  Outputs as ca_glm_fit (no guard is applied). */
+int ca_glm_refit_l1(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                    double thres_disp, int maxiter, double tol, const double* l1, const uint8_t* gene_mask,
+                    double* B, double* dev, int32_t* n_iter, int32_t* status);
 /* Signed deviance residuals of the last fit, (n x p). */
 int ca_glm_resid(ca_glm_t h, double* resid);
 /* Same residual matrix left on the device: *dev_ptr receives a DEVICE pointer

@@ -83,6 +83,42 @@ def test_glm_orthogonal_block_layout(fam, d_cov, r):
     np.testing.assert_allclose(out["ortho"][0][ok], B_ref[ok], rtol=1e-7, atol=1e-8)
 
 
+@pytest.mark.parametrize("fam", ["poisson", "nb"])
+def test_glm_guard_lasso_refit(fam):
+    """Genes that trip the reference's coefficient guards (a tiny-scale column forces |beta| > 50)
+    are refitted with the lasso objective of the reference's fit_regularized fallback: optimality
+    conditions of that objective and agreement with the oracle's minimiser."""
+    from causarray_b200 import glm as cglm
+    from causarray_b200.device import GlmDevice
+    rng = np.random.default_rng(8)
+    n, p = 600, 40
+    u = rng.standard_normal(n)
+    u /= np.linalg.norm(u)                          # unit-norm column like the SVD factors of the init
+    X = np.c_[np.ones(n), rng.standard_normal((n, 2)) * 0.3, u]
+    beta = np.c_[rng.uniform(0.5, 2.0, p), rng.standard_normal((p, 2)) * 0.2, rng.choice([-1, 1], p) * rng.uniform(20, 120, p)]
+    mu = np.exp(X @ beta.T)
+    nu = rng.uniform(0.5, 2.0, p)
+    Y = (rng.poisson(mu) if fam == "poisson" else rng.negative_binomial(nu[None, :], nu[None, :] / (nu[None, :] + mu))).astype(float)
+    off = rng.standard_normal(n) * 0.1
+    dev = GlmDevice(n, p)
+    dev.load_counts(Y)
+    fit = cglm._device_fit(dev, X, fam, off, nu if fam == "nb" else None, 100.0, 100, X.shape[1])
+    bad = fit.refit_mask
+    print(fam, "genes refitted", int(bad.sum()), "of", p)
+    assert bad.sum() >= 5 and (~bad).sum() >= 5
+    pen = np.r_[0.0, np.full(X.shape[1] - 1, 1e-4)]
+    for j in np.where(bad)[0]:
+        a_nb = None if fam == "poisson" else 1.0 / nu[j]
+        viol = og.lasso_kkt_violation(Y[:, j], X, off, a_nb, pen, fit.B[j])
+        assert viol <= 2e-7, (j, viol)                # 1e-4 is the penalty itself
+        b_ref, _ = og.lasso_glm(Y[:, j], X, off, a_nb, pen)
+        np.testing.assert_allclose(fit.B[j], b_ref, rtol=1e-4, atol=1e-6)   # both stop short of the exact minimiser
+    # genes that pass the guards keep the unpenalised fit
+    j = int(np.where(~bad)[0][0])
+    b_mle = og.irls(Y[:, j], X, off, None if fam == "poisson" else 1.0 / nu[j], maxiter=100)[0]
+    np.testing.assert_allclose(fit.B[j], b_mle, rtol=1e-7, atol=1e-8)
+
+
 def test_glm_golden_helpers(golden_dir):
     """MoM dispersion against the reference's own estimate_disp (golden)."""
     g = np.load(os.path.join(golden_dir, "misc.npz"))

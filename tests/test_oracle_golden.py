@@ -160,3 +160,23 @@ def test_poisson_deviance_known_answers():
     mu = np.array([[2.0, 3.0]])
     np.testing.assert_allclose(og.resid_deviance(np.zeros((1, 2)), mu, None), -np.sqrt(2 * mu))
     np.testing.assert_allclose(og.resid_deviance(mu.copy(), mu, None), 0.0, atol=1e-12)
+
+
+def test_oracle_lasso_fallback_is_the_minimiser():
+    """The restated ``fit_regularized`` fallback (lasso objective of statsmodels' elastic net):
+    optimality conditions hold at its answer and the unpenalised MLE violates them by the penalty."""
+    from oracle import glm as og
+    rng = np.random.default_rng(0)
+    n, k = 300, 5
+    X = np.c_[np.ones(n), rng.standard_normal((n, k - 2)) * 0.4, rng.standard_normal(n) * 0.02]
+    beta = np.array([1.0, 0.3, -0.2, 0.1, 25.0])
+    y = rng.poisson(np.exp(X @ beta)).astype(float)
+    pen = np.r_[0.0, np.full(k - 1, 1e-4)]
+    for a_nb in (None, 0.8):
+        b, mu = og.lasso_glm(y, X, None, a_nb, pen)
+        assert og.lasso_kkt_violation(y, X, None, a_nb, pen, b) < 1e-8
+        b_mle = og.irls(y, X, None, a_nb, maxiter=200)[0]
+        assert abs(og.lasso_kkt_violation(y, X, None, a_nb, pen, b_mle) - 1e-4) < 2e-6
+        fam = og.families.Poisson() if a_nb is None else og.families.NegativeBinomial(alpha=a_nb)
+        res = og.SMGLM(y, X, family=fam, offset=None).fit_regularized(alpha=pen, cnvrg_tol=1e-5)
+        np.testing.assert_allclose(res.params, b)
