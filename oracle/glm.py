@@ -121,10 +121,48 @@ def irls(y, X, offset=None, alpha=None, maxiter=100, tol=1e-8):
     return beta, mu, dev_prev, it, converged
 
 
+def _lasso_quadratic(G, r, pen, b_start):
+    """Minimiser of ``1/2 b^T G b - r^T b + sum_k pen_k |b_k|`` (G symmetric positive definite):
+    active-set rounds on the sign pattern (exact linear solves), cyclic coordinate descent if the
+    pattern does not settle."""
+    k = r.size
+    free = pen == 0
+    b = np.linalg.solve(G, r) if b_start is None else b_start.copy()
+    sg = np.sign(b)
+    for _ in range(10):
+        act = free | (sg != 0)
+        rhs = r - np.where(free, 0.0, pen * sg)
+        b = np.zeros(k)
+        if act.any():
+            b[act] = np.linalg.solve(G[np.ix_(act, act)], rhs[act])
+        changed = False
+        wrong = act & ~free & (np.sign(b) != sg)
+        if wrong.any():
+            sg = np.where(wrong, 0.0, sg)
+            changed = True
+        res = r - G @ b
+        wake = ~act & (np.abs(res) > pen * (1.0 + 1e-12))
+        if wake.any():
+            sg = np.where(wake, np.sign(res), sg)
+            changed = True
+        if not changed:
+            return b
+    for sweep in range(20000):
+        chg = 0.0
+        for j in range(k):
+            rj = r[j] - G[j] @ b + G[j, j] * b[j]
+            nw = np.sign(rj) * max(abs(rj) - pen[j], 0.0) / G[j, j]
+            chg = max(chg, abs(nw - b[j]))
+            b[j] = nw
+        if chg <= 1e-14 * (1.0 + np.abs(b).max()):
+            break
+    return b
+
+
 def lasso_glm(y, X, offset, alpha_nb, pen, tol=1e-12, maxiter=500):
     """Minimiser of ``-loglike(b) / n + sum_k pen_k |b_k|`` for the log-link Poisson (``alpha_nb`` None)
     or NB2 (``var = mu + alpha_nb mu^2``) GLM, by proximal IRLS: each step minimises the weighted
-    least-squares model plus the L1 term by coordinate descent on the normal equations."""
+    least-squares model plus the L1 term exactly (``_lasso_quadratic``)."""
     y = np.asarray(y, dtype=np.float64)
     X = np.asarray(X, dtype=np.float64)
     n, k = X.shape
@@ -132,24 +170,14 @@ def lasso_glm(y, X, offset, alpha_nb, pen, tol=1e-12, maxiter=500):
     off = 0.0 if offset is None else np.asarray(offset, dtype=np.float64)
     mu = (y + y.mean()) / 2.0
     eta = np.log(mu)
-    beta = np.zeros(k)
+    beta = None
     obj_prev = np.inf
     for it in range(maxiter):
         w = mu if alpha_nb is None else mu / (1.0 + alpha_nb * mu)
         z = eta + (y - mu) / mu - off
         G = X.T @ (w[:, None] * X)
         r = X.T @ (w * z)
-        b = np.linalg.solve(G, r) if it == 0 else beta.copy()
-        for sweep in range(20000):
-            chg = 0.0
-            for j in range(k):
-                rj = r[j] - G[j] @ b + G[j, j] * b[j]
-                nw = np.sign(rj) * max(abs(rj) - pen[j], 0.0) / G[j, j]
-                chg = max(chg, abs(nw - b[j]))
-                b[j] = nw
-            if chg <= 1e-14 * (1.0 + np.abs(b).max()):
-                break
-        beta = b
+        beta = _lasso_quadratic(G, r, pen, beta)
         eta = X @ beta + off
         mu = np.exp(eta)
         obj = 0.5 * np.sum(unit_deviance(y, mu, alpha_nb)) + np.sum(pen * np.abs(beta))
@@ -234,8 +262,8 @@ def fit_glm_original(Y, X, A=None, family="poisson", disp_glm=None, offset=None,
     Returns ``B (p, d[+a]), Yhat, disp_glm, offset, resid (n, p), status (p,)``
     where ``Yhat`` is ``(n, p)`` or ``(Yhat0, Yhat1)`` each ``(n, p, a)`` when
     ``impute`` is not False, and ``status[j]`` is 0 for a clean IRLS fit and 1
-    when the reference would have taken its regularised fallback (guards at
-    ``:205``) -- those genes get zeros here.
+    when the reference takes its regularised fallback (guards at ``:205``) -- those
+    genes get the lasso minimiser (``lasso_glm``) and zero residuals.
     """
     Y = np.asarray(Y, dtype=np.float64)
     X = np.asarray(X, dtype=np.float64)
@@ -267,7 +295,25 @@ def fit_glm_original(Y, X, A=None, family="poisson", disp_glm=None, offset=None,
             if (not np.all(np.isfinite(beta)) or np.any(np.abs(beta[:d]) > 50) or np.any(np.abs(beta[d:]) > 10)):
                 raise ValueError("GLM did not converge")
         except ValueError:
+            # the reference's fit_regularized fallback (gcate_glm.py:209): lasso with alpha = 1e-4 on
+            # the non-constant columns, zero deviance residuals (:210)
             status[j] = 1
+            try:
+                pen = np.where(np.all(Xf == Xf[0, :], axis=0), 0.0, 1e-4)
+                beta, mu = lasso_glm(Y[:, j], Xf, off, alpha, pen, tol=1e-10)
+                if not np.all(np.isfinite(beta)):
+                    raise ValueError("lasso fallback failed")
+            except (ValueError, np.linalg.LinAlgError):
+                continue
+            B[j] = beta
+            if impute is not False and A is not None:
+                eta0 = X @ beta[:d] + (0 if off is None else off)
+                for k in range(a):
+                    Yhat0[:, j, k] = np.exp(eta0)
+                    Yhat1[:, j, k] = np.exp(eta0 + beta[d + k])
+            else:
+                Yhat0[:, j, :] = mu[:, None]
+                Yhat1[:, j, :] = mu[:, None]
             continue
         B[j] = beta
         resid[:, j] = resid_deviance(Y[:, j], mu, alpha)

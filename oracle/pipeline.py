@@ -199,7 +199,7 @@ def lfc_cpu(Y, W, A, W_A, family, offset, usevar="unequal", disp=None, n_jobs=1,
     stats["t_glm_lfc"] = time.perf_counter() - t0
     stats["irls_gene_iters"] = stats.get("irls_gene_iters", 0) + it_sum
     t0 = time.perf_counter()
-    # status == 1 genes: guard tripped -- zero coefficients here (reference: lasso fallback)
+    # status == 1 genes: guard tripped -- lasso fallback coefficients (oracle/glm.py::lasso_glm)
     eta0 = W @ B[:, :d].T + offset[:, None]
     with np.errstate(over="ignore"):
         Yh0 = np.minimum(np.exp(eta0), 1e5)
