@@ -409,6 +409,8 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
     s.lam = nullptr;
     s.ldlam = 0;
     s.prox_lo = s.prox_hi = 0;
+    s.mv_lo = d;
+    s.mv_hi = k;
     s.alpha_row = nullptr;
     s.alpha = alpha;
     s.beta = beta;
@@ -501,6 +503,10 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       s.ldlam = a;
       s.prox_lo = d - a;
       s.prox_hi = d;
+      // columns that differ between candidates: where the direction is non-zero, plus the prox block
+      // (the soft threshold moves a coefficient even where the direction is zero)
+      s.mv_lo = pa.lam ? std::min(gc_lo, d - a) : gc_lo;
+      s.mv_hi = pa.lam ? std::max(gc_lo + gc_n, d) : gc_lo + gc_n;
       s.alpha_row = h->has_alpha_gene ? h->alpha_gene.ptr : nullptr;
       s.alpha = alpha;
       s.beta = beta;

@@ -33,6 +33,7 @@ struct SearchLaunch {
   const double* lam;    // rows x ldlam or nullptr
   int ldlam;
   int prox_lo, prox_hi;
+  int mv_lo, mv_hi;     // columns in which g can be non-zero (0, kpad when unknown)
   const double* alpha_row;
   double alpha, beta, tol;
   int max_iters;

@@ -94,6 +94,8 @@ int launch_search(const RowProblem& rp, const SearchLaunch& s, cudaStream_t st) 
   A.ldlam = s.ldlam;
   A.prox_lo = s.prox_lo;
   A.prox_hi = s.prox_hi;
+  A.mv_lo = s.mv_lo;
+  A.mv_hi = s.mv_hi;
   A.alpha_row = s.alpha_row;
   A.alpha = s.alpha;
   A.beta = s.beta;

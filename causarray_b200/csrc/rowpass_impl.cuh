@@ -71,6 +71,7 @@ struct SearchArgs {
   const double* lam;
   int ldlam;
   int prox_lo, prox_hi;
+  int mv_lo, mv_hi;         // columns the step direction can be non-zero in ([0, kpad) when unknown)
   const double* alpha_row;  // nullptr -> alpha
   double alpha, beta, tol;
   int max_iters;
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search(PassCfg P, SearchA
 // ---------------------------------------------------------------------------
 template <int KS, int MODE, int NC>
 __device__ __forceinline__ void tile_pass_multi_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
-                                                     const double* s_Xc, const Smem& S, Pipe& pipe) {
+                                                     const double* s_Xc, const Smem& S, Pipe& pipe, unsigned mv) {
   constexpr int KPAD = 4 * KS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
@@ -670,15 +671,32 @@ __device__ __forceinline__ void tile_pass_multi_mode(const PassCfg& P, const FmT
       double pa[NC][2], pb[NC][2];
 #pragma unroll
       for (int c = 0; c < NC; ++c) pa[c][0] = pa[c][1] = pb[c][0] = pb[c][1] = 0.0;
+      // k-steps whose four columns the step direction never touches (bit clear in mv) contribute
+      // the same product to every candidate: they are accumulated once (stage 2 moves only the
+      // treatment columns: 4 of the 7 k-steps at k = 26)
+      double fA0 = 0.0, fA1 = 0.0, fB0 = 0.0, fB1 = 0.0;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const double bA = bpA[ks * 4], bB = bpB[ks * 4];
+        if (!((mv >> ks) & 1u)) {  // block uniform
+          const double a = ap[ks * 4];
+          dmma884(fA0, fA1, a, bA);
+          dmma884(fB0, fB1, a, bB);
+        } else {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const double a = ap[c * 8 * KPAD + ks * 4];
-          dmma884(pa[c][0], pa[c][1], a, bA);
-          dmma884(pb[c][0], pb[c][1], a, bB);
+          for (int c = 0; c < NC; ++c) {
+            const double a = ap[c * 8 * KPAD + ks * 4];
+            dmma884(pa[c][0], pa[c][1], a, bA);
+            dmma884(pb[c][0], pb[c][1], a, bB);
+          }
         }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        pa[c][0] += fA0;
+        pa[c][1] += fA1;
+        pb[c][0] += fB0;
+        pb[c][1] += fB1;
       }
       double4 cA0 = make_double4(nu_r, inu_r, lnu_r, pois_r ? 1.0 : 0.0), cA1 = cA0, cB0 = cA0, cB1 = cA0;
       if (mode_col(MODE)) {
@@ -735,17 +753,17 @@ __device__ __forceinline__ void tile_pass_multi_mode(const PassCfg& P, const FmT
 
 template <int KS, int NC>
 __device__ __forceinline__ void tile_pass_multi(const PassCfg& P, const FmTables& FT, const int* s_rows,
-                                                const double* s_Xc, const Smem& S, Pipe& pipe) {
+                                                const double* s_Xc, const Smem& S, Pipe& pipe, unsigned mv) {
   if (P.family != CA_FAMILY_NB)
-    tile_pass_multi_mode<KS, MODE_POIS, NC>(P, FT, s_rows, s_Xc, S, pipe);
+    tile_pass_multi_mode<KS, MODE_POIS, NC>(P, FT, s_rows, s_Xc, S, pipe, mv);
   else if (P.nu_per_row && P.any_pois)
-    tile_pass_multi_mode<KS, MODE_NB_ROW, NC>(P, FT, s_rows, s_Xc, S, pipe);
+    tile_pass_multi_mode<KS, MODE_NB_ROW, NC>(P, FT, s_rows, s_Xc, S, pipe, mv);
   else if (P.nu_per_row)
-    tile_pass_multi_mode<KS, MODE_NB_ROW_F, NC>(P, FT, s_rows, s_Xc, S, pipe);
+    tile_pass_multi_mode<KS, MODE_NB_ROW_F, NC>(P, FT, s_rows, s_Xc, S, pipe, mv);
   else if (P.any_pois)
-    tile_pass_multi_mode<KS, MODE_NB_COL, NC>(P, FT, s_rows, s_Xc, S, pipe);
+    tile_pass_multi_mode<KS, MODE_NB_COL, NC>(P, FT, s_rows, s_Xc, S, pipe, mv);
   else
-    tile_pass_multi_mode<KS, MODE_NB_COL_F, NC>(P, FT, s_rows, s_Xc, S, pipe);
+    tile_pass_multi_mode<KS, MODE_NB_COL_F, NC>(P, FT, s_rows, s_Xc, S, pipe, mv);
 }
 
 #ifndef CA_SEARCH_NC
@@ -805,6 +823,9 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search_multi(PassCfg P, S
   }
   const double ncols_d = (double)P.ncols;
   const int nprox = A.prox_hi - A.prox_lo;
+  unsigned mv = 0;  // k-steps that overlap the moving columns
+  for (int ks = 0; ks < KS; ++ks)
+    if (4 * ks < A.mv_hi && 4 * ks + 4 > A.mv_lo) mv |= 1u << ks;
   int groups = 0;
   for (int j0 = 1; j0 < A.max_iters; j0 += NC) {
     ++groups;
@@ -826,7 +847,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_search_multi(PassCfg P, S
       Xc[e] = v;
     }
     __syncthreads();
-    tile_pass_multi<KS, NC>(P, FT, s_rows, Xc, S, pipe);
+    tile_pass_multi<KS, NC>(P, FT, s_rows, Xc, S, pipe, mv);
     if (tid < 8 && !s_done[tid]) {
       const int row = s_rows[tid];
       for (int c = 0; c < NC; ++c) {
