@@ -337,8 +337,8 @@ def main():
         r["launches"] = cnt
         r["traffic"] = tr["dram_bytes"] if tr else None
         if tr:
-            r["traffic_note"] = "DRAM read+write bytes of one captured launch (%s); algorithmic bytes of that launch %d" \
-                                % (tr["capture"], tr["algorithmic_bytes"])
+            r["traffic_note"] = "DRAM read+write bytes of one captured launch (%s); algorithmic bytes of that launch: %s" \
+                                % (tr["capture"], tr.get("algorithmic_bytes") or tr.get("algorithmic_note"))
         return r
 
     roofline = None
