@@ -83,6 +83,23 @@ def _validate_clip(clip):
     return lo, hi
 
 
+def _fit_logistic(lr_kw, x, y, x_te):
+    return LogisticRegression(**lr_kw).fit(x, y).predict_proba(x_te)[:, 1]
+
+
+def _ps_procs():
+    try:
+        v = int(os.environ.get('CAUSARRAY_B200_PS_PROCS', '8'))
+    except ValueError:
+        v = 8
+    # one process per GPU (torchrun): share the host cores between the ranks of the node
+    try:
+        ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))))
+    except ValueError:
+        ranks = 1
+    return max(0, min(v, max(1, (os.cpu_count() or 1) // ranks)))
+
+
 def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip=None, random_state=0,
                                verbose=False, class_weight='balanced', **kwargs):
     """Per-treatment logistic propensity scores against the shared all-zero control group.
@@ -130,7 +147,9 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
     for tr, te in folds:
         A_tr, X_tr, X_te = A[tr], X_A[tr], X_A[te]
         ctrl = np.sum(A_tr, axis=1) == 0
-        def fit_one(j):
+
+        def task(j):
+            """Inputs of treatment j's fit, or the constant prediction of a degenerate design."""
             elig = mask[tr, j] if mask is not None else (ctrl | (A_tr[:, j] == 1))
             y = A_tr[elig, j]
             if y.size == 0 or np.unique(y).size != 2:
@@ -139,17 +158,32 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
             x = X_tr[elig]
             if np.all(np.ptp(x, axis=0) == 0):
                 if class_weight == 'balanced':
-                    return 0.5
+                    return None, 0.5
                 if isinstance(class_weight, dict):
                     sw = np.asarray([class_weight.get(int(v), 1.0) for v in y])
-                    return np.average(y, weights=sw)
-                return np.mean(y)
-            return LogisticRegression(**lr_kw).fit(x, y).predict_proba(X_te)[:, 1]
+                    return None, np.average(y, weights=sw)
+                return None, np.mean(y)
+            return (x, y), None
 
-        # the per-treatment fits are independent (shared controls, own cases): fan them out over host
-        # threads; results are collected in treatment order
+        # The per-treatment fits are independent (shared controls, own cases).  sklearn's lbfgs path is
+        # Python-bound (150 ms for 15 treatments of a 4 000-cell batch, 56 ms over threads because of
+        # the GIL), so with four or more treatments they go to joblib's reusable worker processes
+        # (22 ms once the workers are up; CAUSARRAY_B200_PS_PROCS=0 keeps them in this process).
         n_trt = A.shape[1]
-        fits = list(_PS_FIT_POOL.map(fit_one, range(n_trt))) if n_trt > 2 else [fit_one(j) for j in range(n_trt)]
+        tasks = [task(j) for j in range(n_trt)]
+        todo = [j for j in range(n_trt) if tasks[j][0] is not None]
+        fits = [t[1] for t in tasks]
+        n_procs = _ps_procs()
+        if len(todo) >= 4 and n_procs > 1:
+            from joblib import Parallel, delayed
+            res = Parallel(n_jobs=n_procs, backend='loky')(
+                delayed(_fit_logistic)(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo)
+        elif len(todo) > 2:
+            res = list(_PS_FIT_POOL.map(lambda j: _fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te), todo))
+        else:
+            res = [_fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo]
+        for j, r in zip(todo, res):
+            fits[j] = r
         for j in range(n_trt):
             pi_hat[te, j] = fits[j]
     if clip is not None:
