@@ -31,6 +31,7 @@
 #include "kernels.h"
 #include "glm_state.h"
 #include "prof.h"
+#include "fastmath.cuh"
 
 namespace ca {
 
@@ -56,19 +57,21 @@ struct DrArgs {
   double* mean0; double* mean1; double* tau; double* var; double* df; uint8_t* estimable;  // a x p
   // explicit-Yhat variant
   const double* Yhat;  // n x p x a x 2 or nullptr
+  const double* fm_tables;
 };
 
 // PASS 0: sums of psi0 / psi1.  PASS 1: centred second moments -> outputs.
 template <int PASS>
 __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
   extern __shared__ __align__(16) double smem[];
-  double* Rs = smem;  // 2 * DR_CHUNK * ldr
+  double* Rs = smem;  // 2 * DR_CHUNK * ldr, then the exp / log tables
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const FmTables FT = fm_load_tables(smem + 2 * DR_CHUNK * D.ldr, D.fm_tables);
   const int gene = blockIdx.x * DR_WARPS + warp;
   const bool ok_gene = gene < D.p;
   const int ldr = D.ldr, kw = D.kw;
   const double* bcov = D.Bcov ? D.Bcov + (size_t)(ok_gene ? gene : 0) * kw : nullptr;
-  double ej[JT], t0[JT], t1[JT], shift[JT];
+  double ej[JT], t0[JT], t1[JT], shift[JT];  // in pass 1, t0 / t1 hold the RECIPROCALS of tau_0 / tau_1
 #pragma unroll
   for (int j = 0; j < JT; ++j) {
     ej[j] = 1.0;
@@ -82,9 +85,11 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
         const double m0 = D.S[((size_t)jj * D.p + gene) * 2 + 0] / N;
         const double m1 = D.S[((size_t)jj * D.p + gene) * 2 + 1] / N;
         const bool est = isfinite(m0) && isfinite(m1) && m0 > 0.0 && m1 > 0.0;
-        t0[j] = est ? fmax(m0, D.thres_diff) : 1.0;
-        t1[j] = est ? fmax(m1, D.thres_diff) : 1.0;
-        shift[j] = m1 / t1[j] - m0 / t0[j];
+        const double tt0 = est ? fmax(m0, D.thres_diff) : 1.0;
+        const double tt1 = est ? fmax(m1, D.thres_diff) : 1.0;
+        shift[j] = m1 / tt1 - m0 / tt0;
+        t0[j] = 1.0 / tt0;   // the per-cell influence values are scaled by multiplication
+        t1[j] = 1.0 / tt1;
       }
     }
   }
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
         if (!D.Yhat) {
           double eta = rec[kw];
           for (int q = 0; q < kw; ++q) eta = fma(rec[q], bcov[q], eta);
-          yh0_raw = exp(eta);
+          // table-driven exp (fastmath.cuh); anything beyond the clamp is cut by the cap below
+          yh0_raw = fm_exp(eta < 700.0 ? (eta > -700.0 ? eta : -700.0) : 700.0, FT.exp_t);
         }
 #pragma unroll
         for (int j = 0; j < JT; ++j) {
@@ -132,8 +138,9 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
             yh0 = fmin(D.Yhat[base], D.cap);
             yh1 = fmin(D.Yhat[base + 1], D.cap);
           } else {
-            yh0 = fmin(yh0_raw, D.cap);
-            yh1 = fmin(yh0_raw * ej[j], D.cap);
+            const double r1 = yh0_raw * ej[j];
+            yh0 = yh0_raw < D.cap ? yh0_raw : D.cap;
+            yh1 = r1 < D.cap ? r1 : D.cap;
           }
           // w0 = (1-A)/(1-pi)/sf, w1 = A/pi/sf, isf = 1/sf
           const double psi0 = w0 * (y - yh0) + yh0 * isf;
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
             acc0[j] += psi0;
             acc1[j] += psi1;
           } else {
-            const double dlt = psi1 / t1[j] - psi0 / t0[j] - shift[j];
+            const double dlt = fma(psi1, t1[j], -fma(psi0, t0[j], shift[j]));
             if (w1 != 0.0) {  // A == 1 arm
               acc2[j] += dlt;
               acc3[j] += dlt * dlt;
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
         const double m0 = D.S[((size_t)jj * D.p + gene) * 2 + 0] / N;
         const double m1 = D.S[((size_t)jj * D.p + gene) * 2 + 1] / N;
         const bool est = isfinite(m0) && isfinite(m1) && m0 > 0.0 && m1 > 0.0;
-        double tau = log(t1[j] / t0[j]);
+        double tau = log(t0[j] / t1[j]);   // (reciprocals: tau_1 / tau_0)
         double var, dfe = NAN;
         if (D.usevar == 1) {
           const double var0 = (s1 - s0 * s0 / n0) / (n0 - 1.0);
@@ -293,7 +300,9 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
   D.df = d_out.ptr + (size_t)4 * a * p;
   D.estimable = d_est.ptr;
   D.Yhat = Yhat_dev;
-  const size_t sm = sizeof(double) * 2 * DR_CHUNK * ldr;
+  D.fm_tables = fastmath_tables();
+  CA_REQUIRE(D.fm_tables, "fastmath tables unavailable");
+  const size_t sm = sizeof(double) * (2 * DR_CHUNK * ldr + FM_TABLE_DOUBLES);
   CA_CUDA(cudaFuncSetAttribute(k_aipw<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   CA_CUDA(cudaFuncSetAttribute(k_aipw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   const int grid = (p + DR_WARPS - 1) / DR_WARPS;
