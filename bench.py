@@ -20,9 +20,16 @@ import argparse
 import json
 import os
 
-# keep stdout to the single JSON line: a box-level NCCL_DEBUG=VERSION makes NCCL print its banner there
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION",):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# Keep stdout to the single JSON line: NCCL prints its version banner there and libraries may log.
+# Everything written to fd 1 while the benchmark runs goes to stderr; the JSON line is written to the
+# saved descriptor at the end (emit_json).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_json(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 import subprocess
 import sys
 import threading
@@ -166,7 +173,7 @@ def run_reference(args, rank, world):
                             "sample": sample},
            "e2e": {"value": value, "unit": "cell*gene updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "phases_s": {k: round(v, 3) for k, v in stats.items() if k.startswith("t_")}}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def main():
@@ -379,7 +386,7 @@ def main():
                       "C/OpenMP alternating iteration (%d threads) + per-gene numpy IRLS over %d processes"
                       % (n, w["r"], w["n_perts"], args.cpu_genes, w["p"], cport.threads(), cores),
             "phases_s": {k: round(v, 3) for k, v in st.items() if k.startswith("t_")}}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -92,12 +92,11 @@ def _ps_procs():
         v = int(os.environ.get('CAUSARRAY_B200_PS_PROCS', '8'))
     except ValueError:
         v = 8
-    # one process per GPU (torchrun): share the host cores between the ranks of the node
-    try:
-        ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1'))))
-    except ValueError:
-        ranks = 1
-    return max(0, min(v, max(1, (os.cpu_count() or 1) // ranks)))
+    # one process per GPU (torchrun): the ranks of a node share the host cores; leave one core of the
+    # share to the main thread, which is inside the outcome GLM while the workers fit
+    from .inference import _cores_per_rank
+    share = _cores_per_rank()
+    return max(0, min(v, share if share >= (os.cpu_count() or 1) else max(1, share - 2)))
 
 
 def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip=None, random_state=0,

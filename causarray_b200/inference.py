@@ -47,7 +47,16 @@ def bh_correction(tvalues_init, df=None):
 
 import concurrent.futures as _cf
 import os as _os
-_N_THREADS = max(1, min(16, (_os.cpu_count() or 1)))
+def _cores_per_rank():
+    """Host cores this process may use: all of them, or its share when torchrun runs one process per GPU."""
+    try:
+        ranks = max(1, int(_os.environ.get('LOCAL_WORLD_SIZE', _os.environ.get('WORLD_SIZE', '1'))))
+    except ValueError:
+        ranks = 1
+    return max(1, (_os.cpu_count() or 1) // ranks)
+
+
+_N_THREADS = max(1, min(16, _cores_per_rank()))
 _POOL = _cf.ThreadPoolExecutor(max_workers=_N_THREADS, thread_name_prefix='causarray_inf')
 _MAD_NORMAL = 0.6744897501960817   # scipy's scale="normal": Phi^{-1}(3/4)
 
