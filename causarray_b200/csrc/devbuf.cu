@@ -1,6 +1,10 @@
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
 #include "../../include/causarray_b200.h"
 #include "devbuf.h"
 
@@ -81,3 +85,58 @@ extern "C" int ca_release_cached(void) {
   ca::pool_release_all();
   return 0;
 }
+
+namespace ca {
+
+namespace {
+constexpr size_t STAGE_CHUNK = 32u << 20;
+struct Staging {
+  void* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  bool used[2] = {false, false};
+  bool ok = false;
+  std::mutex mu;
+};
+Staging g_stage;
+}  // namespace
+
+int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes < (16u << 20) || getenv("CA_NO_STAGED_H2D")) {
+    CA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  if (!g_stage.ok) {
+    for (int b = 0; b < 2; ++b) {
+      CA_CUDA(cudaHostAlloc(&g_stage.buf[b], STAGE_CHUNK, cudaHostAllocDefault));
+      CA_CUDA(cudaEventCreateWithFlags(&g_stage.ev[b], cudaEventDisableTiming));
+    }
+    g_stage.ok = true;
+  }
+  const int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  int i = 0;
+  for (size_t off = 0; off < bytes; off += STAGE_CHUNK, ++i) {
+    const int b = i & 1;
+    const size_t len = std::min(STAGE_CHUNK, bytes - off);
+    if (g_stage.used[b]) CA_CUDA(cudaEventSynchronize(g_stage.ev[b]));  // the previous upload from this buffer
+    char* pin = static_cast<char*>(g_stage.buf[b]);
+    const size_t piece = (len / nt + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (int w = 1; w < nt; ++w) {
+      const size_t lo = (size_t)w * piece;
+      if (lo >= len) break;
+      const size_t n = std::min(piece, len - lo);
+      th.emplace_back([=]() { memcpy(pin + lo, s + off + lo, n); });
+    }
+    memcpy(pin, s + off, std::min(piece, len));
+    for (auto& t : th) t.join();
+    CA_CUDA(cudaMemcpyAsync(d + off, pin, len, cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaEventRecord(g_stage.ev[b], st));
+    g_stage.used[b] = true;
+  }
+  return 0;
+}
+
+}  // namespace ca

@@ -173,7 +173,7 @@ extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_
   CA_REQUIRE(h && Y, "null argument");
   const int n = h->n, p = h->p;
   if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
-  CA_CUDA(cudaMemcpyAsync(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  if (h2d_staged(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, h->st)) return -1;
   CA_CUDA(cudaMemsetAsync(h->Yraw_t.ptr, 0, h->Yraw_t.bytes(), h->st));
   if (launch_transpose(h->Yraw.ptr, n, p, p, h->Yraw_t.ptr, h->ldn, h->st)) return -1;
   h->raw_loaded = true;
@@ -234,11 +234,11 @@ extern "C" int ca_gcate_load_normalized(ca_gcate_t h, const double* Yn, const do
   const int n = h->n, p = h->p;
   DevBuf<double> tmp, ys;
   if (tmp.alloc((size_t)n * p)) return -1;
-  CA_CUDA(cudaMemcpyAsync(tmp.ptr, Yn, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  if (h2d_staged(tmp.ptr, Yn, sizeof(double) * (size_t)n * p, h->st)) return -1;
   if (launch_normalize_transpose(tmp.ptr, n, p, p, nullptr, h->Yn.ptr, h->ldp, h->Ynt.ptr, h->ldn, h->st)) return -1;
   if (Ys) {
     if (ys.alloc((size_t)n * p)) return -1;
-    CA_CUDA(cudaMemcpyAsync(ys.ptr, Ys, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+    if (h2d_staged(ys.ptr, Ys, sizeof(double) * (size_t)n * p, h->st)) return -1;
   }
   return finish_load(h, nu, Ys ? ys.ptr : nullptr);
 }

@@ -624,7 +624,7 @@ extern "C" int ca_glm_load_counts(ca_glm_t h, const double* Y) {
   CA_REQUIRE(h && Y, "null argument");
   const int n = h->n, p = h->p;
   if (h->Yraw_own.alloc((size_t)n * p) || h->Yt_own.alloc((size_t)p * h->ldn)) return -1;
-  CA_CUDA(cudaMemcpyAsync(h->Yraw_own.ptr, Y, sizeof(double) * (size_t)n * p, cudaMemcpyHostToDevice, h->st));
+  if (h2d_staged(h->Yraw_own.ptr, Y, sizeof(double) * (size_t)n * p, h->st)) return -1;
   CA_CUDA(cudaMemsetAsync(h->Yt_own.ptr, 0, h->Yt_own.bytes(), h->st));
   if (launch_transpose(h->Yraw_own.ptr, n, p, p, h->Yt_own.ptr, h->ldn, h->st)) return -1;
   CA_CUDA(cudaStreamSynchronize(h->st));
