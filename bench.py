@@ -23,12 +23,25 @@ import os
 # Keep stdout to the single JSON line: NCCL prints its version banner there and libraries may log.
 # Everything written to fd 1 while the benchmark runs goes to stderr; the JSON line is written to the
 # saved descriptor at the end (emit_json).
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Called by main(): from here on fd 1 is stderr; emit_json writes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit_json(obj):
-    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 import subprocess
 import sys
@@ -186,6 +199,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--genes", type=int, default=None, help="override p (debug only; makes the number invalid)")
     args = ap.parse_args()
+    capture_stdout()
     warnings.simplefilter("ignore")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
