@@ -188,8 +188,11 @@ def estimate_r(Y, X, A, r_max, c=1., family='nb', disp_glm=None, disp_family='po
     nu = (d + a) * np.maximum(n, p) * np.log(n * p / np.maximum(n, p)) / (n * p)
     rows.append([0, ll, nu, ll + c * nu])
     for r in r_list[r_list > 0][::-1]:
+        # The reference passes ``A=A1[:, :d+a+r]`` here, but ``estimate`` drops a stray ``A=`` keyword
+        # (causarray/gcate.py:176-178), so every r starts from its own GLM + SVD initialisation; the
+        # same happens here (no ``A_init``) -- a warm start would lower the deviances of r < r_max.
         _, res_2 = estimate(Y, X, int(r), a, 0, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2, kwargs_es_2,
-                            A_init=A1[:, :d + a + r], **{k_: v for k_, v in kwargs.items() if k_ != 'A'})
+                            **{k_: v for k_, v in kwargs.items() if k_ != 'A'})
         res_2.pop('_ws').close()
         A1, A2 = res_2['X_U'], res_2['B_Gamma']
         ll = 2 * (_nll_raw(A1, A2) / p - logh_sum / (n * p))

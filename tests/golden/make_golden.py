@@ -238,9 +238,55 @@ def golden_pipeline(ca, family, seed, tag):
     print("pipeline", tag, "iters", res1["n_iter"], res2["n_iter"], "sig", int(np.nansum(df["padj"] < 0.05)))
 
 
+def golden_estimate_r(ca, seed):
+    """JIC sweep (causarray/gcate.py:196-325) through the REAL reference orchestration."""
+    import causarray.gcate_glm as gg
+    import scipy.sparse.linalg as sla
+    import causarray.gcate_opt as go
+    import causarray.gcate as gc
+    sim = simulate_screen(n_ctrl=140, n_perts=2, cells_per_pert=40, p=110, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.0, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    disp = sim["disp"]
+    orig = sla.svds
+
+    def svds_det(M, k, **kw):
+        v0 = np.ones(min(M.shape)) / np.sqrt(min(M.shape))
+        u, s, vt = orig(M, k=k, v0=v0, tol=1e-14)
+        for i in range(k):
+            j = np.argmax(np.abs(u[:, i]))
+            if u[j, i] < 0:
+                u[:, i] *= -1
+                vt[i] *= -1
+        return u, s, vt
+    go.svds = svds_det
+    go.sp.sparse.linalg.svds = svds_det
+    if hasattr(gc, "svds"):
+        gc.svds = svds_det
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    try:
+        with gg._backend_override("original"):
+            df = ca.estimate_r(Y.copy(), X, A, 3, family="nb", disp_glm=disp.copy(),
+                               kwargs_es_1=dict(max_iters=30), kwargs_es_2=dict(max_iters=30))
+    finally:
+        go.svds = orig
+        go.sp.sparse.linalg.svds = orig
+        if hasattr(gc, "svds"):
+            gc.svds = orig
+        gg.Parallel = n_jobs_patch
+    out = dict(Y=Y, X=X, A=A, disp=disp, r=df["r"].to_numpy().astype(np.float64),
+               deviance=df["deviance"].to_numpy().astype(np.float64), nu=df["nu"].to_numpy().astype(np.float64),
+               JIC=df["JIC"].to_numpy().astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "estimate_r.npz"), **out)
+    print("estimate_r", df.to_string())
+
+
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r"]
+    if "estimate_r" in which:
+        golden_estimate_r(ca, 41)
     if "kernels" in which:
         golden_kernels(ca, "nb", 11, "nb")
         golden_kernels(ca, "poisson", 12, "poisson")
