@@ -282,11 +282,55 @@ def golden_estimate_r(ca, seed):
     print("estimate_r", df.to_string())
 
 
+def golden_batch(ca, seed):
+    """gcate_lfc_batch (causarray/DR_learner.py:584-866) through the REAL reference: control
+    subsampling, per-batch fits (dispersion estimated once, up front), result frame."""
+    import causarray.gcate_glm as gg
+    import scipy.sparse.linalg as sla
+    import causarray.gcate_opt as go
+    sim = simulate_screen(n_ctrl=160, n_perts=4, cells_per_pert=35, p=100, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.0, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    orig = sla.svds
+
+    def svds_det(M, k, **kw):
+        v0 = np.ones(min(M.shape)) / np.sqrt(min(M.shape))
+        u, s, vt = orig(M, k=k, v0=v0, tol=1e-14)
+        for i in range(k):
+            j = np.argmax(np.abs(u[:, i]))
+            if u[j, i] < 0:
+                u[:, i] *= -1
+                vt[i] *= -1
+        return u, s, vt
+    go.svds = svds_det
+    go.sp.sparse.linalg.svds = svds_det
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    kw = dict(batch_size=2, max_cells=2000, n_ctrl=120, family="nb",
+              gcate_kwargs=dict(disp_glm=sim["disp"].copy(), kwargs_es_1=dict(max_iters=20), kwargs_es_2=dict(max_iters=20)),
+              lfc_kwargs=dict(usevar="unequal", disp_glm=sim["disp"].copy()), random_state=0)
+    try:
+        with gg._backend_override("original"):
+            df = ca.gcate_lfc_batch(Y.copy(), X, A, 2, **kw)
+    finally:
+        go.svds = orig
+        go.sp.sparse.linalg.svds = orig
+        gg.Parallel = n_jobs_patch
+    out = dict(Y=Y, X=X, A=A, disp=sim["disp"], columns=np.array(list(df.columns)))
+    for c in df.columns:
+        v = df[c].to_numpy()
+        out["df_" + c] = v.astype(str) if v.dtype == object else v.astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "batch.npz"), **out)
+    print("batch", df.shape, list(df.columns), "sig", int(np.nansum(df["padj"] < 0.05)))
+
+
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
+    if "batch" in which:
+        golden_batch(ca, 51)
     if "kernels" in which:
         golden_kernels(ca, "nb", 11, "nb")
         golden_kernels(ca, "poisson", 12, "poisson")
