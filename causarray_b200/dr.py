@@ -255,12 +255,20 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
             Y_hat = np.zeros((n, Yn.shape[1], A.shape[1], 2))
             for tr, te in folds:
                 pg = dict(params_glm)
-                off_te = None
                 if isinstance(pg.get('offset'), np.ndarray):
-                    off_te = pg['offset'][te]
                     pg['offset'] = pg['offset'][tr]
-                B = _glm_mod.fit_glm(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True, **pg)[0]
-                Y_hat[te] = YhatFactors(X[te], B[:, :d], B[:, d:], off_te, cap=np.inf).materialize()
+                B, _, _, off_tr, _ = _glm_mod.fit_glm(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True,
+                                                      **pg)
+                # Reference behaviour, kept for identical results: ``fit_glm(..., impute=X_test)`` rebuilds
+                # its prediction design from the TRAINING rows (``X_test = np.c_[X, zeros]`` overwrites the
+                # ``impute`` array, causarray/gcate_glm.py:160-165) and predicts with the training offsets,
+                # so the (n_train, p, a) imputations of the training cells are what
+                # ``cross_fitting`` writes into the test rows (DR_estimation.py:612-613) -- which only
+                # broadcasts when both folds have the same size (K = 2, even n).
+                if len(tr) != len(te):
+                    raise ValueError('could not broadcast input array from shape (%d,%d,%d) into shape (%d,%d,%d)'
+                                     % (len(tr), Yn.shape[1], A.shape[1], len(te), Yn.shape[1], A.shape[1]))
+                Y_hat[te] = YhatFactors(X[tr], B[:, :d], B[:, d:], off_tr, cap=np.inf).materialize()
             Y_hat = np.clip(Y_hat, None, 1e5)
         else:
             with phase('lfc_outcome_glm'):

@@ -282,6 +282,32 @@ def golden_estimate_r(ca, seed):
     print("estimate_r", df.to_string())
 
 
+def golden_lfc_fit(ca, seed, tag, cross_est):
+    """LFC with its own nuisance fits (outcome GLM + logistic propensities) through the REAL
+    reference, in-sample (K = 1) or cross-fitted (K = 2)."""
+    import causarray.gcate_glm as gg
+    sim = simulate_screen(n_ctrl=120, n_perts=2, cells_per_pert=40, p=70, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.5, base_hi=2.5)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    W = np.c_[Xc, sim["U"]]
+    sf = ca.comp_size_factor(Y)
+    off = np.log(sf)
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    try:
+        with gg._backend_override("original"):
+            df, est = ca.LFC(Y.copy(), W, Atr, W_A=W, family="nb", offset=off, disp_glm=sim["disp"].copy(),
+                             cross_est=cross_est, usevar="unequal", backend="original")
+    finally:
+        gg.Parallel = n_jobs_patch
+    out = dict(Y=Y, W=W, A=Atr, offset=off, disp=sim["disp"], pi_hat=est["pi_hat"], columns=np.array(list(df.columns)),
+               estimable=df["estimable"].to_numpy().astype(np.uint8))
+    for c in ["tau", "std", "stat", "pvalue", "padj", "mean_control", "mean_treated"]:
+        out["df_" + c] = df[c].to_numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "lfc_fit_%s.npz" % tag), **out)
+    print("lfc_fit", tag, "sig", int(np.nansum(df["padj"] < 0.05)), "filtered", int(np.isinf(df["std"]).sum()))
+
+
 def golden_batch(ca, seed):
     """gcate_lfc_batch (causarray/DR_learner.py:584-866) through the REAL reference: control
     subsampling, per-batch fits (dispersion estimated once, up front), result frame."""
@@ -326,11 +352,14 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
         golden_batch(ca, 51)
+    if "lfc_fit" in which:
+        golden_lfc_fit(ca, 61, "k1", False)
+        golden_lfc_fit(ca, 62, "k2", True)
     if "kernels" in which:
         golden_kernels(ca, "nb", 11, "nb")
         golden_kernels(ca, "poisson", 12, "poisson")
