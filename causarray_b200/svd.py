@@ -35,7 +35,7 @@ def fix_signs(u, vt=None):
 def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, tol=1e-11, seed=0):
     """Top-``r`` singular triplets of the (n, p) float64 matrix at device pointer ``ptr``.
 
-    Returns host arrays ``u (n, r)``, ``s (r,)`` (descending), ``vt (r, p)``.
+    Returns host arrays ``u (n, r)``, ``s (r,)`` (ascending, as ``svds``), ``vt (r, p)``.
     """
     import torch
     if not torch.cuda.is_available():
@@ -83,9 +83,11 @@ def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, t
     if out is None:        # Gram factorisation broke down (rank-deficient block): Householder QR
         out = iterate(orth_qr)
     Ub, S, Vr = out
-    u = Ub[:, :r].cpu().numpy().copy()
-    s = S[:r].cpu().numpy().copy()
-    vt = Vr.T.cpu().numpy().copy()
+    # scipy's svds returns the k triplets in ASCENDING order of the singular values; the latent
+    # columns of X_U / B_Gamma inherit that order, so it is kept for identical outputs
+    u = Ub[:, :r].cpu().numpy()[:, ::-1].copy()
+    s = S[:r].cpu().numpy()[::-1].copy()
+    vt = Vr.T.cpu().numpy()[::-1].copy()
     u, vt = fix_signs(u, vt)
     return u, s, vt
 
@@ -95,12 +97,13 @@ def lowrank_product_svd(U, G):
 
     Replaces ``svds(E, k=r)`` of ``causarray/gcate_opt.py:330-331`` without
     forming ``E``: thin QR of both factors and an r x r SVD.
-    Returns ``u (n, r)``, ``s (r,)`` descending, ``vt (r, p)``.
+    Returns ``u (n, r)``, ``s (r,)`` ascending, ``vt (r, p)``.
     """
     Qa, Ra = np.linalg.qr(U)
     Qb, Rb = np.linalg.qr(G)
     uu, s, vvt = np.linalg.svd(Ra @ Rb.T)
-    u = Qa @ uu
-    vt = vvt @ Qb.T
+    u = (Qa @ uu)[:, ::-1].copy()        # ascending singular values, as svds returns them
+    vt = (vvt @ Qb.T)[::-1].copy()
+    s = s[::-1].copy()
     u, vt = fix_signs(u, vt)
     return u, s, vt

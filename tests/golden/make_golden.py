@@ -308,6 +308,57 @@ def golden_lfc_fit(ca, seed, tag, cross_est):
     print("lfc_fit", tag, "sig", int(np.nansum(df["padj"] < 0.05)), "filtered", int(np.isinf(df["std"]).sum()))
 
 
+def golden_more(ca, seed):
+    """fit_gcate_batch with pert-cell subsampling and the warm start of U across batches, and
+    fit_glm with its own dispersion estimate and imputation, through the REAL reference."""
+    import causarray.gcate_glm as gg
+    import scipy.sparse.linalg as sla
+    import causarray.gcate_opt as go
+    sim = simulate_screen(n_ctrl=150, n_perts=4, cells_per_pert=40, p=90, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.0, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    orig = sla.svds
+
+    def svds_det(M, k, **kw):
+        v0 = np.ones(min(M.shape)) / np.sqrt(min(M.shape))
+        u, s, vt = orig(M, k=k, v0=v0, tol=1e-14)
+        for i in range(k):
+            j = np.argmax(np.abs(u[:, i]))
+            if u[j, i] < 0:
+                u[:, i] *= -1
+                vt[i] *= -1
+        return u, s, vt
+    go.svds = svds_det
+    go.sp.sparse.linalg.svds = svds_det
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    out = dict(Y=Y, X=X, A=A, disp=sim["disp"])
+    try:
+        with gg._backend_override("original"):
+            res = ca.fit_gcate_batch(Y.copy(), X, A, 2, batch_size=2, max_cells=60, n_ctrl=100, family="nb",
+                                     disp_glm=sim["disp"].copy(), warm_start_U=True, random_state=3,
+                                     kwargs_es_1=dict(max_iters=15), kwargs_es_2=dict(max_iters=15))
+            out["n_batches"] = len(res)
+            for i, b in enumerate(res):
+                out["b%d_cell_idx" % i] = np.asarray(b["cell_idx"])
+                out["b%d_ctrl_idx" % i] = np.asarray(b["ctrl_idx"])
+                out["b%d_pert_idx" % i] = np.asarray(b["pert_idx"])
+                out["b%d_X_U" % i] = b["res_2"]["X_U"]
+                out["b%d_B_Gamma" % i] = b["res_2"]["B_Gamma"]
+                out["b%d_hist1" % i] = np.array(b["res_1"]["hist"])
+                out["b%d_hist2" % i] = np.array(b["res_2"]["hist"])
+            B, Yhat, disp, offsets, resid = ca.fit_glm(Y.copy(), X, A, family="nb", disp_glm=None, offset=True,
+                                                       impute=True, maxiter=100)
+            out.update(glm_B=B, glm_Yhat0=Yhat[0], glm_Yhat1=Yhat[1], glm_disp=disp, glm_offsets=offsets,
+                       glm_resid=resid)
+    finally:
+        go.svds = orig
+        go.sp.sparse.linalg.svds = orig
+        gg.Parallel = n_jobs_patch
+    np.savez_compressed(os.path.join(HERE, "more.npz"), **out)
+    print("more: batches", len(res), [len(b["cell_idx"]) for b in res], "glm B", B.shape)
+
+
 def golden_batch(ca, seed):
     """gcate_lfc_batch (causarray/DR_learner.py:584-866) through the REAL reference: control
     subsampling, per-batch fits (dispersion estimated once, up front), result frame."""
@@ -352,11 +403,13 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
         golden_batch(ca, 51)
+    if "more" in which:
+        golden_more(ca, 71)
     if "lfc_fit" in which:
         golden_lfc_fit(ca, 61, "k1", False)
         golden_lfc_fit(ca, 62, "k2", True)

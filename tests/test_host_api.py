@@ -161,7 +161,7 @@ def test_lowrank_product_svd():
     U, G = rng.standard_normal((30, 3)), rng.standard_normal((40, 3))
     u, s, vt = lowrank_product_svd(U, G)
     np.testing.assert_allclose((u * s) @ vt, U @ G.T, atol=1e-10)
-    s_ref = np.linalg.svd(U @ G.T, compute_uv=False)[:3]
+    s_ref = np.linalg.svd(U @ G.T, compute_uv=False)[:3][::-1]     # ascending, the order scipy's svds returns
     np.testing.assert_allclose(s, s_ref, rtol=1e-10)
 
 
