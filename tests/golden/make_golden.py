@@ -359,6 +359,41 @@ def golden_more(ca, seed):
     print("more: batches", len(res), [len(b["cell_idx"]) for b in res], "glm B", B.shape)
 
 
+def golden_lfc_options(ca, seed):
+    """LFC option variants through the REAL reference: pooled variance with a cell mask and
+    unclipped propensities (NB, dispersion estimated inside), and the Poisson family."""
+    import causarray.gcate_glm as gg
+    sim = simulate_screen(n_ctrl=130, n_perts=3, cells_per_pert=30, p=60, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.5, base_hi=2.5)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    rng = np.random.default_rng(seed)
+    W = np.c_[Xc, sim["U"]]
+    n = Y.shape[0]
+    ctrl = Atr.sum(1) == 0
+    mask = np.zeros(Atr.shape, dtype=bool)
+    for j in range(Atr.shape[1]):
+        mask[:, j] = (Atr[:, j] == 1) | (ctrl & (rng.random(n) < 0.7))
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    out = dict(Y=Y, W=W, A=Atr, mask=mask)
+    try:
+        with gg._backend_override("original"):
+            df1, est1 = ca.LFC(Y.copy(), W, Atr, W_A=W, family="nb", offset=True, mask=mask.copy(), usevar="pooled",
+                               ps_clip=None, thres_min=0.05, thres_diff=0.02, backend="original")
+            df2, est2 = ca.LFC(Y.copy(), W, Atr, W_A=W, family="poisson", offset=True, usevar="unequal",
+                               backend="original")
+    finally:
+        gg.Parallel = n_jobs_patch
+    for tag, df, est in (("v1", df1, est1), ("v2", df2, est2)):
+        out[tag + "_pi_hat"] = est["pi_hat"]
+        out[tag + "_estimable"] = df["estimable"].to_numpy().astype(np.uint8)
+        for c in ["tau", "std", "stat", "pvalue", "padj", "mean_control", "mean_treated"]:
+            out[tag + "_" + c] = df[c].to_numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "lfc_options.npz"), **out)
+    print("lfc_options sig", int(np.nansum(df1["padj"] < 0.05)), int(np.nansum(df2["padj"] < 0.05)),
+          "filtered", int(np.isinf(df1["std"]).sum()), int(np.isinf(df2["std"]).sum()))
+
+
 def golden_batch(ca, seed):
     """gcate_lfc_batch (causarray/DR_learner.py:584-866) through the REAL reference: control
     subsampling, per-batch fits (dispersion estimated once, up front), result frame."""
@@ -403,11 +438,13 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
         golden_batch(ca, 51)
+    if "lfc_options" in which:
+        golden_lfc_options(ca, 81)
     if "more" in which:
         golden_more(ca, 71)
     if "lfc_fit" in which:
