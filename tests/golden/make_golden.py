@@ -394,6 +394,49 @@ def golden_lfc_options(ca, seed):
           "filtered", int(np.isinf(df1["std"]).sum()), int(np.isinf(df2["std"]).sum()))
 
 
+def golden_gcate_options(ca, seed):
+    """fit_gcate with non-default options through the REAL reference: no offset, explicit c1,
+    non-default line-search and early-stopping settings.  (The dispersion is passed in: with
+    ``disp_glm=None`` and the statsmodels backend the reference's ``estimate_disp_auto`` falls off its
+    end and every gene gets nu = 1 -- a documented deviation)"""
+    import causarray.gcate_glm as gg
+    import scipy.sparse.linalg as sla
+    import causarray.gcate_opt as go
+    sim = simulate_screen(n_ctrl=120, n_perts=2, cells_per_pert=45, p=80, r=3, d_cov=2, family="nb", seed=seed,
+                          base_lo=0.0, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    orig = sla.svds
+
+    def svds_det(M, k, **kw):
+        v0 = np.ones(min(M.shape)) / np.sqrt(min(M.shape))
+        u, s, vt = orig(M, k=k, v0=v0, tol=1e-14)
+        for i in range(k):
+            j = np.argmax(np.abs(u[:, i]))
+            if u[j, i] < 0:
+                u[:, i] *= -1
+                vt[i] *= -1
+        return u, s, vt
+    go.svds = svds_det
+    go.sp.sparse.linalg.svds = svds_det
+    n_jobs_patch = gg.Parallel
+    gg.Parallel = lambda n_jobs=None: (lambda gen: [f(*a, **k) for f, a, k in gen])
+    kw = dict(family="nb", disp_glm=sim["disp"].copy(), offset=False, c1=0.2,
+              kwargs_ls_1=dict(alpha=0.05, beta=0.6, tol=1e-3), kwargs_ls_2=dict(alpha=0.2, max_iters=15),
+              kwargs_es_1=dict(max_iters=25, patience=3, rel_tol=1e-5), kwargs_es_2=dict(max_iters=12, tolerance=1e-6))
+    try:
+        with gg._backend_override("original"):
+            res1, res2 = ca.fit_gcate(Y.copy(), X, A, 3, **kw)
+    finally:
+        go.svds = orig
+        go.sp.sparse.linalg.svds = orig
+        gg.Parallel = n_jobs_patch
+    out = dict(Y=Y, X=X, A=A, s1_A=res1["X_U"], s1_B=res1["B_Gamma"], s1_hist=np.array(res1["hist"]),
+               s2_A=res2["X_U"], s2_B=res2["B_Gamma"], s2_hist=np.array(res2["hist"]),
+               disp=np.ravel(res2["kwargs_glm"]["disp_glm"]), size_factor=np.ravel(res2["kwargs_glm"]["size_factor"]))
+    np.savez_compressed(os.path.join(HERE, "gcate_options.npz"), **out)
+    print("gcate_options iters", res1["n_iter"], res2["n_iter"], len(res1["hist"]), len(res2["hist"]))
+
+
 def golden_batch(ca, seed):
     """gcate_lfc_batch (causarray/DR_learner.py:584-866) through the REAL reference: control
     subsampling, per-batch fits (dispersion estimated once, up front), result frame."""
@@ -438,11 +481,13 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options", "gcate_options"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
         golden_batch(ca, 51)
+    if "gcate_options" in which:
+        golden_gcate_options(ca, 91)
     if "lfc_options" in which:
         golden_lfc_options(ca, 81)
     if "more" in which:
