@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <vector>
 #include <new>
 
@@ -706,7 +707,12 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
     CA_CUDA(cudaMemcpy(hb.data(), h->beta.ptr, sizeof(double) * (size_t)p * kx, cudaMemcpyDeviceToHost));
     for (int j = 0; j < p; ++j) {
       st0[j] = gene_mask[j] ? 0 : 1;
-      if (gene_mask[j] && !warm)  // (a warm refit starts from the coefficients of the previous fit)
+      if (!gene_mask[j]) continue;
+      // a warm refit starts from the coefficients of the previous fit -- unless that fit broke down
+      // numerically, in which case the gene starts from zero like a cold fit
+      bool reset = !warm;
+      for (int c = 0; c < kx && !reset; ++c) reset = !std::isfinite(hb[(size_t)j * kx + c]);
+      if (reset)
         for (int c = 0; c < kx; ++c) hb[(size_t)j * kx + c] = 0.0;
     }
     CA_CUDA(cudaMemcpy(h->beta.ptr, hb.data(), sizeof(double) * (size_t)p * kx, cudaMemcpyHostToDevice));
