@@ -174,3 +174,34 @@ def test_aipw_single_cell_arm_gives_nan_variance():
     out = aipw_lfc(Y, W, Bcov, Btrt, np.zeros(n), np.ones(n), A, pi, usevar="unequal")
     assert (np.isnan(out["var"][0]) | np.isinf(out["var"][0])).all()      # NaN, or inf where the expression filter applies
     assert np.isfinite(out["var"][1]).mean() > 0.8      # (the low-expression / small-difference filter sets inf)
+
+
+def test_fit_gcate_input_validation():
+    """_check_input (causarray/gcate.py:8-51): non-integer counts are rounded with a warning, an
+    all-zero gene and a near-singular covariate matrix raise the reference's ValueErrors."""
+    import warnings
+    import causarray_b200 as cb
+    from causarray_b200.synth import simulate_screen
+    sim = simulate_screen(n_ctrl=80, n_perts=2, cells_per_pert=20, p=40, r=1, seed=2, base_lo=0.5, base_hi=2.0)
+    Y, X, A = sim["Y"], sim["X"], sim["A"]
+    kw = dict(family="nb", disp_glm=sim["disp"], kwargs_es_1=dict(max_iters=3), kwargs_es_2=dict(max_iters=3))
+    Yz = Y.copy()
+    Yz[:, 5] = 0.0
+    with pytest.raises(ValueError, match="non-expressed"):
+        cb.fit_gcate(Yz, X, A, 1, **kw)
+    Xs = np.c_[X, X[:, 0] * (1 + 1e-9)]
+    with pytest.raises(ValueError, match="near singular"):
+        cb.fit_gcate(Y.copy(), Xs, A, 1, **kw)
+    with pytest.raises(ValueError, match="ndim"):
+        cb.fit_gcate(Y[:, 0], X, A, 1, **kw)
+    Yf = Y + 0.3
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        r1, r2 = cb.fit_gcate(Yf, X, A, 1, **kw)
+    assert any("not integer-valued" in str(w.message) for w in rec)
+    r2.pop("_ws").close()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        q1, q2 = cb.fit_gcate(np.round(Yf), X, A, 1, **kw)
+    q2.pop("_ws").close()
+    np.testing.assert_array_equal(r2["B_Gamma"], q2["B_Gamma"])
