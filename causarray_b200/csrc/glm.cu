@@ -11,8 +11,8 @@
 // deviance residuals (statsmodels resid_deviance / nb_glm_fast.py:729-777).
 //
 // One warp owns one gene.  The shared design X streams through shared memory in
-// chunks of 128 cells (cp.async, double buffered) and is reused by the 8 genes
-// of the CTA.  Per 32 cells a lane evaluates eta/mu/w/z for ONE cell, then the
+// chunks of 128 cells (bulk async copies on mbarriers, double buffered; glm_pass_impl.cuh)
+// and is reused by the 8 genes of the CTA.  Per 32 cells a lane evaluates eta/mu/w/z for ONE cell, then the
 // weighted Gram  X^T diag(w) X  is accumulated on the FP64 tensor cores: for a
 // 4-cell step the fragment X[cell = lane%4][col = lane/4 + 8t] is the B
 // operand as is and, multiplied by w[cell], the A operand (DMMA m8n8k4); only

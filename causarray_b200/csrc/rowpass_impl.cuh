@@ -9,9 +9,10 @@
 //                   accumulates the row sums and -- in the gradient variant -- feeds
 //                   d ell/d theta straight back into a second DMMA that contracts it with
 //                   M (the gradient block).  Theta is never written to memory.
-//   K2  line search: one CTA owns a tile of 8 rows and walks the backtracking candidates
-//                   t = alpha * beta^j sequentially (the accept / fallback rule of
-//                   causarray/gcate_opt.py:30-82), one row pass per candidate.
+//   K2  line search: two phases (k_search: first candidate t = alpha for every row of a tile;
+//                   k_search_multi: the remaining candidates t = alpha * beta^j of the rows that
+//                   failed it, four per pass over the data); the accept / stop / fallback rule
+//                   of causarray/gcate_opt.py:30-82 is replayed over the objectives in order.
 //
 // Replaces: nll / grad (causarray/gcate_likelihood.py:46-142) and line_search as driven
 // from update_with_mask (causarray/gcate_opt.py:168-175, 182-200).
@@ -36,9 +37,6 @@ constexpr int NTHREADS = NWARPS * 32;
 #endif
 #ifndef CA_TC
 #define CA_TC 128
-#endif
-#ifndef CA_ABL
-#define CA_ABL 0
 #endif
 #ifndef CA_NACC
 #define CA_NACC 2
@@ -258,8 +256,8 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
 // sum_col dl * M[col, gc_lo + c].
 //
 // Per iteration a warp handles TWO 8x8 tiles (t and t + 8): four independent per-entry
-// dependency chains per lane and 2 x NACC independent DMMA accumulators, because both the
-// FP64 pipe (~8-10 cycles) and DMMA (~250 cycles) are latency bound with one chain per warp.
+// dependency chains per lane and 2 x NACC independent DMMA accumulators (measured latencies:
+// DFMA 8 cycles, DMMA 26 cycles, one DMMA per 16 cycles per SM sub-partition).
 template <int KS, bool GRAD, int NGT, int MODE>
 __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
                                                const double* s_X, const Smem& S, int gc_lo, Pipe& pipe) {
