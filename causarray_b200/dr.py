@@ -580,10 +580,12 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
     the outcome GLM and the AIPW reduction.
     """
     from .estimators import _dense_counts
+    import scipy.sparse as _sp
     gcate_kwargs = {} if gcate_kwargs is None else gcate_kwargs
     lfc_kwargs = {} if lfc_kwargs is None else lfc_kwargs
     gene_names = list(Y.columns) if isinstance(Y, pd.DataFrame) else None
-    Y_np = _dense_counts(Y)
+    sparse_in = _sp.issparse(Y)      # kept sparse: one batch of rows is densified at a time
+    Y_np = Y.tocsr() if sparse_in else _dense_counts(Y)
     X_np = np.asarray(X)
     W_A_np = np.asarray(W_A) if W_A is not None else None
     if isinstance(A, pd.DataFrame):
@@ -640,7 +642,7 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
         ws = res_2.pop('_ws', None)
         U_b = res_2['U'].copy()
         off_b = np.log(res_2['kwargs_glm']['size_factor'])
-        Y_b_np = Y_np[cell_idx]
+        Y_b_np = np.asarray(Y_np[cell_idx].toarray(), dtype=np.float64) if sparse_in else Y_np[cell_idx]
         Y_b = pd.DataFrame(Y_b_np, columns=gene_names) if gene_names is not None else Y_b_np
         X_b = X_np[cell_idx]
         cols = [col_of[name] for name in br['pert_names']]

@@ -238,7 +238,14 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
                        random_state=0, verbose=False, **kwargs):
     """Generator behind :func:`fit_gcate_batch`: yields one batch dict at a time with the
     device workspace still attached as ``res_2['_ws']`` (the caller closes it)."""
-    Y_np = _dense_counts(Y)
+    # A sparse count matrix stays sparse: only the rows of one batch (and of the control subsample)
+    # are densified at a time, so host memory is bounded by a batch (reference: _maybe_densify on
+    # the batch slice, causarray/gcate.py:451-470)
+    sparse_in = _sp.issparse(Y)
+    Y_np = Y.tocsr() if sparse_in else _dense_counts(Y)
+
+    def rows(idx):
+        return np.asarray(Y_np[idx].toarray(), dtype=np.float64) if sparse_in else Y_np[idx]
     X_np = np.asarray(X)
     if isinstance(A, pd.DataFrame):
         names = list(A.columns)
@@ -258,12 +265,12 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
     ctrl_sel = subsample_ctrl_cells(np.where(A_np.sum(axis=1) == 0)[0], n_ctrl=n_ctrl, random_state=random_state)
     if family == 'nb' and disp_glm is None:
         if offset is True:
-            off_c = np.log(comp_size_factor(Y_np[ctrl_sel]))
+            off_c = np.log(comp_size_factor(rows(ctrl_sel)))
         elif offset is not None and offset is not False:
             off_c = np.asarray(offset)[ctrl_sel]
         else:
             off_c = None
-        disp_glm = _glm_mod.estimate_disp_auto(Y_np[ctrl_sel], X_np[ctrl_sel], offset=off_c)
+        disp_glm = _glm_mod.estimate_disp_auto(rows(ctrl_sel), X_np[ctrl_sel], offset=off_c)
     if n_batches is None:
         n_batches = math.ceil(a_total / batch_size)
     n_batches = max(1, min(n_batches, a_total))
@@ -283,7 +290,7 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
         pert_sel = pert_idx if max_cells is None else subsample_pert_cells(
             pert_idx, max_cells=max_cells, random_state=random_state + batch_i)
         cell_idx = np.sort(np.concatenate([ctrl_sel, pert_sel]))
-        Y_b, X_b = Y_np[cell_idx], X_np[cell_idx]
+        Y_b, X_b = rows(cell_idx), X_np[cell_idx]
         A_b = A_np[cell_idx][:, cols]
         kw = dict(kwargs)
         kw['disp_glm'] = disp_glm
