@@ -67,6 +67,7 @@ _SIGNATURES = {
     "ca_gcate_destroy": [_P],
     "ca_gcate_load_counts": [_P, _D, _D, _D],
     "ca_gcate_upload_counts": [_P, _D] + [ctypes.POINTER(ctypes.c_int64)] * 3,
+    "ca_gcate_upload_counts_csr": [_P, ctypes.POINTER(ctypes.c_int64), _I32, _D, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_size_factor_medians": [_P, _D],
     "ca_gcate_prepare": [_P, _D, _D],
     "ca_gcate_load_normalized": [_P, _D, _D, _D],

@@ -415,6 +415,27 @@ int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi,
 // ---------------------------------------------------------------------------
 namespace ca {
 
+// CSR rows -> dense row-major counts (the destination is zero-filled by the caller); one warp per
+// row, entries with a column index outside [0, p) are ignored
+__global__ void k_csr_expand(const long long* __restrict__ indptr, const int* __restrict__ indices,
+                             const double* __restrict__ data, int n, int p, double* __restrict__ Y) {
+  const int row = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const long long lo = indptr[row], hi = indptr[row + 1];
+  for (long long e = lo + lane; e < hi; e += 32) {
+    const int c = indices[e];
+    if (c >= 0 && c < p) Y[(size_t)row * p + c] = data[e];
+  }
+}
+int launch_csr_expand(const long long* indptr, const int* indices, const double* data, int n, int p, double* Y,
+                      cudaStream_t st) {
+  if (n <= 0) return 0;
+  const long threads = (long)n * 32;
+  k_csr_expand<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(indptr, indices, data, n, p, Y);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
 // flags[0] += #non-integer entries (np.allclose(Y, trunc(Y)) tolerance), flags[1] += #non-finite
 __global__ void k_check_counts(const double* __restrict__ Y, long total, unsigned long long* flags) {
   unsigned long long nonint = 0, nonfin = 0;

@@ -168,12 +168,9 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
   return 0;
 }
 
-extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
-                                      int64_t* n_empty_genes) {
-  CA_REQUIRE(h && Y, "null argument");
+// common tail of the two upload entry points: gene-major copy, input checks
+static int finish_upload(ca_gcate* h, int64_t* n_nonint, int64_t* n_nonfinite, int64_t* n_empty_genes) {
   const int n = h->n, p = h->p;
-  if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
-  if (h2d_staged(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, h->st)) return -1;
   CA_CUDA(cudaMemsetAsync(h->Yraw_t.ptr, 0, h->Yraw_t.bytes(), h->st));
   if (launch_transpose(h->Yraw.ptr, n, p, p, h->Yraw_t.ptr, h->ldn, h->st)) return -1;
   h->raw_loaded = true;
@@ -194,6 +191,40 @@ extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_
     if (n_nonfinite) *n_nonfinite = (int64_t)hf[1];
     if (n_empty_genes) *n_empty_genes = empty;
   }
+  return 0;
+}
+
+extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
+                                      int64_t* n_empty_genes) {
+  CA_REQUIRE(h && Y, "null argument");
+  const int n = h->n, p = h->p;
+  if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
+  if (h2d_staged(h->Yraw.ptr, Y, sizeof(double) * (size_t)n * p, h->st)) return -1;
+  return finish_upload(h, n_nonint, n_nonfinite, n_empty_genes);
+}
+
+extern "C" int ca_gcate_upload_counts_csr(ca_gcate_t h, const int64_t* indptr, const int32_t* indices, const double* data,
+                                          int64_t nnz, int64_t* n_nonint, int64_t* n_nonfinite,
+                                          int64_t* n_empty_genes) {
+  CA_REQUIRE(h && indptr && (nnz == 0 || (indices && data)) && nnz >= 0, "null argument");
+  const int n = h->n, p = h->p;
+  CA_REQUIRE(indptr[0] == 0 && indptr[n] == nnz, "indptr does not describe n rows with nnz entries");
+  if (h->Yraw.alloc((size_t)n * p) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
+  DevBuf<long long> d_ptr;
+  DevBuf<int> d_idx;
+  DevBuf<double> d_val;
+  if (d_ptr.alloc((size_t)n + 1) || d_idx.alloc((size_t)std::max<int64_t>(nnz, 1)) ||
+      d_val.alloc((size_t)std::max<int64_t>(nnz, 1)))
+    return -1;
+  CA_CUDA(cudaMemcpyAsync(d_ptr.ptr, indptr, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->st));
+  if (nnz > 0) {
+    if (h2d_staged(d_idx.ptr, indices, sizeof(int) * (size_t)nnz, h->st)) return -1;
+    if (h2d_staged(d_val.ptr, data, sizeof(double) * (size_t)nnz, h->st)) return -1;
+  }
+  CA_CUDA(cudaMemsetAsync(h->Yraw.ptr, 0, h->Yraw.bytes(), h->st));
+  if (launch_csr_expand(d_ptr.ptr, d_idx.ptr, d_val.ptr, n, p, h->Yraw.ptr, h->st)) return -1;
+  if (int rc = finish_upload(h, n_nonint, n_nonfinite, n_empty_genes)) return rc;
+  CA_CUDA(cudaStreamSynchronize(h->st));  // the CSR staging buffers go out of scope
   return 0;
 }
 

@@ -95,6 +95,8 @@ struct PrepArgs {
 };
 int launch_prep_search(const PrepArgs& a, cudaStream_t st);
 
+int launch_csr_expand(const long long* indptr, const int* indices, const double* data, int n, int p, double* Y,
+                      cudaStream_t st);
 int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream_t st);
 int launch_compact_by_key(const uint8_t* mask, const int* key, int n, int* list, int* count, cudaStream_t st);
 // clip X[:, lo:hi) to [-bound, bound]; rows where something changed are appended to list/count

@@ -38,12 +38,26 @@ class GcateDevice:
         L.check(self.lib.ca_gcate_load_counts(self.h, L.dptr(Y), L.dptr(sf), L.dptr(nu)))
 
     def upload_counts(self, Y, check=True):
-        """H2D of the raw counts; returns (#non-integer entries, #non-finite, #all-zero genes)."""
-        Y = L.f64(Y)
-        assert Y.shape == (self.n, self.p)
+        """H2D of the raw counts (dense array, or a scipy.sparse matrix uploaded as CSR and expanded
+        on the device); returns (#non-integer entries, #non-finite, #all-zero genes)."""
         c = [ctypes.c_int64(0) for _ in range(3)]
         refs = [ctypes.byref(x) for x in c] if check else [None, None, None]
-        L.check(self.lib.ca_gcate_upload_counts(self.h, L.dptr(Y), *refs))
+        if hasattr(Y, "tocsr"):
+            csr = Y.tocsr()
+            if not csr.has_canonical_format:
+                csr = csr.copy()
+                csr.sum_duplicates()
+            assert csr.shape == (self.n, self.p)
+            indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+            data = np.ascontiguousarray(csr.data, dtype=np.float64)
+            L.check(self.lib.ca_gcate_upload_counts_csr(
+                self.h, indptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), L.i32ptr(indices), L.dptr(data),
+                int(data.size), *refs))
+        else:
+            Y = L.f64(Y)
+            assert Y.shape == (self.n, self.p)
+            L.check(self.lib.ca_gcate_upload_counts(self.h, L.dptr(Y), *refs))
         return tuple(int(x.value) for x in c)
 
     def size_factors(self):

@@ -335,10 +335,16 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         Y = Y.values
     else:
         gene_names = range(Y.shape[1])
-    Y = np.asarray(Y).astype(float, copy=False)
+    if hasattr(Y, "tocsr"):
+        # sparse counts: with the device copy at hand (_glm) and in-sample nuisance fits nothing on the
+        # host needs the dense form; otherwise densify like the reference does
+        if _glm is None or K != 1 or Y_hat is not None:
+            Y = np.asarray(Y.toarray(), dtype=float)
+    else:
+        Y = np.asarray(Y).astype(float, copy=False)
     n, p = Y.shape
     # (_trusted: the counts were already validated on the device when the workspace was uploaded)
-    if not _trusted and not np.all(np.isfinite(Y)):
+    if not _trusted and not np.all(np.isfinite(Y.data if hasattr(Y, "tocsr") else Y)):
         raise ValueError('Y must contain only finite values')
     if len(A.shape) == 1:
         A = A.reshape(-1, 1)
@@ -642,8 +648,8 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
         ws = res_2.pop('_ws', None)
         U_b = res_2['U'].copy()
         off_b = np.log(res_2['kwargs_glm']['size_factor'])
-        Y_b_np = np.asarray(Y_np[cell_idx].toarray(), dtype=np.float64) if sparse_in else Y_np[cell_idx]
-        Y_b = pd.DataFrame(Y_b_np, columns=gene_names) if gene_names is not None else Y_b_np
+        Y_b_np = Y_np[cell_idx]            # (a sparse slice stays sparse: the counts are on the device already)
+        Y_b = pd.DataFrame(Y_b_np, columns=gene_names) if (gene_names is not None and not sparse_in) else Y_b_np
         X_b = X_np[cell_idx]
         cols = [col_of[name] for name in br['pert_names']]
         A_b = A_np[np.ix_(cell_idx, cols)]

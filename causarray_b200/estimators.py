@@ -43,7 +43,7 @@ def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0,
     n_nonint, n_nonfin, n_empty = ws.checks
     if n_nonint > 0 or n_nonfin > 0:
         warnings.warn("Y is not integer-valued. It will be rounded to the nearest integer.")
-        Y = np.round(Y)
+        Y = np.round(Y.toarray() if _sp.issparse(Y) else Y)
         ws.gcate.upload_counts(Y, check=False)
     if n_empty > 0:
         raise ValueError("Y contains non-expressed features.")
@@ -110,8 +110,8 @@ def fit_gcate(Y, X, A, r, family='nb', disp_glm=None, disp_family=None, offset=T
     ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
     with ctx:
         with phase('gcate_upload_checks_sizefactors'):
-            Y, kwargs_glm, lam1, ws = _check_input(np.asarray(Y), X, family, disp_glm, disp_family, offset, c1,
-                                                   _ws=_ws, r=int(r), **kwargs)
+            Y, kwargs_glm, lam1, ws = _check_input(Y if _sp.issparse(Y) else np.asarray(Y), X, family, disp_glm,
+                                                   disp_family, offset, c1, _ws=_ws, r=int(r), **kwargs)
         res_1, res_2 = estimate(Y, X, int(r), a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2,
                                 kwargs_es_2, A_init=A_init, _ws=ws, **kwargs)
     return res_1, res_2
@@ -244,8 +244,10 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
     sparse_in = _sp.issparse(Y)
     Y_np = Y.tocsr() if sparse_in else _dense_counts(Y)
 
-    def rows(idx):
-        return np.asarray(Y_np[idx].toarray(), dtype=np.float64) if sparse_in else Y_np[idx]
+    def rows(idx, dense=True):
+        if not sparse_in:
+            return Y_np[idx]
+        return np.asarray(Y_np[idx].toarray(), dtype=np.float64) if dense else Y_np[idx]
     X_np = np.asarray(X)
     if isinstance(A, pd.DataFrame):
         names = list(A.columns)
@@ -290,7 +292,8 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
         pert_sel = pert_idx if max_cells is None else subsample_pert_cells(
             pert_idx, max_cells=max_cells, random_state=random_state + batch_i)
         cell_idx = np.sort(np.concatenate([ctrl_sel, pert_sel]))
-        Y_b, X_b = rows(cell_idx), X_np[cell_idx]
+        # (a sparse batch slice goes to the device as CSR; nothing on the host needs its dense form)
+        Y_b, X_b = rows(cell_idx, dense=False), X_np[cell_idx]
         A_b = A_np[cell_idx][:, cols]
         kw = dict(kwargs)
         kw['disp_glm'] = disp_glm

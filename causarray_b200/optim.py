@@ -116,7 +116,8 @@ class BatchWorkspace:
     """
 
     def __init__(self, Y, size_factor, disp, family, d, r, thres_disp=100., _defer=False):
-        Y = np.asarray(Y, dtype=np.float64)
+        if not hasattr(Y, "tocsr"):          # a scipy.sparse matrix is uploaded as CSR
+            Y = np.asarray(Y, dtype=np.float64)
         n, p = Y.shape
         self.n, self.p = n, p
         self.gcate = GcateDevice(n, p, d, r, family, thres_disp)
@@ -152,7 +153,8 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     kwargs_glm, kwargs_ls, kwargs_es, total_gene_updates, total_cell_updates,
     X_U, B_Gamma, U``.
     """
-    Y = np.asarray(Y)
+    if not hasattr(Y, "tocsr"):              # (sparse counts live on the device only: _ws holds them)
+        Y = np.asarray(Y)
     n, p = Y.shape
     d = X.shape[1]
     assert d > 0

@@ -59,6 +59,12 @@ int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_facto
  *   prepare: normalisation by the size factors + constant-term sums. */
 int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
                            int64_t* n_empty_genes);
+/* Same from a CSR matrix of the counts (scipy.sparse layout: indptr n+1 int64, indices nnz int32,
+ * data nnz double, no duplicate entries): only nnz * 12 bytes cross the bus, the dense copy is
+ * expanded on the device.  Replaces the host-side densification of a batch slice
+ * (_maybe_densify, causarray/nb_glm_fast.py:68-84; causarray/gcate.py:451-470). */
+int ca_gcate_upload_counts_csr(ca_gcate_t h, const int64_t* indptr, const int32_t* indices, const double* data,
+                               int64_t nnz, int64_t* n_nonint, int64_t* n_nonfinite, int64_t* n_empty_genes);
 int ca_gcate_size_factor_medians(ca_gcate_t h, double* log_sf);
 int ca_gcate_prepare(ca_gcate_t h, const double* size_factor, const double* nu);
 /* Same, for callers of update_with_mask that already hold the normalised Y
