@@ -84,6 +84,7 @@ def _validate_clip(clip):
 
 
 _TP_CONTROLLER = None
+_PS_STATE = {'procs_failed': False}
 
 
 def _fit_logistic(lr_kw, x, y, x_te):
@@ -187,10 +188,21 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
         todo = [j for j in range(n_trt) if tasks[j][0] is not None]
         fits = [t[1] for t in tasks]
         n_procs = _ps_procs()
-        if len(todo) >= 4 and n_procs > 1:
-            from joblib import Parallel, delayed
-            res = Parallel(n_jobs=n_procs, backend='loky')(
-                delayed(_fit_logistic)(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo)
+        res = None
+        if len(todo) >= 4 and n_procs > 1 and not _PS_STATE['procs_failed']:
+            try:
+                from joblib import Parallel, delayed
+                res = Parallel(n_jobs=n_procs, backend='loky')(
+                    delayed(_fit_logistic)(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo)
+            except ValueError:
+                raise
+            except Exception as exc:       # worker processes unavailable (sandbox, /dev/shm ...): threads
+                _PS_STATE['procs_failed'] = True
+                warnings.warn(f'propensity fits: worker processes unavailable ({exc!r}); using threads',
+                              RuntimeWarning, stacklevel=2)
+                res = None
+        if res is not None:
+            pass
         elif len(todo) > 2:
             res = list(_PS_FIT_POOL.map(lambda j: _fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te), todo))
         else:
