@@ -65,6 +65,8 @@ _SIGNATURES = {
     "ca_release_cached": [],
     "ca_gcate_create": [ctypes.POINTER(_P), _c_int, _c_int, _c_int, _c_int, _c_int, _c_double],
     "ca_gcate_destroy": [_P],
+    "ca_comm_unique_id": [_U8],
+    "ca_gcate_set_shard": [_P, _c_int, _c_int, ctypes.c_int64, _U8],
     "ca_gcate_load_counts": [_P, _D, _D, _D],
     "ca_gcate_upload_counts": [_P, _D] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_upload_counts_csr": [_P, ctypes.POINTER(ctypes.c_int64), _I32, _D, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int64)] * 3,

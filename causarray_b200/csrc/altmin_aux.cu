@@ -211,6 +211,77 @@ int launch_prep_search(const PrepArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// ---- gene-sharded cell line search (multi-GPU): candidates and decisions as separate steps ----
+// With the genes split over ranks a cell's objective is a sum over ranks, so the walk of
+// causarray/gcate_opt.py:60-82 becomes: build the candidate rows, evaluate the local partial
+// log-likelihoods with the ordinary row pass, all-reduce them, decide per row.  Cells have no prox
+// term (lam = 0, gcate_opt.py:173) and a common initial step.
+__global__ void k_ls_candidates(LsShard a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = *a.count;
+  if (idx >= total) return;
+  const int row = a.rowlist[idx];
+  const double t = a.round == 0 ? a.alpha : a.t[row];
+  if (a.round == 0) {
+    a.t[row] = t;
+    a.ne[row] = 0;
+  }
+  const double* x0 = a.X + (size_t)row * a.kpad;
+  const double* g = a.g + (size_t)row * a.kpad;
+  double* xc = a.Xc + (size_t)row * a.kpad;
+  for (int c = 0; c < a.kpad; ++c) xc[c] = x0[c] - t * g[c];
+}
+__global__ void k_ls_decide(LsShard a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = *a.count;
+  if (idx >= total) return;
+  const int row = a.rowlist[idx];
+  const double ell = a.ell[row];                       // reduced over the ranks
+  const double f1 = -(ell + a.tys[row]) / a.ncols_total;
+  const double t = a.t[row];
+  a.ne[row] += 1;
+  if (a.round == 0) {
+    a.f01[row] = f1;
+    a.e01[row] = ell;
+  }
+  bool done = false, fallback = false;
+  double efin = ell;
+  if (f1 < a.f0[row] - a.tol * t * a.normg[row]) {
+    done = true;
+  } else if (t < 1e-4 || a.round == a.max_iters - 1) {
+    done = true;
+    if (a.f01[row] < 1.1 * f1) {
+      fallback = true;
+      efin = a.e01[row];
+    }
+  }
+  if (done) {
+    double* x = a.X + (size_t)row * a.kpad;
+    const double* g = a.g + (size_t)row * a.kpad;
+    const double* xc = a.Xc + (size_t)row * a.kpad;
+    for (int c = 0; c < a.kpad; ++c) x[c] = fallback ? x[c] - a.alpha * g[c] : xc[c];
+    a.ell_fin[row] = efin;
+    a.pend[row] = 0;
+    atomicAdd(a.eval_total, (unsigned long long)a.ne[row]);
+  } else {
+    a.t[row] = t * a.beta;
+    a.pend[row] = 1;
+    atomicAdd(a.n_pending, 1);
+  }
+}
+int launch_ls_candidates(const LsShard& a, int nrows, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  k_ls_candidates<<<(nrows + 127) / 128, 128, 0, st>>>(a);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+int launch_ls_decide(const LsShard& a, int nrows, cudaStream_t st) {
+  if (nrows <= 0) return 0;
+  k_ls_decide<<<(nrows + 127) / 128, 128, 0, st>>>(a);
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---- mask compaction (deterministic, single CTA) ---------------------------
 __global__ void k_compact(const uint8_t* __restrict__ mask, int n, int* __restrict__ list, int* __restrict__ count) {
   __shared__ int warp_tot[32];

@@ -13,6 +13,7 @@
 #include "../../include/causarray_b200.h"
 #include "common.cuh"
 #include "devbuf.h"
+#include "comm.h"
 #include "kernels.h"
 #include "gcate_state.h"
 
@@ -42,6 +43,13 @@ int kpad_for(int k) {
 }  // namespace ca
 
 using namespace ca;
+
+// gene sharding: sums over genes are completed over the ranks (no-op for a single rank)
+static inline bool sharded(const ca_gcate* h) { return h->comm != nullptr && h->world > 1; }
+static inline int allreduce(ca_gcate* h, double* buf, size_t count) {
+  return sharded(h) ? comm_allreduce_sum(h->comm, buf, count, h->st) : 0;
+}
+static inline double genes_total(const ca_gcate* h) { return h->p_total > 0 ? (double)h->p_total : (double)h->p; }
 
 
 static int gcate_alloc(ca_gcate* h) {
@@ -119,7 +127,31 @@ extern "C" int ca_gcate_create(ca_gcate_t* out, int n, int p, int d, int r, int 
 extern "C" int ca_gcate_destroy(ca_gcate_t h) {
   if (h) {
     cudaStreamSynchronize(h->st);
+    if (h->comm) comm_destroy(h->comm);
     delete h;
+  }
+  return 0;
+}
+
+extern "C" int ca_comm_unique_id(uint8_t* out128) {
+  CA_REQUIRE(out128, "null argument");
+  return comm_unique_id(out128);
+}
+
+extern "C" int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_total, const uint8_t* id128) {
+  CA_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world && p_total >= h->p, "bad shard description");
+  CA_REQUIRE(!h->counts_loaded, "set the shard before the counts are loaded (the constant row sums are reduced there)");
+  if (h->comm) {
+    comm_destroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->rank = rank;
+  h->world = world;
+  h->p_total = (long)p_total;
+  if (world > 1) {
+    if (comm_init(&h->comm, rank, world, id128)) return -1;
+    const size_t n = (size_t)h->n;
+    if (h->ls_Xc.alloc(n * h->kpad) || h->ls_t.alloc(n) || h->ls_ell.alloc(n) || h->ls_ne.alloc(n)) return -1;
   }
   return 0;
 }
@@ -162,6 +194,7 @@ static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_
     if (launch_tys_rowsum(h->Ynt.ptr, h->ldn, p, n, h->nu.ptr, 1, h->family, h->thres, h->tys_col.ptr, h->st)) return -1;
   }
   if (launch_sum(h->tys_col.ptr, p, h->tys_total.ptr, h->st)) return -1;
+  if (allreduce(h, h->tys_row.ptr, (size_t)n) || allreduce(h, h->tys_total.ptr, 1)) return -1;
   if (launch_zero_fraction(h->Ynt.ptr, h->ldn, p, n, h->sparsity.ptr, h->st)) return -1;
   CA_CUDA(cudaStreamSynchronize(h->st));
   h->counts_loaded = true;
@@ -395,6 +428,59 @@ static RowProblem gene_problem(ca_gcate* h) {
   return rp;
 }
 
+// Cell line search with the genes split over ranks (see k_ls_candidates / k_ls_decide): per round
+// the candidate rows are built, their partial log-likelihoods come from the ordinary row pass over
+// this rank's genes, one all-reduce completes them and every rank takes the same decisions.  The
+// number of rounds is data dependent but identical on all ranks (the reduced sums are), so the
+// pending count is read back once per round.
+static int cell_search_sharded(ca_gcate* h, const RowProblem& rp, double alpha, double beta, int max_iters, double tol) {
+  const int n = h->n, kp = h->kpad;
+  cudaStream_t st = h->st;
+  int* cnt = h->counts.ptr;
+  LsShard a;
+  a.X = h->A.ptr;
+  a.g = h->g_c.ptr;
+  a.Xc = h->ls_Xc.ptr;
+  a.t = h->ls_t.ptr;
+  a.ne = h->ls_ne.ptr;
+  a.ell = h->ls_ell.ptr;
+  a.tys = h->tys_row.ptr;
+  a.f0 = h->f0_c.ptr;
+  a.normg = h->ng_c.ptr;
+  a.f01 = h->ls_f01.ptr;
+  a.e01 = h->ls_e01.ptr;
+  a.ell_fin = h->ellfin_c.ptr;
+  a.pend = h->ls_pend.ptr;
+  a.n_pending = cnt + 7;
+  a.eval_total = h->evals.ptr + 0;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.tol = tol;
+  a.ncols_total = genes_total(h);
+  a.kpad = kp;
+  a.max_iters = max_iters;
+  a.rowlist = h->list_c.ptr;
+  a.count = cnt + 0;
+  CA_CUDA(cudaMemsetAsync(h->ls_pend.ptr, 0, (size_t)n, st));
+  for (int round = 0; round < max_iters; ++round) {
+    a.round = round;
+    if (launch_ls_candidates(a, n, st)) return -1;
+    CA_CUDA(cudaMemsetAsync(h->ls_ell.ptr, 0, sizeof(double) * n, st));
+    if (launch_rowpass(rp, h->ls_Xc.ptr, a.rowlist, a.count, n, false, 0, 0, h->ls_ell.ptr, nullptr, 0, st)) return -1;
+    if (allreduce(h, h->ls_ell.ptr, (size_t)n)) return -1;
+    CA_CUDA(cudaMemsetAsync(cnt + 7, 0, sizeof(int), st));
+    if (launch_ls_decide(a, n, st)) return -1;
+    int npend = 0;
+    CA_CUDA(cudaMemcpyAsync(&npend, cnt + 7, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CA_CUDA(cudaStreamSynchronize(st));
+    if (npend == 0) break;
+    if (launch_compact(h->ls_pend.ptr, n, h->ls_list2.ptr, cnt + 5, st)) return -1;
+    a.rowlist = h->ls_list2.ptr;
+    a.count = cnt + 5;
+  }
+  return 0;
+}
+
 // One alternating iteration, asynchronous on h->st.  On completion
 // scal[0] = sum_j ell_fin_g[j] (log-likelihood sum at the new A, B).
 static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int max_iters, double tol) {
@@ -407,13 +493,15 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
     if (launch_compact(h->cell_active.ptr, n, h->list_c.ptr, cnt + 0, st)) return -1;
     if (launch_rowpass(rp, h->A.ptr, h->list_c.ptr, cnt + 0, n, true, d, r, h->ell_c.ptr, h->Graw_c.ptr, h->ldG, st))
       return -1;
-    if (launch_div_scalar(h->Graw_c.ptr, (long)n * h->ldG, (double)p, st)) return -1;
+    // gene shards: the per-cell log-likelihoods and gradient blocks are sums over all genes
+    if (allreduce(h, h->ell_c.ptr, (size_t)n) || allreduce(h, h->Graw_c.ptr, (size_t)n * h->ldG)) return -1;
+    if (launch_div_scalar(h->Graw_c.ptr, (long)n * h->ldG, genes_total(h), st)) return -1;
     PrepArgs pa;
     pa.nrows = n;
     pa.rowlist = h->list_c.ptr;
     pa.count = cnt + 0;
     pa.kpad = kp;
-    pa.ncols = p;
+    pa.ncols = (int)genes_total(h);
     pa.G = h->Graw_c.ptr;
     pa.ldG = h->ldG;
     pa.gc_lo = d;
@@ -458,7 +546,11 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
     s.e01s = h->ls_e01.ptr;
     s.list2 = h->ls_list2.ptr;
     s.count2 = cnt + 5;
-    if (launch_search(rp, s, st)) return -1;
+    if (sharded(h)) {
+      if (cell_search_sharded(h, rp, alpha, beta, max_iters, tol)) return -1;
+    } else if (launch_search(rp, s, st)) {
+      return -1;
+    }
     if (h->has_P1) {
       if (launch_pt_v(h->P1.ptr, h->d1, h->d1, h->A.ptr + d, kp, r, n, h->W.ptr, st)) return -1;
       if (launch_sub_p_w(h->P1.ptr, h->d1, h->d1, h->A.ptr + d, kp, r, n, h->W.ptr, st)) return -1;
@@ -494,6 +586,7 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       if (launch_div_scalar(h->Graw_g.ptr, (long)p * h->ldG, (double)n, st)) return -1;
       if (h->has_P2) {
         if (launch_pt_v(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
+        if (allreduce(h, h->W.ptr, (size_t)h->r2 * a)) return -1;   // P2^T G sums over genes
         if (launch_sub_p_w(h->P2.ptr, h->r2, h->r2, h->Graw_g.ptr, h->ldG, a, p, h->W.ptr, st)) return -1;
       }
       static const bool nosort = getenv("CA_NOSORT") != nullptr;
@@ -563,6 +656,7 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
         return -1;
     }
     if (launch_sum(h->ellfin_g.ptr, p, h->scal.ptr + 0, st)) return -1;
+    if (allreduce(h, h->scal.ptr + 0, 1)) return -1;
   }
   return 0;
 }
@@ -623,6 +717,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   // stage-2 entry projection  B[:, d-a:d] -= P2 (P2^T B[:, d-a:d])   (gcate_opt.py:337-340)
   if (h->has_P2 && a > 0) {
     if (launch_pt_v(h->P2.ptr, h->r2, h->r2, h->B.ptr + (d - a), kp, a, p, h->W.ptr, st)) return -1;
+    if (allreduce(h, h->W.ptr, (size_t)h->r2 * a)) return -1;
     if (launch_sub_p_w(h->P2.ptr, h->r2, h->r2, h->B.ptr + (d - a), kp, a, p, h->W.ptr, st)) return -1;
   }
   // adaptive lasso weights (gcate_opt.py:352-353)
@@ -650,9 +745,12 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
 
   double tys_total = 0.0;
   CA_CUDA(cudaMemcpyAsync(&tys_total, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, st));
-  auto objective = [&](double ell_sum, double pen) { return (nll_from_sum(h, ell_sum, tys_total) + pen) / (double)p; };
+  auto objective = [&](double ell_sum, double pen) { return (nll_from_sum(h, ell_sum, tys_total) + pen) / genes_total(h); };
   auto penalty_async = [&]() -> int {
-    if (a > 0 && h->has_lam) return launch_l1_penalty(h->B.ptr, p, kp, d - a, d, h->lam.ptr, a, h->l1part.ptr, h->scal.ptr + 2, st);
+    if (a > 0 && h->has_lam) {
+      if (launch_l1_penalty(h->B.ptr, p, kp, d - a, d, h->lam.ptr, a, h->l1part.ptr, h->scal.ptr + 2, st)) return -1;
+      return allreduce(h, h->scal.ptr + 2, 1);
+    }
     CA_CUDA(cudaMemsetAsync(h->scal.ptr + 2, 0, sizeof(double), st));
     return 0;
   };
@@ -662,6 +760,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
     RowProblem rp = gene_problem(h);
     if (launch_rowpass(rp, h->B.ptr, nullptr, nullptr, p, false, 0, 0, h->ell_g.ptr, nullptr, 0, st)) return -1;
     if (launch_sum(h->ell_g.ptr, p, h->scal.ptr + 0, st)) return -1;
+    if (allreduce(h, h->scal.ptr + 0, 1)) return -1;
     if (penalty_async()) return -1;
     CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
     CA_CUDA(cudaStreamSynchronize(st));

@@ -26,6 +26,12 @@ struct ca_gcate {
   DevBuf<int> ls_list2;
   DevBuf<int> neval_g;               // candidates each gene needed in its last line search (list ordering key)
   int ldG = 64;
+  // gene sharding over ranks (one process per GPU): this handle holds p of p_total genes
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+  long p_total = 0;                  // 0: not sharded (= p)
+  DevBuf<double> ls_Xc, ls_t, ls_ell;
+  DevBuf<int> ls_ne;
   int any_pois = 0;                  // some nu exceeds thres (the NB kernels then keep their Poisson switch)
   bool counts_loaded = false, factors_set = false;
   // raw counts kept for the GLM / AIPW handles that share them

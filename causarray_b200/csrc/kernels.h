@@ -53,6 +53,31 @@ struct SearchLaunch {
   int* count2;
 };
 
+// gene-sharded cell line search (altmin_aux.cu)
+struct LsShard {
+  const int* rowlist;
+  const int* count;
+  double* X;             // rows x kpad: current point, overwritten with the accepted point
+  const double* g;       // rows x kpad
+  double* Xc;            // rows x kpad: candidate rows
+  double* t;             // per row: current step
+  int* ne;               // per row: candidates evaluated
+  const double* ell;     // per row: log-likelihood sum of the candidate, reduced over the ranks
+  const double* tys;
+  const double* f0;
+  const double* normg;
+  double* f01;
+  double* e01;
+  double* ell_fin;
+  unsigned char* pend;
+  int* n_pending;
+  unsigned long long* eval_total;
+  double alpha, beta, tol, ncols_total;
+  int kpad, round, max_iters;
+};
+int launch_ls_candidates(const LsShard& a, int nrows, cudaStream_t st);
+int launch_ls_decide(const LsShard& a, int nrows, cudaStream_t st);
+
 int launch_rowpass(const RowProblem& rp, const double* X, const int* rowlist, const int* count, int nrows,
                    bool want_grad, int gc_lo, int gc_n, double* ell_out, double* G_out, int ldG,
                    cudaStream_t st);

@@ -30,6 +30,14 @@ class GcateDevice:
         except Exception:
             pass
 
+    def set_shard(self, rank, world, p_total, unique_id):
+        """Gene sharding over ``world`` ranks (one process per GPU): this handle holds ``p`` of
+        ``p_total`` genes.  ``unique_id`` is the 128-byte NCCL id from :func:`comm_unique_id` of one
+        rank.  Collective; call before the counts are loaded."""
+        uid = np.ascontiguousarray(np.frombuffer(bytes(unique_id), dtype=np.uint8))
+        assert uid.size == 128
+        L.check(self.lib.ca_gcate_set_shard(self.h, int(rank), int(world), int(p_total), L.u8ptr(uid)))
+
     def load_counts(self, Y, size_factor=None, nu=None):
         Y = L.f64(Y)
         assert Y.shape == (self.n, self.p)
@@ -142,6 +150,13 @@ class GcateDevice:
         hist = np.zeros(int(kwargs_es['max_iters']) + 1)
         L.check(self.lib.ca_gcate_alter_min(self.h, ctypes.byref(prm), ctypes.byref(res), L.dptr(hist)))
         return res, hist[:res.hist_len].copy()
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (generate on one rank, broadcast to the others)."""
+    out = np.zeros(128, dtype=np.uint8)
+    L.check(L.load().ca_comm_unique_id(L.u8ptr(out)))
+    return out.tobytes()
 
 
 class GlmDevice:

@@ -48,6 +48,16 @@ int ca_gcate_destroy(ca_gcate_t h);
  * Tys = -lgamma(Y+1) [+ lgamma(nu+Y) - lgamma(nu)] sums on the device
  * (causarray/gcate_opt.py:343-347) and the per-gene zero fraction (:305). */
 int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_factor, const double* nu);
+/* ---- gene shards over ranks (one process per GPU) -------------------
+ * A handle may hold p of p_total genes (columns of Y, rows of B, nu, lam, gene masks); A / U, X and
+ * the size factors are replicated.  The gene step of update_with_mask (gcate_opt.py:182-200) is
+ * gene-local; the cell step sums over genes (grad(Y^T, B, A) :168 and the per-candidate nll of the
+ * line search :173-175), as do the returned nll (:204), the L1 term (:440) and the stage-2
+ * projector P2^T G (:188): those sums are completed with NCCL all-reduces on the handle's stream.
+ * ca_comm_unique_id: 128-byte NCCL id generated on one rank and handed to all of them;
+ * ca_gcate_set_shard: collective over the ranks, before the counts are loaded. */
+int ca_comm_unique_id(uint8_t* out128);
+int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_total, const uint8_t* id128);
 /* The same in three steps, so that the input checks of fit_gcate
  * (causarray/gcate.py:12-17: integer-valued, no all-zero gene) and the
  * median-of-ratios size factors (causarray/utils.py:179-219) run on the device
