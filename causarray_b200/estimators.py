@@ -24,7 +24,8 @@ from .prep import comp_size_factor, _filter_params, subsample_ctrl_cells, subsam
 from ._timing import phase
 
 
-def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0, **kwargs):
+def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0, _shard=None, _size_factor=None,
+                 **kwargs):
     """Input validation, size factors and dispersion (reference ``_check_input``).
 
     The O(n p) passes (integer check, empty-gene check, median-of-ratios size factors, the
@@ -37,9 +38,12 @@ def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0,
         raise ValueError('Family not recognized')
     n, p = Y.shape
     ws = _ws if _ws is not None else BatchWorkspace.upload(Y, family, X.shape[1], int(r),
-                                                            kwargs.get('thres_disp', 100.))
+                                                            kwargs.get('thres_disp', 100.), shard=_shard)
     if ws.checks is None:
         ws.checks = (0, 0, 0)
+    if ws.shard is not None:      # every rank must take the same branch below
+        from .parallel import allreduce_sum_np
+        ws.checks = tuple(int(v) for v in allreduce_sum_np(np.asarray(ws.checks, dtype=np.float64)))
     n_nonint, n_nonfin, n_empty = ws.checks
     if n_nonint > 0 or n_nonfin > 0:
         warnings.warn("Y is not integer-valued. It will be rounded to the nearest integer.")
@@ -52,7 +56,8 @@ def _check_input(Y, X, family, disp_glm, disp_family, offset, c1, _ws=None, r=0,
     kwargs_glm = {'family': family}
     if offset is not None:
         if type(offset) == bool and offset is True:
-            size_factor = ws.gcate.size_factors()
+            # (a gene shard cannot take the per-cell median over all genes: the caller supplies it)
+            size_factor = ws.gcate.size_factors() if _size_factor is None else np.asarray(_size_factor, dtype=type_f)
             kwargs_glm['size_factor'] = size_factor
             offset = np.log(size_factor)
         else:
@@ -87,7 +92,15 @@ def estimate(Y, X, r, a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2
         X.shape[1], int(r), valid.get('thres_disp', 100.))
     res_1 = alter_min(Y, r, X=X, P1=True, A=A_init, kwargs_glm=kwargs_glm, kwargs_ls=kwargs_ls_1,
                       kwargs_es=kwargs_es_1, _ws=ws, **valid)
-    Q, _ = scipy.linalg.qr(res_1['B_Gamma'][:, -r:], mode='economic')
+    if ws.shard is not None:
+        # thin Q of Gamma-hat with its rows (genes) split over ranks: Cholesky-QR through the all-reduced
+        # r x r Gram matrix (P2 enters only through the projector Q Q^T, so the basis is immaterial)
+        from .parallel import allreduce_sum_np
+        Gm = res_1['B_Gamma'][:, -r:]
+        Rc = np.linalg.cholesky(allreduce_sum_np(Gm.T @ Gm)).T
+        Q = np.linalg.solve(Rc.T, Gm.T).T
+    else:
+        Q, _ = scipy.linalg.qr(res_1['B_Gamma'][:, -r:], mode='economic')
     if lam1 == 0.:
         res_2 = {'X_U': res_1['X_U'], 'B_Gamma': res_1['B_Gamma']}
     else:
@@ -100,20 +113,45 @@ def estimate(Y, X, r, a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2
 
 def fit_gcate(Y, X, A, r, family='nb', disp_glm=None, disp_family=None, offset=True,
               kwargs_ls_1={}, kwargs_ls_2={}, kwargs_es_1={}, kwargs_es_2={},
-              c1=None, backend: str = "auto", A_init=None, _ws=None, **kwargs):
+              c1=None, backend: str = "auto", A_init=None, _ws=None, gene_shard=False, **kwargs):
     """Fit GCATE: returns ``(res_1, res_2)``; ``res_2['X_U']`` is ``[X | A | U]`` and
     ``res_2['B_Gamma']`` the gene-level coefficients.  ``res_2['_ws']`` holds the device
     workspace of the fit (counts stay resident for a following :func:`LFC`); close it with
     ``res_2.pop('_ws').close()`` or let it be garbage collected."""
     X = np.hstack((np.asarray(X), np.asarray(A)))
     a = np.asarray(A).shape[1]
+    shard_kw = {}
+    if gene_shard:
+        # One fit with its GENES split over the ranks of the default process group (one process per
+        # GPU; every rank makes the same call with the full inputs and keeps its block of columns).
+        # ``res['B_Gamma']`` then holds this rank's rows, ``res['gene_slice']`` says which.
+        from .parallel import dist_info, gene_bounds, broadcast_bytes
+        from .device import comm_unique_id
+        rank, world = dist_info()
+        if world > 1:
+            Yf = _dense_counts(Y)
+            p_total = Yf.shape[1]
+            lo, hi = gene_bounds(p_total, world)[rank]
+            uid = broadcast_bytes(comm_unique_id() if rank == 0 else None)
+            shard_kw['_shard'] = (rank, world, p_total, uid)
+            if offset is True:
+                shard_kw['_size_factor'] = comp_size_factor(Yf)     # per-cell median over ALL genes
+            Y = np.ascontiguousarray(Yf[:, lo:hi])
+            if disp_glm is not None:
+                disp_glm = np.ravel(disp_glm)[lo:hi]
+            if A_init is not None:
+                A_init = np.asarray(A_init)
     ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
     with ctx:
         with phase('gcate_upload_checks_sizefactors'):
             Y, kwargs_glm, lam1, ws = _check_input(Y if _sp.issparse(Y) else np.asarray(Y), X, family, disp_glm,
-                                                   disp_family, offset, c1, _ws=_ws, r=int(r), **kwargs)
+                                                   disp_family, offset, c1, _ws=_ws, r=int(r), **shard_kw, **kwargs)
         res_1, res_2 = estimate(Y, X, int(r), a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2,
                                 kwargs_es_2, A_init=A_init, _ws=ws, **kwargs)
+    if shard_kw.get('_shard') is not None:
+        rank, world, p_total, _ = shard_kw['_shard']
+        from .parallel import gene_bounds
+        res_1['gene_slice'] = res_2['gene_slice'] = gene_bounds(p_total, world)[rank]
     return res_1, res_2
 
 

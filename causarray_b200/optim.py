@@ -115,12 +115,17 @@ class BatchWorkspace:
     ``prepare``.
     """
 
-    def __init__(self, Y, size_factor, disp, family, d, r, thres_disp=100., _defer=False):
+    def __init__(self, Y, size_factor, disp, family, d, r, thres_disp=100., _defer=False, shard=None):
         if not hasattr(Y, "tocsr"):          # a scipy.sparse matrix is uploaded as CSR
             Y = np.asarray(Y, dtype=np.float64)
         n, p = Y.shape
         self.n, self.p = n, p
         self.gcate = GcateDevice(n, p, d, r, family, thres_disp)
+        # gene shard of a fit spread over ranks: (rank, world, p_total, nccl_unique_id); Y holds this
+        # rank's genes only
+        self.shard = shard
+        if shard is not None:
+            self.gcate.set_shard(shard[0], shard[1], shard[2], shard[3])
         self.glm = GlmDevice(n, p)
         self.checks = None
         self.prepared = False
@@ -132,8 +137,8 @@ class BatchWorkspace:
         self.glm.share_counts(self.gcate)
 
     @classmethod
-    def upload(cls, Y, family, d, r, thres_disp=100.):
-        return cls(Y, None, None, family, d, r, thres_disp, _defer=True)
+    def upload(cls, Y, family, d, r, thres_disp=100., shard=None):
+        return cls(Y, None, None, family, d, r, thres_disp, _defer=True, shard=shard)
 
     def prepare(self, size_factor, disp):
         self.gcate.prepare(size_factor, disp)
@@ -191,7 +196,7 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
                                                 verbose=verbose, _glm=ws.glm, _lazy=True)
         with phase('gcate_init_svd'):
             ptr = ws.glm.resid_device_ptr()
-            u, s, vt = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask)
+            u, s, vt = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask, sharded=ws.shard is not None)
         if u.shape[1] < r:
             raise ValueError('The number of latent factors is larger than the rank of deviance residuals '
                              '({}). Try to decrease the value of r.'.format(u.shape[1]))
@@ -206,7 +211,7 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
         with phase('gcate_init_glm'):
             B = _glm_mod.fit_glm(Y, A, offset=offset, family=family, disp_glm=nuisance, maxiter=100, verbose=verbose,
                                  _glm=ws.glm, _lazy=True)[0]
-        u, s, vt = lowrank_product_svd(A[:, d:], B[:, d:])
+        u, s, vt = lowrank_product_svd(A[:, d:], B[:, d:], sharded=ws.shard is not None)
         A[:, d:] = u * s[None, :] ** (1 / 2)
         B[:, d:] = vt.T * s[None, :] ** (1 / 2)
     B = np.array(B, dtype=type_f)

@@ -48,6 +48,58 @@ def gather_frames(frames_by_batch, dst=0):
     return merged
 
 
+def gene_bounds(p, world_size):
+    """Contiguous gene shards: ``[(lo, hi)] * world_size`` covering ``range(p)`` (sizes differ by <= 1)."""
+    import numpy as np
+    edges = np.linspace(0, p, world_size + 1).astype(int)
+    return [(int(edges[i]), int(edges[i + 1])) for i in range(world_size)]
+
+
+def allreduce_sum(t):
+    """In-place sum of a torch tensor over the default process group (no-op for one process).  CUDA
+    tensors under a ``gloo`` group make the round trip through the host -- the tensors of the sharded
+    initialisation are small ((n x b) and (b x b))."""
+    rank, world = dist_info()
+    if world == 1:
+        return t
+    import torch.distributed as dist
+    if t.is_cuda and dist.get_backend() == "gloo":
+        c = t.detach().cpu()
+        dist.all_reduce(c)
+        t.copy_(c)
+    else:
+        dist.all_reduce(t)
+    return t
+
+
+def allreduce_sum_np(a):
+    """Sum of a numpy array over the ranks (returns a new array; identity for one process)."""
+    import numpy as np
+    rank, world = dist_info()
+    if world == 1:
+        return np.asarray(a)
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        dist.all_reduce(t)
+        t = t.cpu()
+    else:
+        dist.all_reduce(t)
+    return t.numpy()
+
+
+def broadcast_bytes(b, src=0):
+    rank, world = dist_info()
+    if world == 1:
+        return b
+    import torch.distributed as dist
+    box = [b if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def set_device_from_env():
     """Bind this process to ``cuda:LOCAL_RANK`` (torchrun convention) for the C-ABI library."""
     from . import _lib as L

@@ -32,11 +32,18 @@ def fix_signs(u, vt=None):
     return u, vt
 
 
-def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, tol=1e-11, seed=0):
+def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, tol=1e-11, seed=0, sharded=False):
     """Top-``r`` singular triplets of the (n, p) float64 matrix at device pointer ``ptr``.
 
     Returns host arrays ``u (n, r)``, ``s (r,)`` (ascending, as ``svds``), ``vt (r, p)``.
+    ``sharded``: the matrix is this rank's block of COLUMNS (genes) of the full matrix; sums over
+    genes -- the (n, b) products ``R V``, the (b, b) Gram matrices of the Cholesky-QR and the Ritz
+    residual -- are all-reduced over the process group, ``u`` / ``s`` come back replicated and ``vt``
+    holds this rank's columns.
     """
+    from .parallel import allreduce_sum, dist_info
+    shard = sharded and dist_info()[1] > 1
+    red = allreduce_sum if shard else (lambda t: t)
     import torch
     if not torch.cuda.is_available():
         from ._lib import CausarrayCudaError
@@ -44,35 +51,42 @@ def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, t
     R = torch.as_tensor(_DevArray(ptr, (n, p)), device="cuda")
     if zero_cols is not None and np.any(zero_cols):
         R[:, torch.as_tensor(np.where(zero_cols)[0], device="cuda")] = 0.0
-    b = int(min(min(n, p), r + oversample))
+    b = int(min(n, r + oversample) if shard else min(min(n, p), r + oversample))   # (same block width on every rank)
     gen = torch.Generator(device="cuda")
-    gen.manual_seed(seed)
+    gen.manual_seed(seed + (dist_info()[0] if shard else 0))
     V0 = torch.randn(p, b, dtype=torch.float64, device="cuda", generator=gen)
 
-    def orth_chol(X):
+    def orth_chol(X, rows_sharded=False):
         # CholeskyQR2: two rounds of X <- X R^-1 with R^T R = X^T X (a b x b Gram, Cholesky and a
         # triangular solve -- three small kernels instead of cuSOLVER's Householder panel, which
-        # took 0.3 ms per call on these tall-skinny blocks and half of this routine's time)
+        # took 0.3 ms per call on these tall-skinny blocks and half of this routine's time).  With the
+        # rows of X split over ranks only the Gram matrix needs a reduction.
         for _ in range(2):
-            Lc = torch.linalg.cholesky_ex(X.T @ X)[0]
+            G = X.T @ X
+            if rows_sharded:
+                G = red(G)
+            Lc = torch.linalg.cholesky_ex(G)[0]
             X = torch.linalg.solve_triangular(Lc, X.T, upper=False).T
         return X
 
-    def orth_qr(X):
+    def orth_qr(X, rows_sharded=False):
+        if rows_sharded:
+            return orth_chol(X, True)
         return torch.linalg.qr(X)[0]
 
     def iterate(orth):
         V = V0
         Ub = S = Vr = None
         for it in range(max_iter):
-            Q = orth(R @ V)                        # (n, b)
-            V = orth(R.T @ Q)                      # (p, b)
+            Q = orth(red(R @ V))                   # (n, b), replicated
+            V = orth(R.T @ Q, shard)               # (p, b), rows = this rank's genes
             if it % 4 == 3 or it == max_iter - 1:
-                Bm = R @ V                          # (n, b): R restricted to span(V)
+                Bm = red(R @ V)                     # (n, b): R restricted to span(V)
                 Ub, S, Wt = torch.linalg.svd(Bm, full_matrices=False)
                 # Ritz residual of the leading r right vectors: || R^T u - s v ||
                 Vr = V @ Wt[:r].T                   # (p, r)
-                res = torch.linalg.norm(R.T @ Ub[:, :r] - Vr * S[:r], dim=0).max().item()
+                res2 = red(((R.T @ Ub[:, :r] - Vr * S[:r]) ** 2).sum(dim=0))
+                res = torch.sqrt(res2).max().item()
                 if not np.isfinite(res):
                     return None
                 if res <= tol * S[0].item():
@@ -92,15 +106,22 @@ def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, t
     return u, s, vt
 
 
-def lowrank_product_svd(U, G):
+def lowrank_product_svd(U, G, sharded=False):
     """SVD of ``E = U @ G.T`` (n x p, rank r) from its factors ``U (n, r)``, ``G (p, r)``.
+    ``sharded``: ``G`` holds this rank's rows (genes); its orthogonalisation goes through the
+    all-reduced r x r Gram matrix (Cholesky-QR) and ``vt`` comes back with this rank's columns.
 
     Replaces ``svds(E, k=r)`` of ``causarray/gcate_opt.py:330-331`` without
     forming ``E``: thin QR of both factors and an r x r SVD.
     Returns ``u (n, r)``, ``s (r,)`` ascending, ``vt (r, p)``.
     """
     Qa, Ra = np.linalg.qr(U)
-    Qb, Rb = np.linalg.qr(G)
+    if sharded:
+        from .parallel import allreduce_sum_np
+        Rb = np.linalg.cholesky(allreduce_sum_np(G.T @ G)).T      # G = Qb Rb, Rb upper triangular
+        Qb = np.linalg.solve(Rb.T, G.T).T
+    else:
+        Qb, Rb = np.linalg.qr(G)
     uu, s, vvt = np.linalg.svd(Ra @ Rb.T)
     u = (Qa @ uu)[:, ::-1].copy()        # ascending singular values, as svds returns them
     vt = (vvt @ Qb.T)[::-1].copy()
