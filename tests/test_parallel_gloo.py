@@ -53,3 +53,53 @@ def test_gather_frames_world2():
         assert p.exitcode == 0
     assert keys == [0, 1, 2, 3, 4]
     assert total == 3 * (0 + 1 + 2 + 3 + 4)
+
+
+def test_gene_bounds_cover():
+    for p in (1, 7, 301, 8000):
+        for w in (1, 2, 3, 8):
+            b = par.gene_bounds(p, w)
+            assert b[0][0] == 0 and b[-1][1] == p and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_sharded_linalg(rank, world, port, q):
+    """Host pieces of the gene-sharded initialisation: the low-rank product SVD and the Cholesky-QR of
+    Gamma-hat with the genes (rows) split over two ranks against the unsharded results."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    from causarray_b200.svd import lowrank_product_svd
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    n, p, r = 40, 61, 3
+    U, G = rng.standard_normal((n, r)), rng.standard_normal((p, r))
+    lo, hi = par.gene_bounds(p, world)[rank]
+    u_ref, s_ref, vt_ref = lowrank_product_svd(U, G)
+    u, s, vt = lowrank_product_svd(U, G[lo:hi], sharded=True)
+    ok = np.allclose(s, s_ref, rtol=1e-12) and np.allclose(u, u_ref, atol=1e-10) and np.allclose(vt, vt_ref[:, lo:hi], atol=1e-10)
+    tot = par.allreduce_sum_np(np.array([float(hi - lo)]))
+    ok = ok and tot[0] == p
+    t = par.allreduce_sum(torch.ones(3, dtype=torch.float64) * (rank + 1))
+    ok = ok and bool((t == 3.0).all())
+    blob = par.broadcast_bytes(b"id-from-rank-0" if rank == 0 else None)
+    ok = ok and blob == b"id-from-rank-0"
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_linalg_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_sharded_linalg, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
