@@ -342,6 +342,7 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         raise TypeError('clip_pseudo_outcomes has been removed; AIPW pseudo-outcomes are always left unclipped')
     lfc_opts = kwargs.pop('_lfc_opts', None)
     ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
+    gene_slice = kwargs.pop('_gene_slice', None)
     if isinstance(Y, pd.DataFrame):
         gene_names = Y.columns
         Y = Y.values
@@ -419,6 +420,11 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
             with phase('lfc_aipw'):
                 out = aipw_lfc(Y, Y_hat.W, Y_hat.Bcov, Y_hat.Btrt, Y_hat.offset, size_factors, A, pi_hat,
                                cell_mask=cm, glm=getattr(Y_hat, 'glm', None) or _glm, **lfc_opts)
+        if gene_slice is not None:     # gene shards: per-gene results of all ranks, in gene order
+            from .parallel import allgather_concat
+            out = {k_: allgather_concat(v_, axis=1) for k_, v_ in out.items()}
+            p = out['tau'].shape[1]
+            gene_names = gene_slice[2]
         ctrl = np.sum(A, axis=1) == 0.
         for j in range(A.shape[1]):
             cells = mask[:, j] if mask is not None else (ctrl | (A[:, j] == 1.))
@@ -531,6 +537,22 @@ def LFC(Y, W, A, W_A=None, family='nb', offset=False, Y_hat=None, pi_hat=None, c
         raise ValueError('usevar must be either "pooled" or "unequal"')
     if K is None:
         K = 2 if cross_est else 1
+    if kwargs.pop('gene_shard', False):
+        # genes split over the ranks (every rank makes the same call with the full inputs): the outcome
+        # GLM and the AIPW reduction run on this rank's genes, the per-gene results are gathered and the
+        # per-treatment BH runs on all genes; every rank returns the full frame
+        from .parallel import dist_info, gene_bounds
+        rank, world = dist_info()
+        if world > 1:
+            names_full = list(Y.columns) if isinstance(Y, pd.DataFrame) else None
+            Yf = Y.values if isinstance(Y, pd.DataFrame) else (Y.toarray() if hasattr(Y, 'tocsr') else np.asarray(Y))
+            p_total = Yf.shape[1]
+            lo, hi = gene_bounds(p_total, world)[rank]
+            if kwargs.get('_glm') is None or kwargs['_glm'].p != p_total:
+                Y = np.ascontiguousarray(Yf[:, lo:hi])
+            if kwargs.get('disp_glm') is not None and np.size(kwargs['disp_glm']) == p_total:
+                kwargs['disp_glm'] = np.ravel(kwargs['disp_glm'])[lo:hi]
+            kwargs['_gene_slice'] = (lo, hi, names_full if names_full is not None else range(p_total))
     opts = dict(usevar=usevar, thres_min=thres_min, thres_diff=thres_diff, eps_var=eps_var)
     if fdx:
         # FDX needs the per-cell influence values: dense reference-style estimand (small problems)

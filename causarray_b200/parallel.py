@@ -90,6 +90,18 @@ def allreduce_sum_np(a):
     return t.numpy()
 
 
+def allgather_concat(a, axis=0):
+    """Concatenate the ranks' numpy arrays along ``axis`` in rank order (identity for one process)."""
+    import numpy as np
+    rank, world = dist_info()
+    if world == 1:
+        return np.asarray(a)
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, np.asarray(a))
+    return np.concatenate(parts, axis=axis)
+
+
 def broadcast_bytes(b, src=0):
     rank, world = dist_info()
     if world == 1:

@@ -29,9 +29,17 @@ def main():
     Y, X, A = sim["Y"], sim["X"], sim["A"]
     kw = dict(family="nb", disp_glm=sim["disp"], kwargs_es_1=dict(max_iters=25), kwargs_es_2=dict(max_iters=25))
     r1, r2 = cb.fit_gcate(Y.copy(), X, A, 2, **kw)                      # whole fit on this rank's GPU
-    r2.pop("_ws").close()
+    ws = r2.pop("_ws")
+    W = np.c_[X, r2["U"]]
+    off = np.log(r2["kwargs_glm"]["size_factor"])
+    df_ref, _ = cb.LFC(Y.copy(), W, A, W_A=W, family="nb", offset=off, disp_glm=sim["disp"], _glm=ws.glm, _trusted=True)
+    ws.close()
     s1, s2 = cb.fit_gcate(Y.copy(), X, A, 2, gene_shard=True, **kw)     # genes split over the ranks
-    s2.pop("_ws").close()
+    ws = s2.pop("_ws")
+    Ws = np.c_[X, s2["U"]]
+    df_sh, _ = cb.LFC(Y.copy(), Ws, A, W_A=Ws, family="nb", offset=np.log(s2["kwargs_glm"]["size_factor"]),
+                      disp_glm=sim["disp"], _glm=ws.glm, _trusted=True, gene_shard=True)
+    ws.close()
     lo, hi = s2["gene_slice"]
     ok = True
 
@@ -51,6 +59,13 @@ def main():
     check("s1 B", s1["B_Gamma"], r1["B_Gamma"][lo:hi], 2e-5)
     check("s2 X_U", s2["X_U"], r2["X_U"], 2e-5)
     check("s2 B", s2["B_Gamma"], r2["B_Gamma"][lo:hi], 2e-5)
+    ok &= len(df_sh) == len(df_ref) and list(df_sh.columns) == list(df_ref.columns)
+    for c in ("tau", "std", "pvalue", "padj"):
+        a_, b_ = df_sh[c].to_numpy().astype(float), df_ref[c].to_numpy().astype(float)
+        fin = np.isfinite(b_)
+        ok &= bool(np.array_equal(np.isfinite(a_), fin))
+        check("LFC " + c, a_[fin] / np.where(np.abs(b_[fin]) > 1e-3, b_[fin], 1.0), b_[fin] / np.where(np.abs(b_[fin]) > 1e-3, b_[fin], 1.0), 1e-5)
+    ok &= bool(np.array_equal(df_sh["padj"].to_numpy() < 0.05, df_ref["padj"].to_numpy() < 0.05))
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
