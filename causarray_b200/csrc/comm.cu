@@ -1,6 +1,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "../../include/causarray_b200.h"
 #include "comm.h"
@@ -14,6 +17,7 @@ struct Api {
   ncclResult_t (*get_unique_id)(ncclUniqueId*) = nullptr;
   ncclResult_t (*comm_init_rank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*all_reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*all_gather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*comm_destroy)(ncclComm_t) = nullptr;
   const char* (*error_string)(ncclResult_t) = nullptr;
   bool tried = false;
@@ -39,6 +43,7 @@ int load_api() {
   g_api.get_unique_id = (decltype(g_api.get_unique_id))dlsym(g_api.lib, "ncclGetUniqueId");
   g_api.comm_init_rank = (decltype(g_api.comm_init_rank))dlsym(g_api.lib, "ncclCommInitRank");
   g_api.all_reduce = (decltype(g_api.all_reduce))dlsym(g_api.lib, "ncclAllReduce");
+  g_api.all_gather = (decltype(g_api.all_gather))dlsym(g_api.lib, "ncclAllGather");
   g_api.comm_destroy = (decltype(g_api.comm_destroy))dlsym(g_api.lib, "ncclCommDestroy");
   g_api.error_string = (decltype(g_api.error_string))dlsym(g_api.lib, "ncclGetErrorString");
   if (!g_api.get_unique_id || !g_api.comm_init_rank || !g_api.all_reduce || !g_api.comm_destroy) {
@@ -85,6 +90,231 @@ int comm_allreduce_sum(void* comm, double* buf, size_t count, cudaStream_t st) {
   ncclResult_t r = g_api.all_reduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)comm, st);
   if (r != ncclSuccess) return nccl_fail(r, "ncclAllReduce");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// all-reduce over peer memory
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int PEER_THREADS = 256;
+constexpr int PEER_PER_THREAD = 8;
+constexpr int PEER_CHUNK = PEER_THREADS * PEER_PER_THREAD;              // doubles per block
+constexpr int PEER_MAX_BLOCKS = (int)(PEER_MAX_DOUBLES / PEER_CHUNK);   // 256: all resident at once
+constexpr size_t PEER_FLAG_BYTES = sizeof(unsigned long long) * PEER_MAX_BLOCKS * PEER_MAX_WORLD;
+constexpr size_t PEER_ERR_OFF = PEER_FLAG_BYTES;                        // one int, padded to 256 bytes
+constexpr size_t PEER_STAGE_OFF = PEER_FLAG_BYTES + 256;
+constexpr size_t PEER_STAGE_BYTES = PEER_MAX_DOUBLES * sizeof(double);
+constexpr size_t PEER_ARENA_BYTES = PEER_STAGE_OFF + 2 * PEER_STAGE_BYTES;
+constexpr unsigned long long PEER_TIMEOUT_NS = 30000000000ull;          // a peer that never arrives: flag an error, do not hang
+
+struct PeerArgs {
+  double* buf;          // elements [0, count0) ...
+  double* buf1;         // ... and [count0, count): two arrays reduced by one launch
+  size_t count0;
+  size_t count;
+  int rank;
+  unsigned long long epoch;
+  double* stage[PEER_MAX_WORLD];                // staging area of this epoch's parity, per rank
+  unsigned long long* flags[PEER_MAX_WORLD];    // flag table per rank: [block][source rank]
+  int* err;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int WORLD>
+__global__ void __launch_bounds__(PEER_THREADS) k_peer_allreduce(PeerArgs a) {
+  const int tid = threadIdx.x;
+  const size_t lo = (size_t)blockIdx.x * PEER_CHUNK;
+  double mine[PEER_PER_THREAD];
+  // 1. stage this block's slice in my own arena (the peers read it from there)
+#pragma unroll
+  for (int j = 0; j < PEER_PER_THREAD; ++j) {
+    const size_t i = lo + (size_t)j * PEER_THREADS + tid;
+    mine[j] = i < a.count ? (i < a.count0 ? a.buf[i] : a.buf1[i - a.count0]) : 0.0;
+    if (i < a.count) a.stage[a.rank][i] = mine[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. tell every peer that slice `blockIdx.x` of epoch `a.epoch` is staged; 3. wait for theirs
+  if (tid < WORLD && tid != a.rank) {
+    st_release_sys(a.flags[tid] + (size_t)blockIdx.x * PEER_MAX_WORLD + a.rank, a.epoch);
+    const unsigned long long* f = a.flags[a.rank] + (size_t)blockIdx.x * PEER_MAX_WORLD + tid;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < a.epoch) {
+      __nanosleep(40);
+      if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+        atomicExch(a.err, 1);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // 4. sum in rank order (identical on every rank)
+  double acc[PEER_PER_THREAD];
+  double v[WORLD][PEER_PER_THREAD];
+#pragma unroll
+  for (int r = 0; r < WORLD; ++r) {
+#pragma unroll
+    for (int j = 0; j < PEER_PER_THREAD; ++j) {
+      const size_t i = lo + (size_t)j * PEER_THREADS + tid;
+      v[r][j] = (r == a.rank) ? mine[j] : (i < a.count ? __ldcg(a.stage[r] + i) : 0.0);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PEER_PER_THREAD; ++j) {
+    acc[j] = v[0][j];
+#pragma unroll
+    for (int r = 1; r < WORLD; ++r) acc[j] += v[r][j];
+    const size_t i = lo + (size_t)j * PEER_THREADS + tid;
+    if (i < a.count) {
+      if (i < a.count0) a.buf[i] = acc[j];
+      else a.buf1[i - a.count0] = acc[j];
+    }
+  }
+}
+}  // namespace
+
+int peer_setup(void* comm, int rank, int world, cudaStream_t st, PeerArena** out) {
+  *out = nullptr;
+  if (!comm || world < 2 || world > PEER_MAX_WORLD || (world & (world - 1)) != 0 || !g_api.all_gather) return 0;
+  const char* env = getenv("CA_PEER_REDUCE");
+  if (env && env[0] == '0') return 0;
+  PeerArena* a = new PeerArena();
+  a->rank = rank;
+  a->world = world;
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (cudaMalloc(&a->base, PEER_ARENA_BYTES) != cudaSuccess || cudaMemset(a->base, 0, PEER_ARENA_BYTES) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, a->base) != cudaSuccess)
+    ok = 0;
+  cudaGetLastError();
+  // exchange the handles (and whether each rank got this far) through the communicator
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  unsigned char hrec[sizeof(cudaIpcMemHandle_t) + 8] = {0};
+  memcpy(hrec, &mine, sizeof(mine));
+  hrec[sizeof(mine)] = (unsigned char)ok;
+  unsigned char* dsend = nullptr;
+  unsigned char* drecv = nullptr;
+  std::vector<unsigned char> all(rec * world);
+  CA_CUDA(cudaMalloc((void**)&dsend, rec));
+  CA_CUDA(cudaMalloc((void**)&drecv, rec * world));
+  CA_CUDA(cudaMemcpyAsync(dsend, hrec, rec, cudaMemcpyHostToDevice, st));
+  ncclResult_t r = g_api.all_gather(dsend, drecv, rec, ncclChar, (ncclComm_t)comm, st);
+  if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
+  CA_CUDA(cudaMemcpyAsync(all.data(), drecv, rec * world, cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  cudaFree(dsend);
+  cudaFree(drecv);
+  for (int q = 0; q < world; ++q) ok &= (int)all[q * rec + sizeof(mine)];
+  if (ok) {
+    for (int q = 0; q < world && ok; ++q) {
+      if (q == rank) {
+        a->peer[q] = a->base;
+        continue;
+      }
+      cudaIpcMemHandle_t hq;
+      memcpy(&hq, &all[q * rec], sizeof(hq));
+      if (cudaIpcOpenMemHandle(&a->peer[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        a->peer[q] = nullptr;
+        ok = 0;
+      }
+    }
+    cudaGetLastError();
+  }
+  // every rank must take the same path: agree through one more reduction
+  double* dflag = nullptr;
+  double hflag = ok ? 0.0 : 1.0;
+  CA_CUDA(cudaMalloc((void**)&dflag, sizeof(double)));
+  CA_CUDA(cudaMemcpyAsync(dflag, &hflag, sizeof(double), cudaMemcpyHostToDevice, st));
+  if (comm_allreduce_sum(comm, dflag, 1, st)) return -1;
+  CA_CUDA(cudaMemcpyAsync(&hflag, dflag, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CA_CUDA(cudaStreamSynchronize(st));
+  cudaFree(dflag);
+  if (hflag != 0.0) {
+    for (int q = 0; q < world; ++q)
+      if (q != rank && a->peer[q]) cudaIpcCloseMemHandle(a->peer[q]);
+    if (a->base) cudaFree(a->base);
+    cudaGetLastError();
+    delete a;
+    return 0;
+  }
+  *out = a;
+  return 0;
+}
+
+void peer_destroy(void* comm, PeerArena* a, cudaStream_t st) {
+  if (!a) return;
+  // a peer may still be reading this rank's staging area in its last reduction: meet first
+  double* dflag = nullptr;
+  if (comm && cudaMalloc((void**)&dflag, sizeof(double)) == cudaSuccess) {
+    cudaMemsetAsync(dflag, 0, sizeof(double), st);
+    comm_allreduce_sum(comm, dflag, 1, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dflag);
+  }
+  for (int q = 0; q < a->world; ++q)
+    if (q != a->rank && a->peer[q]) cudaIpcCloseMemHandle(a->peer[q]);
+  cudaFree(a->base);
+  cudaGetLastError();
+  delete a;
+}
+
+int peer_allreduce_sum(PeerArena* a, double* buf, size_t count, cudaStream_t st) {
+  return peer_allreduce_sum2(a, buf, count, nullptr, 0, st);
+}
+
+int peer_allreduce_sum2(PeerArena* a, double* buf, size_t count0, double* buf1, size_t count1, cudaStream_t st) {
+  const size_t count = count0 + count1;
+  if (count == 0) return 0;
+  if (count > PEER_MAX_DOUBLES) {
+    set_error("peer_allreduce_sum: %zu doubles exceed the staging area", count);
+    return -1;
+  }
+  a->epoch += 1;
+  PeerArgs pa;
+  pa.buf = buf;
+  pa.buf1 = buf1;
+  pa.count0 = count0;
+  pa.count = count;
+  pa.rank = a->rank;
+  pa.epoch = a->epoch;
+  for (int q = 0; q < PEER_MAX_WORLD; ++q) {
+    char* b = (char*)a->peer[q < a->world ? q : a->rank];
+    pa.stage[q] = (double*)(b + PEER_STAGE_OFF + (a->epoch & 1) * PEER_STAGE_BYTES);
+    pa.flags[q] = (unsigned long long*)b;
+  }
+  pa.err = (int*)((char*)a->base + PEER_ERR_OFF);
+  const int blocks = (int)((count + PEER_CHUNK - 1) / PEER_CHUNK);
+  switch (a->world) {
+    case 2: k_peer_allreduce<2><<<blocks, PEER_THREADS, 0, st>>>(pa); break;
+    case 4: k_peer_allreduce<4><<<blocks, PEER_THREADS, 0, st>>>(pa); break;
+    case 8: k_peer_allreduce<8><<<blocks, PEER_THREADS, 0, st>>>(pa); break;
+    default: set_error("peer_allreduce_sum: world size %d", a->world); return -1;
+  }
+  CA_LAUNCH_CHECK();
+  return 0;
+}
+
+int peer_error(PeerArena* a, cudaStream_t st) {
+  if (!a) return 0;
+  int e = 0;
+  int* d = (int*)((char*)a->base + PEER_ERR_OFF);
+  if (cudaMemcpyAsync(&e, d, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return 1;
+  if (e) cudaMemsetAsync(d, 0, sizeof(int), st);
+  return e;
 }
 
 }  // namespace ca

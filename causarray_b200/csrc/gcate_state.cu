@@ -47,7 +47,22 @@ using namespace ca;
 // gene sharding: sums over genes are completed over the ranks (no-op for a single rank)
 static inline bool sharded(const ca_gcate* h) { return h->comm != nullptr && h->world > 1; }
 static inline int allreduce(ca_gcate* h, double* buf, size_t count) {
-  return sharded(h) ? comm_allreduce_sum(h->comm, buf, count, h->st) : 0;
+  if (!sharded(h)) return 0;
+  if (h->peer && count <= PEER_MAX_DOUBLES) return peer_allreduce_sum((PeerArena*)h->peer, buf, count, h->st);
+  return comm_allreduce_sum(h->comm, buf, count, h->st);
+}
+static inline int allreduce2(ca_gcate* h, double* b0, size_t c0, double* b1, size_t c1) {
+  if (!sharded(h)) return 0;
+  if (h->peer && c0 + c1 <= PEER_MAX_DOUBLES) return peer_allreduce_sum2((PeerArena*)h->peer, b0, c0, b1, c1, h->st);
+  return allreduce(h, b0, c0) || allreduce(h, b1, c1);
+}
+// a peer that never reached a reduction makes the kernel give up after a few seconds instead of hanging
+static inline int peer_check(ca_gcate* h) {
+  if (h->peer && peer_error((PeerArena*)h->peer, h->st)) {
+    set_error("a rank did not arrive at a peer-memory reduction (timed out); results are invalid");
+    return -1;
+  }
+  return 0;
 }
 static inline double genes_total(const ca_gcate* h) { return h->p_total > 0 ? (double)h->p_total : (double)h->p; }
 
@@ -127,6 +142,7 @@ extern "C" int ca_gcate_create(ca_gcate_t* out, int n, int p, int d, int r, int 
 extern "C" int ca_gcate_destroy(ca_gcate_t h) {
   if (h) {
     cudaStreamSynchronize(h->st);
+    if (h->peer) peer_destroy(h->comm, (PeerArena*)h->peer, h->st);
     if (h->comm) comm_destroy(h->comm);
     delete h;
   }
@@ -141,6 +157,10 @@ extern "C" int ca_comm_unique_id(uint8_t* out128) {
 extern "C" int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_total, const uint8_t* id128) {
   CA_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world && p_total >= h->p, "bad shard description");
   CA_REQUIRE(!h->counts_loaded, "set the shard before the counts are loaded (the constant row sums are reduced there)");
+  if (h->peer) {
+    peer_destroy(h->comm, (PeerArena*)h->peer, h->st);
+    h->peer = nullptr;
+  }
   if (h->comm) {
     comm_destroy(h->comm);
     h->comm = nullptr;
@@ -150,6 +170,9 @@ extern "C" int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_t
   h->p_total = (long)p_total;
   if (world > 1) {
     if (comm_init(&h->comm, rank, world, id128)) return -1;
+    PeerArena* pa = nullptr;
+    if (peer_setup(h->comm, rank, world, h->st, &pa)) return -1;
+    h->peer = pa;
     const size_t n = (size_t)h->n;
     if (h->ls_Xc.alloc(n * h->kpad) || h->ls_t.alloc(n) || h->ls_ell.alloc(n) || h->ls_ne.alloc(n)) return -1;
   }
@@ -494,7 +517,7 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
     if (launch_rowpass(rp, h->A.ptr, h->list_c.ptr, cnt + 0, n, true, d, r, h->ell_c.ptr, h->Graw_c.ptr, h->ldG, st))
       return -1;
     // gene shards: the per-cell log-likelihoods and gradient blocks are sums over all genes
-    if (allreduce(h, h->ell_c.ptr, (size_t)n) || allreduce(h, h->Graw_c.ptr, (size_t)n * h->ldG)) return -1;
+    if (allreduce2(h, h->Graw_c.ptr, (size_t)n * h->ldG, h->ell_c.ptr, (size_t)n)) return -1;
     if (launch_div_scalar(h->Graw_c.ptr, (long)n * h->ldG, genes_total(h), st)) return -1;
     PrepArgs pa;
     pa.nrows = n;
@@ -673,6 +696,7 @@ extern "C" int ca_gcate_update(ca_gcate_t h, double C, double alpha, double beta
   CA_CUDA(cudaMemcpyAsync(host, h->scal.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CA_CUDA(cudaMemcpyAsync(host + 1, h->tys_total.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CA_CUDA(cudaStreamSynchronize(h->st));
+  if (peer_check(h)) return -1;
   if (func_val) *func_val = nll_from_sum(h, host[0], host[1]);
   return 0;
 }
@@ -860,6 +884,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
     f_pre = f;
   }
   if (t == prm->es_max_iters) t = prm->es_max_iters - 1;  // python's loop variable after exhaustion
+  if (peer_check(h)) return -1;
   auto t1 = std::chrono::steady_clock::now();
   unsigned long long ev[4];
   CA_CUDA(cudaMemcpy(ev, h->evals.ptr, sizeof ev, cudaMemcpyDeviceToHost));

@@ -28,6 +28,7 @@ struct ca_gcate {
   int ldG = 64;
   // gene sharding over ranks (one process per GPU): this handle holds p of p_total genes
   void* comm = nullptr;
+  void* peer = nullptr;              // ca::PeerArena: small reductions over NVLink peer memory (comm.h), or null
   int world = 1, rank = 0;
   long p_total = 0;                  // 0: not sharded (= p)
   DevBuf<double> ls_Xc, ls_t, ls_ell;
