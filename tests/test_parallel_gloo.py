@@ -86,6 +86,10 @@ def _worker_sharded_linalg(rank, world, port, q):
     ok = ok and bool((t == 3.0).all())
     blob = par.broadcast_bytes(b"id-from-rank-0" if rank == 0 else None)
     ok = ok and blob == b"id-from-rank-0"
+    # per-gene result blocks of the sharded LFC, gathered along the gene axis in rank order
+    full = rng.standard_normal((4, p))
+    got = par.allgather_concat(full[:, lo:hi], axis=1)
+    ok = ok and np.array_equal(got, full)
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
