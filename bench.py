@@ -55,7 +55,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="replogle_k562_gcate_lfc_batch", n_ctrl=2000, n_perts=15, cells_per_pert=133, p=8000, r=10,
-                family="nb", es_max_iters=30, es_rel_tol=2e-4, usevar="unequal")
+                family="nb", es_max_iters=30, es_rel_tol=2e-4, usevar="unequal",
+                counts_dtype="int32")     # host storage type of the UMI counts
 
 
 def make_batch(seed, p=None):
@@ -66,7 +67,7 @@ def make_batch(seed, p=None):
                           p=p or w["p"], r=w["r"], d_cov=1, family=w["family"], seed=seed, base_lo=-1.5, base_hi=1.5)
     Y, A = sim["Y"], sim["A"]
     _, _, X, X_A = prep_causarray_data(Y, A)
-    return dict(Y=np.ascontiguousarray(Y), X=X, A=A, X_A=X_A, disp=sim["disp"])
+    return dict(Y=np.ascontiguousarray(Y.astype(w["counts_dtype"])), X=X, A=A, X_A=X_A, disp=sim["disp"])
 
 
 class ClockSampler:
@@ -145,7 +146,7 @@ def cpu_step(batch, n_jobs):
     from oracle import pipeline as op
     w = WORKLOAD
     es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
-    g, l, st = op.gcate_lfc_one_batch_cpu(batch["Y"], batch["X"], batch["A"], batch["X_A"], w["r"],
+    g, l, st = op.gcate_lfc_one_batch_cpu(np.asarray(batch["Y"], dtype=np.float64), batch["X"], batch["A"], batch["X_A"], w["r"],
                                           family=w["family"], disp=batch["disp"], es1=dict(es), es2=dict(es),
                                           usevar=w["usevar"], n_jobs=n_jobs)
     return st
@@ -375,6 +376,7 @@ def main():
            "config": {"workload": w["name"], "n_cells": n, "n_genes": p, "r": w["r"],
                       "perturbations_per_batch": w["n_perts"], "family": w["family"],
                       "batches_per_step_per_gpu": 1, "parallelism": "batch-sharded x%d" % world,
+                      "counts_dtype_host": w["counts_dtype"],
                       "l2_policy": "inputs larger than L2 (Y and Y^T are 256 MB each at fp64)"},
            "e2e": {"value": upd_e2e / t_e2e, "unit": "cell*gene updates/s", "ms_per_step": 1e3 * t_e2e / args.steps,
                    "h2d_bytes_per_step": int(batches[0]["Y"].nbytes + batches[0]["X"].nbytes

@@ -5,6 +5,7 @@
 // convergence masks (:427-438), the L1 objective term (:440) and the adaptive
 // lasso weights (:353).  All reductions use fixed-order trees.
 #include "common.cuh"
+#include <algorithm>
 #include "kernels.h"
 
 namespace ca {
@@ -485,6 +486,27 @@ int launch_adaptive_weights(const double* X, int rows, int kpad, int lo, int hi,
 // (causarray/gcate.py:12-17 and causarray/utils.py:179-219).
 // ---------------------------------------------------------------------------
 namespace ca {
+
+template <typename T>
+__global__ void k_widen_counts(const T* __restrict__ src, long count, double* __restrict__ dst) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = (double)src[i];
+}
+
+int launch_widen_counts(const void* src, int dtype, long count, double* dst, cudaStream_t st) {
+  if (count <= 0) return 0;
+  const unsigned blocks = (unsigned)std::min<long>((count + 255) / 256, 148L * 16);
+  switch (dtype) {
+    case 1: k_widen_counts<<<blocks, 256, 0, st>>>((const float*)src, count, dst); break;
+    case 2: k_widen_counts<<<blocks, 256, 0, st>>>((const int*)src, count, dst); break;
+    case 3: k_widen_counts<<<blocks, 256, 0, st>>>((const long long*)src, count, dst); break;
+    case 4: k_widen_counts<<<blocks, 256, 0, st>>>((const unsigned short*)src, count, dst); break;
+    case 5: k_widen_counts<<<blocks, 256, 0, st>>>((const unsigned char*)src, count, dst); break;
+    default: set_error("launch_widen_counts: element type %d", dtype); return -1;
+  }
+  CA_LAUNCH_CHECK();
+  return 0;
+}
 
 // CSR rows -> dense row-major counts (the destination is zero-filled by the caller); one warp per
 // row, entries with a column index outside [0, p) are ignored

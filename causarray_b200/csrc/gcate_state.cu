@@ -259,6 +259,24 @@ extern "C" int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_
   return finish_upload(h, n_nonint, n_nonfinite, n_empty_genes);
 }
 
+extern "C" int ca_gcate_upload_counts_typed(ca_gcate_t h, const void* Y, int dtype, int64_t* n_nonint,
+                                            int64_t* n_nonfinite, int64_t* n_empty_genes) {
+  CA_REQUIRE(h && Y, "null argument");
+  if (dtype == CA_F64) return ca_gcate_upload_counts(h, (const double*)Y, n_nonint, n_nonfinite, n_empty_genes);
+  static const size_t width[6] = {8, 4, 4, 8, 2, 1};
+  CA_REQUIRE(dtype > 0 && dtype <= CA_U8, "unknown element type");
+  const int n = h->n, p = h->p;
+  const size_t count = (size_t)n * p;
+  if (h->Yraw.alloc(count) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
+  DevBuf<unsigned char> narrow;
+  if (narrow.alloc(count * width[dtype])) return -1;
+  if (h2d_staged(narrow.ptr, Y, count * width[dtype], h->st)) return -1;
+  if (launch_widen_counts(narrow.ptr, dtype, (long)count, h->Yraw.ptr, h->st)) return -1;
+  if (int rc = finish_upload(h, n_nonint, n_nonfinite, n_empty_genes)) return rc;
+  CA_CUDA(cudaStreamSynchronize(h->st));  // the narrow staging copy goes out of scope
+  return 0;
+}
+
 extern "C" int ca_gcate_upload_counts_csr(ca_gcate_t h, const int64_t* indptr, const int32_t* indices, const double* data,
                                           int64_t nnz, int64_t* n_nonint, int64_t* n_nonfinite,
                                           int64_t* n_empty_genes) {

@@ -120,6 +120,8 @@ struct PrepArgs {
 };
 int launch_prep_search(const PrepArgs& a, cudaStream_t st);
 
+// widen a dense count matrix of element type `dtype` (CA_F32 ... CA_U8 of the public header) to FP64
+int launch_widen_counts(const void* src, int dtype, long count, double* dst, cudaStream_t st);
 int launch_csr_expand(const long long* indptr, const int* indices, const double* data, int n, int p, double* Y,
                       cudaStream_t st);
 int launch_compact(const uint8_t* mask, int n, int* list, int* count, cudaStream_t st);

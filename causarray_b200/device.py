@@ -6,6 +6,16 @@ import numpy as np
 from . import _lib as L
 
 
+# element types ca_gcate_upload_counts_typed widens on the device (include/causarray_b200.h)
+_NARROW_DTYPES = {np.dtype(np.float32).str: 1, np.dtype(np.int32).str: 2, np.dtype(np.int64).str: 3,
+                  np.dtype(np.uint16).str: 4, np.dtype(np.uint8).str: 5}
+
+
+def device_dtype(Y):
+    """True when ``Y`` is a dense array the device upload takes without a host cast to float64."""
+    return isinstance(Y, np.ndarray) and (Y.dtype == np.float64 or Y.dtype.str in _NARROW_DTYPES)
+
+
 class GcateDevice:
     """Device-resident GCATE problem (``ca_gcate_t``): S1 seam of SURVEY.md section 8b."""
 
@@ -62,6 +72,11 @@ class GcateDevice:
             L.check(self.lib.ca_gcate_upload_counts_csr(
                 self.h, indptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), L.i32ptr(indices), L.dptr(data),
                 int(data.size), *refs))
+        elif isinstance(Y, np.ndarray) and Y.dtype.str in _NARROW_DTYPES and Y.flags.c_contiguous:
+            # int32 / float32 / ... counts cross the bus as they are and are widened on the device
+            assert Y.shape == (self.n, self.p)
+            L.check(self.lib.ca_gcate_upload_counts_typed(self.h, ctypes.c_void_p(Y.ctypes.data),
+                                                          _NARROW_DTYPES[Y.dtype.str], *refs))
         else:
             Y = L.f64(Y)
             assert Y.shape == (self.n, self.p)

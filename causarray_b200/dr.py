@@ -354,7 +354,10 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         if _glm is None or K != 1 or Y_hat is not None:
             Y = np.asarray(Y.toarray(), dtype=float)
     else:
-        Y = np.asarray(Y).astype(float, copy=False)
+        Y = np.asarray(Y)
+        # (integer / float32 counts whose device copy is at hand need no float64 copy on the host)
+        if _glm is None or K != 1 or Y_hat is not None or Y.dtype.kind not in 'iuf':
+            Y = Y.astype(float, copy=False)
     n, p = Y.shape
     # (_trusted: the counts were already validated on the device when the workspace was uploaded)
     if not _trusted and not np.all(np.isfinite(Y.data if hasattr(Y, "tocsr") else Y)):

@@ -17,7 +17,7 @@ import numpy as np
 import scipy.linalg
 
 from . import glm as _glm_mod
-from .device import GcateDevice, GlmDevice
+from .device import GcateDevice, GlmDevice, device_dtype
 from .svd import topr_svd_device, lowrank_product_svd
 from ._timing import phase
 
@@ -117,7 +117,9 @@ class BatchWorkspace:
 
     def __init__(self, Y, size_factor, disp, family, d, r, thres_disp=100., _defer=False, shard=None):
         if not hasattr(Y, "tocsr"):          # a scipy.sparse matrix is uploaded as CSR
-            Y = np.asarray(Y, dtype=np.float64)
+            Y = np.asarray(Y)
+            if not device_dtype(Y):          # int32 / float32 / ... are widened on the device
+                Y = np.asarray(Y, dtype=np.float64)
         n, p = Y.shape
         self.n, self.p = n, p
         self.gcate = GcateDevice(n, p, d, r, family, thres_disp)

@@ -75,6 +75,13 @@ int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int
  * (_maybe_densify, causarray/nb_glm_fast.py:68-84; causarray/gcate.py:451-470). */
 int ca_gcate_upload_counts_csr(ca_gcate_t h, const int64_t* indptr, const int32_t* indices, const double* data,
                                int64_t nnz, int64_t* n_nonint, int64_t* n_nonfinite, int64_t* n_empty_genes);
+/* Same from a dense matrix of another element type: count matrices usually arrive as int32 /
+ * float32 (AnnData) or small unsigned integers; the reference casts them on the host
+ * (Y.astype(float), causarray/gcate.py:24-36), here the narrow array crosses the bus and is widened
+ * to FP64 on the device.  dtype: CA_F64 0, CA_F32 1, CA_I32 2, CA_I64 3, CA_U16 4, CA_U8 5. */
+enum { CA_F64 = 0, CA_F32 = 1, CA_I32 = 2, CA_I64 = 3, CA_U16 = 4, CA_U8 = 5 };
+int ca_gcate_upload_counts_typed(ca_gcate_t h, const void* Y, int dtype, int64_t* n_nonint, int64_t* n_nonfinite,
+                                 int64_t* n_empty_genes);
 int ca_gcate_size_factor_medians(ca_gcate_t h, double* log_sf);
 int ca_gcate_prepare(ca_gcate_t h, const double* size_factor, const double* nu);
 /* Same, for callers of update_with_mask that already hold the normalised Y
