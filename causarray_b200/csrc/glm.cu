@@ -60,6 +60,8 @@ struct GlmSolve {
   double* beta;
   int iter;
   double tol;
+  double* step;          // p: relative size of the gene's last coefficient update (lasso refit)
+  double steptol;        // lasso refit: also require step <= steptol (see the convergence test)
   int finalize;          // only the deviance
   int* n_active;
 };
@@ -106,7 +108,10 @@ __global__ void k_glm_solve(GlmSolve Q) {
         Q.status[gene] = 2;
         Q.n_iter[gene] = Q.iter - 1;
       }
-    } else if (Q.iter > 1 && fabs(dev - prev) <= Q.tol) {
+    } else if (Q.iter > 1 && fabs(dev - prev) <= Q.tol && (!Q.l1 || Q.step[gene] <= Q.steptol)) {
+      // (lasso refit: the penalised objective is flat along the weakly identified columns -- a change
+      // of 1e-8 in it still leaves their coefficients 1e-4 from the minimiser -- so the refit also
+      // waits for the update itself to become small)
       run = false;
       if (lane == 0) {
         Q.status[gene] = 1;
@@ -360,10 +365,17 @@ __global__ void k_glm_solve(GlmSolve Q) {
     }
   }
   bool fin = true;
+  double stepmax = 0.0;
   for (int i = lane; i < kx; i += 32) {
     const double v = b[i] * sc[i];
+    const double old = Q.beta[(size_t)gene * kx + i];
+    stepmax = fmax(stepmax, fabs(v - old) / (1.0 + fabs(v)));
     Q.beta[(size_t)gene * kx + i] = v;
     fin = fin && (v == v) && !isinf(v);
+  }
+  if (Q.l1) {
+    for (int o = 16; o > 0; o >>= 1) stepmax = fmax(stepmax, __shfl_xor_sync(0xffffffffu, stepmax, o));
+    if (lane == 0) Q.step[gene] = stepmax;
   }
   fin = __all_sync(0xffffffffu, fin);
   if (!fin && lane == 0) {
@@ -681,7 +693,7 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   const int kxi = lay.kxi;
   const int ldx = 8 * ((kxi + 7) / 8) + 4;
   if (h->X.alloc((size_t)n * ldx) || h->beta.alloc((size_t)p * kx) || h->ybar.alloc(p) || h->cst.alloc((size_t)p * 3) ||
-      h->dev.alloc(p) || h->dev_prev.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
+      h->dev.alloc(p) || h->dev_prev.alloc(p) || h->step.alloc(p) || h->status.alloc(p) || h->n_iter.alloc(p) ||
       h->part.alloc((size_t)p * (kxi * kxi + kxi + 4)) || h->mu_t.alloc((size_t)p * h->ldn) ||
       h->counter.alloc(2) || h->offset.alloc((size_t)n + 8) || h->nu.alloc(p) || h->ridge.alloc(2 * kx))
     return -1;
@@ -777,6 +789,8 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   Q.cst = h->cst.ptr;
   Q.dev = h->dev.ptr;
   Q.dev_prev = h->dev_prev.ptr;
+  Q.step = h->step.ptr;
+  Q.steptol = 1e-8;
   Q.status = h->status.ptr;
   Q.n_iter = h->n_iter.ptr;
   Q.beta = h->beta.ptr;

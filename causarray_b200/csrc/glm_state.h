@@ -11,7 +11,7 @@ struct ca_glm {
   ca::DevBuf<double> Yraw_own, Yt_own;
   const double* Yraw = nullptr;  // n x p cell-major raw counts
   const double* Yt = nullptr;    // p x ldn gene-major raw counts
-  ca::DevBuf<double> X, beta, ybar, cst, dev, dev_prev, part, mu_t, offset, nu, ridge, resid;
+  ca::DevBuf<double> X, beta, ybar, cst, dev, dev_prev, step, part, mu_t, offset, nu, ridge, resid;
   ca::DevBuf<int> status, n_iter, counter, genelist;
   bool has_offset = false, has_nu = false;
   int family = 0;

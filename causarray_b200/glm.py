@@ -80,7 +80,7 @@ def _device_fit(dev, Xf, family, offsets, disp, thres_disp, maxiter, d_guard, al
     if bad.any():
         const = np.all(Xf == Xf[0, :], axis=0)
         l1 = np.where(const, 0.0, alpha * n)
-        B2, dv2, it2, st2 = dev.refit_l1(fam, Xf, l1, bad, offset=offsets, nu=nu, thres_disp=thres_disp, maxiter=100,
+        B2, dv2, it2, st2 = dev.refit_l1(fam, Xf, l1, bad, offset=offsets, nu=nu, thres_disp=thres_disp, maxiter=200,
                                          tol=1e-8)
         still = bad & (st2 != 0)
         B = B2

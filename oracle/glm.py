@@ -159,7 +159,7 @@ def _lasso_quadratic(G, r, pen, b_start):
     return b
 
 
-def lasso_glm(y, X, offset, alpha_nb, pen, tol=1e-12, maxiter=500):
+def lasso_glm(y, X, offset, alpha_nb, pen, tol=1e-12, maxiter=500, step_tol=1e-11):
     """Minimiser of ``-loglike(b) / n + sum_k pen_k |b_k|`` for the log-link Poisson (``alpha_nb`` None)
     or NB2 (``var = mu + alpha_nb mu^2``) GLM, by proximal IRLS: each step minimises the weighted
     least-squares model plus the L1 term exactly (``_lasso_quadratic``)."""
@@ -177,11 +177,15 @@ def lasso_glm(y, X, offset, alpha_nb, pen, tol=1e-12, maxiter=500):
         z = eta + (y - mu) / mu - off
         G = X.T @ (w[:, None] * X)
         r = X.T @ (w * z)
+        beta_prev = beta
         beta = _lasso_quadratic(G, r, pen, beta)
         eta = X @ beta + off
         mu = np.exp(eta)
         obj = 0.5 * np.sum(unit_deviance(y, mu, alpha_nb)) + np.sum(pen * np.abs(beta))
-        if abs(obj - obj_prev) <= tol * max(1.0, abs(obj)):
+        # the objective is flat along weakly identified columns (a relative change of 1e-10 still
+        # leaves their coefficients ~1e-4 from the minimiser): also wait for the update to vanish
+        step = np.inf if beta_prev is None else np.max(np.abs(beta - beta_prev) / (1.0 + np.abs(beta)))
+        if abs(obj - obj_prev) <= tol * max(1.0, abs(obj)) and step <= step_tol:
             break
         obj_prev = obj
     return beta, mu
