@@ -735,6 +735,7 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
     CA_CUDA(cudaMemsetAsync(h->n_iter.ptr, 0, h->n_iter.bytes(), st));
   }
   CA_CUDA(cudaMemsetAsync(h->dev_prev.ptr, 0, h->dev_prev.bytes(), st));
+  CA_CUDA(cudaMemsetAsync(h->step.ptr, 0x7f, h->step.bytes(), st));  // "large": expected-information weights first
   h->has_offset = offset != nullptr;
   h->family = family;
   h->thres = thres_disp;
@@ -768,6 +769,7 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   P.genelist = nullptr;
   P.n_list = 0;
   P.fm_tables = fastmath_tables();
+  P.newton_step = l1 ? h->step.ptr : nullptr;
   CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   if (h->genelist.alloc(p)) return -1;
   const int solve_warps = 4;

@@ -49,6 +49,9 @@ struct GlmPass {
   const int* genelist;   // compacted list of running genes (nullptr = all genes)
   int n_list;            // entries of genelist
   const double* fm_tables;
+  const double* newton_step;  // lasso refit only (else nullptr): relative size of each gene's last update;
+                              // once it is below 1e-2 the NB weights switch from expected to observed
+                              // information (same minimiser, quadratic instead of linear convergence)
 };
 
 inline size_t glm_pass_smem_bytes(int nt) {
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
     nu = P.nu[gene];
     pois = nu > P.thres;
   }
+  const bool newton = NB && !FIRST && !FIN && gene_ok && !pois && P.newton_step && P.newton_step[gene] <= 1e-2;
   const double ybar = gene_ok ? P.ybar[gene] : 1.0;
   const int rot0 = lane % NT8;
   const double* yrow = P.Yt + (size_t)(gene_ok ? gene : 0) * P.ldn;
@@ -193,6 +197,13 @@ __global__ void __launch_bounds__(GLM_THREADS, (NT <= 5 ? 2 : 1)) k_glm_pass(Glm
           const double z = eta + (y - mu) * fm_rcp(mu) - off;
           w = okf * wv;
           wz = w * z;
+          if (NB && newton) {
+            // -d score / d eta of the NB2 log-likelihood: nu mu (nu + y) / (nu + mu)^2; rhs = w (eta - off) + score
+            const double rc = fm_rcp(nu + mu);
+            const double wn = mu * nu * rc * ((nu + y) * rc);
+            w = okf * wn;
+            wz = okf * fma(wn, eta - off, (y - mu) * (nu * rc));
+          }
         }
       };
       // ---- Gram / rhs accumulation of block b on the FP64 tensor cores ----
