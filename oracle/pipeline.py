@@ -194,7 +194,9 @@ def lfc_cpu(Y, W, A, W_A, family, offset, usevar="unequal", disp=None, n_jobs=1,
         _, _, _, itp, mu_p = fit_glm_parallel(Y, Xf, None, "poisson", None, offset, maxiter=1000, n_jobs=n_jobs)
         disp = og.estimate_disp_moments(Y, mu_p, offset)
         it_sum += int(itp.sum())
-    B, _, status, itn, _ = fit_glm_parallel(Y, Xf, None, family, disp, offset, maxiter=1000, n_jobs=n_jobs)
+    # (treatments passed separately: their coefficients carry the tighter guard |beta| > 10 of
+    # gcate_glm.py:205, as in the reference's cross_fitting -> fit_glm(Y, X, A) call)
+    B, _, status, itn, _ = fit_glm_parallel(Y, W, A, family, disp, offset, maxiter=1000, n_jobs=n_jobs)
     it_sum += int(itn.sum())
     stats["t_glm_lfc"] = time.perf_counter() - t0
     stats["irls_gene_iters"] = stats.get("irls_gene_iters", 0) + it_sum

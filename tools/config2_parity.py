@@ -46,7 +46,6 @@ def main():
     off = np.log(r2["kwargs_glm"]["size_factor"])
     df, _ = cb.LFC(Y, np.c_[X, r2["U"]], pd.DataFrame(A), np.c_[X_A, r2["U"]], family="nb", offset=off,
                    usevar="unequal", _glm=ws.glm, _trusted=True)
-    ws.close()
     t_gpu = time.perf_counter() - t0
     cores = os.cpu_count() or 1
     cport.set_threads(cores)
@@ -99,6 +98,30 @@ def main():
     Bg_, Bc_ = r2["B_Gamma"], g["B_Gamma"]
     d_ = X.shape[1] + a
     out["B_trt_max_abs_diff"] = float(np.abs(Bg_[:, X.shape[1]:d_] - Bc_[:, X.shape[1]:d_]).max())
+    # the pairs above 1e-8: which genes, and does the outcome GLM of those genes stop at the same
+    # iteration on both sides?  (same design, offset and dispersion on both sides: the oracle's)
+    from causarray_b200 import glm as cglm
+    worst = np.zeros((a, p), dtype=bool)
+    worst[fin] = rt > 1e-8
+    wg = np.where(worst.any(axis=0))[0]
+    out["genes_with_pairs_above_1e-8"] = [int(j) for j in wg[:20]]
+    out["pairs_above_1e-8"] = int(worst.sum())
+    Wc = np.c_[X, g["U"]]
+    offc = np.log(g["size_factor"])
+    Bg2, fit2, _, _, _ = cglm.fit_glm(Y, np.c_[Wc, A], offset=offc, family="nb", disp_glm=l["disp"], maxiter=1000,
+                                      _glm=ws.glm, _lazy=True)
+    itg = np.asarray(fit2.n_iter)
+    Bc2, _, stc, itc, _ = op.fit_glm_parallel(Y, np.c_[Wc, A], None, "nb", l["disp"], offc, maxiter=1000, n_jobs=cores)
+    okg = (~np.asarray(fit2.refit_mask)) & (stc == 0)
+    diff_it = okg & (itg != itc)
+    out["outcome_glm_iter_mismatch_genes"] = [int(j) for j in np.where(diff_it)[0][:20]]
+    out["outcome_glm_iter_mismatch_count"] = int(diff_it.sum())
+    out["outcome_glm_B_abs_max_same_iters"] = float(np.abs(Bg2[okg & ~diff_it] - Bc2[okg & ~diff_it]).max())
+    if diff_it.any():
+        out["outcome_glm_B_abs_max_mismatch"] = float(np.abs(Bg2[diff_it] - Bc2[diff_it]).max())
+        out["outcome_glm_iters_mismatch"] = [[int(itg[j]), int(itc[j])] for j in np.where(diff_it)[0][:20]]
+    out["worst_genes_are_iter_mismatch_genes"] = bool(set(wg.tolist()) <= set(np.where(diff_it)[0].tolist()))
+    ws.close()
     print(json.dumps(out))
 
 
