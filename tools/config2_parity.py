@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--ctrl", type=int, default=800)
     ap.add_argument("--r", type=int, default=5)
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--label", default="C2")
     args = ap.parse_args()
     warnings.simplefilter("ignore")
     import causarray_b200 as cb
@@ -34,7 +36,7 @@ def main():
     from causarray_b200.prep import prep_causarray_data
     from oracle import pipeline as op, cport
     sim = simulate_screen(n_ctrl=args.ctrl, n_perts=args.perts, cells_per_pert=args.cells, p=args.p, r=args.r, d_cov=1,
-                          family="nb", seed=2, base_lo=-1.5, base_hi=1.5)
+                          family="nb", seed=args.seed, base_lo=-1.5, base_hi=1.5)
     Y, A = sim["Y"], sim["A"]
     _, _, X, X_A = prep_causarray_data(Y, A)
     n, p = Y.shape
@@ -63,7 +65,7 @@ def main():
     rt, rs = rel(tau_g[fin], tau_c[fin]), rel(std_g[fin], std_c[fin])
     rej_g, rej_c = padj_g < 0.05, padj_c < 0.05
     out = {
-        "config": "C2", "n": n, "p": p, "a": a, "r": args.r, "k": int(r2["X_U"].shape[1]),
+        "config": args.label, "n": n, "p": p, "a": a, "r": args.r, "k": int(r2["X_U"].shape[1]),
         "gpu_seconds": round(t_gpu, 3), "cpu_seconds": round(t_cpu, 1), "cpu_cores": cores,
         "iters_gpu": [len(r1["hist"]) - 1, len(r2["hist"]) - 1], "iters_cpu": [len(g["hist1"]) - 1, len(g["hist2"]) - 1],
         "pairs_compared": int(fin.sum()), "pairs_total": int(a * p),
