@@ -183,3 +183,20 @@ def test_host_inference_helpers_match_numpy():
     med, mad = inf._median_mad_rows(t)
     np.testing.assert_allclose(med, np.nanmedian(t, axis=1), rtol=0, atol=0)
     np.testing.assert_allclose(mad, np.nanmedian(np.abs(t - med[:, None]), axis=1) / inf._MAD_NORMAL, rtol=1e-15)
+
+
+def test_typed_upload_codes_match_header():
+    """The element-type codes the Python layer passes to ca_gcate_upload_counts_typed are the header's."""
+    import os
+    import re
+    import numpy as np
+    from causarray_b200.device import _NARROW_DTYPES, device_dtype
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "causarray_b200.h")).read()
+    m = re.search(r"enum\s*\{([^}]*CA_F64[^}]*)\}", hdr)
+    codes = {k.strip(): int(v) for k, v in (kv.split("=") for kv in m.group(1).split(","))}
+    want = {"CA_F32": np.float32, "CA_I32": np.int32, "CA_I64": np.int64, "CA_U16": np.uint16, "CA_U8": np.uint8}
+    assert codes["CA_F64"] == 0
+    for name, t in want.items():
+        assert _NARROW_DTYPES[np.dtype(t).str] == codes[name]
+    assert device_dtype(np.zeros((2, 2), dtype=np.int32)) and device_dtype(np.zeros((2, 2)))
+    assert not device_dtype(np.zeros((2, 2), dtype=np.int16)) and not device_dtype([[1, 2]])
