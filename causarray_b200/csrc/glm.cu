@@ -34,6 +34,7 @@
 #include "prof.h"
 #include "fastmath.cuh"
 #include "glm_pass_impl.cuh"
+#include "glm_solve.cuh"
 
 namespace ca {
 
@@ -130,14 +131,10 @@ __global__ void k_glm_solve(GlmSolve Q) {
   // ---- normal equations ----
   const int ld = kx + 1;
   // (the lasso refit keeps a second copy of the system; plain fits do not pay its shared memory)
-  double* L = sm + (size_t)warp * (kx * ld + 3 * kx + (Q.l1 ? kx * ld + 3 * kx : 0));
-  double* sc = L + kx * ld;
-  double* b = sc + kx;
-  double* invd = b + kx;  // reciprocals of the Cholesky diagonal
-  double* Gc = invd + kx; // lasso refit: copy of the scaled Gram matrix (the factorisation is in place)
-  double* b0 = Gc + kx * ld;
-  double* t2 = b0 + kx;
-  double* zf = t2 + kx;   // 1.0 where the coefficient is held at zero
+  const GlmSolveWork W = glm_solve_carve(sm + (size_t)warp * glm_solve_work_doubles(kx, Q.l1 != nullptr), kx);
+  double* L = W.L;
+  double* sc = W.sc;
+  double* b = W.b;
   {
     // fixed summation order over the splits; a lane walks the flat index e = i * kx + j in steps of
     // 32 (row / column tracked incrementally: no division) and keeps 2 x nsplit loads in flight
@@ -192,177 +189,13 @@ __global__ void k_glm_solve(GlmSolve Q) {
     b[i] = r;
   }
   __syncwarp();
-  bool bad = false;
-  for (int i = lane; i < kx; i += 32) {
-    const double dgn = L[i * ld + i];
-    sc[i] = dgn > 0.0 ? rsqrt(dgn) : 0.0;
-    if (!(dgn > 0.0)) bad = true;
-  }
-  __syncwarp();
-  // Jacobi scaling, one matrix row per lane
-  for (int i = lane; i < kx; i += 32) {
-    const double si = sc[i];
-    for (int j = 0; j <= i; ++j) L[i * ld + j] *= si * sc[j];
-    b[i] *= si;
-    if (Q.l1) {
-      for (int j = 0; j <= i; ++j) Gc[i * ld + j] = L[i * ld + j];
-      b0[i] = b[i];
-    }
-  }
-  __syncwarp();
-  if (Q.l1) {  // mirror: the coordinate descent below reads full rows
-    for (int i = lane; i < kx; i += 32)
-      for (int j = 0; j < i; ++j) Gc[j * ld + i] = Gc[i * ld + j];
-    __syncwarp();
-  }
-  // Right-looking Cholesky of the lower triangle, one matrix ROW per lane (rows lane and lane + 32):
-  // the trailing update of row i is a run of FMAs over its columns with no index arithmetic (the
-  // first version walked the trailing block as a flat index with a division and a modulo per
-  // element and took 80 us per 26 x 26 system -- most of an IRLS tail iteration).
-  // ld = kx + 1 is odd, so the row-per-lane accesses are bank-conflict free.
-  auto factor = [&]() {
-    bool sing = false;
-    for (int j = 0; j < kx; ++j) {
-      const double djj = L[j * ld + j];
-      if (!(djj > 1e-13)) sing = true;
-      const double inv = rsqrt(djj > 1e-300 ? djj : 1e-300);
-      if (lane == 0) invd[j] = inv;
-      for (int i = lane; i < kx; i += 32)
-        if (i >= j) L[i * ld + j] *= inv;
-      __syncwarp();
-      for (int i = lane; i < kx; i += 32)
-        if (i > j) {
-          const double lij = L[i * ld + j];
-          double* Li = L + i * ld;
-          const double* Lj = L + j;
-          int c = j + 1;
-          for (; c + 3 <= i; c += 4) {  // four independent updates in flight
-            const double a0 = Lj[c * ld], a1 = Lj[(c + 1) * ld], a2 = Lj[(c + 2) * ld], a3 = Lj[(c + 3) * ld];
-            const double r0 = Li[c], r1 = Li[c + 1], r2 = Li[c + 2], r3 = Li[c + 3];
-            Li[c] = fma(-lij, a0, r0);
-            Li[c + 1] = fma(-lij, a1, r1);
-            Li[c + 2] = fma(-lij, a2, r2);
-            Li[c + 3] = fma(-lij, a3, r3);
-          }
-          for (; c <= i; ++c) Li[c] = fma(-lij, Lj[c * ld], Li[c]);
-        }
-      __syncwarp();
-    }
-    return sing;
-  };
-  if (factor()) bad = true;
-  bad = __any_sync(0xffffffffu, bad);
-  if (bad) {
+  if (glm_solve_system(W, kx, Q.l1, lane)) {
     if (lane == 0) {
       Q.status[gene] = 2;
       Q.n_iter[gene] = Q.iter;
       atomicAdd(Q.n_active, -1);
     }
     return;
-  }
-  // column-oriented forward / backward substitution: lane i owns v[i]; the diagonal enters through
-  // its stored reciprocal (after the scaled column the diagonal entry of L is djj * inv = 1 / inv)
-  auto substitute = [&](double* v) {
-    for (int j = 0; j < kx; ++j) {
-      const double yj = v[j] * invd[j];
-      __syncwarp();
-      for (int i = lane; i < kx; i += 32) {
-        if (i > j)
-          v[i] = fma(-L[i * ld + j], yj, v[i]);
-        else if (i == j)
-          v[i] = yj;
-      }
-      __syncwarp();
-    }
-    for (int j = kx - 1; j >= 0; --j) {
-      const double xj = v[j] * invd[j];
-      __syncwarp();
-      for (int i = lane; i < kx; i += 32) {
-        if (i < j)
-          v[i] = fma(-L[j * ld + i], xj, v[i]);
-        else if (i == j)
-          v[i] = xj;
-      }
-      __syncwarp();
-    }
-  };
-  substitute(b);
-  if (Q.l1) {
-    // Lasso step of the penalised IRLS (glmnet form): minimise the quadratic model
-    //   1/2 b^T G b - r^T b + sum_k l1_k |b_k|
-    // on the (scaled) kx x kx system.  Its fixed point over the IRLS iterations is the minimiser of
-    // -loglike / n + sum_k alpha_k |beta_k|, the objective of statsmodels' fit_regularized
-    // (elastic net with L1_wt = 1) that causarray/gcate_glm.py:209 falls back to.
-    // Active-set rounds: with a sign pattern s (0 = coefficient held at zero) the optimality system is
-    //   G_AA b_A = r_A - l1_A s_A,  b_Z = 0;
-    // it is solved with the rows / columns of Z replaced by the identity, then checked: an active
-    // coefficient whose sign came out wrong joins Z, a zero coefficient whose gradient exceeds its
-    // weight rejoins A.  The unpenalised solution supplies the first pattern; one or two rounds
-    // settle it.  Fallback (pattern still moving after 6 rounds): cyclic coordinate descent.
-    double sg[2] = {0.0, 0.0};   // pattern of the (up to two) coordinates this lane owns
-    for (int i = lane, q = 0; i < kx; i += 32, ++q) {
-      const double lam = Q.l1[i] * sc[i];
-      sg[q] = b[i] > 0.0 ? 1.0 : (b[i] < 0.0 ? -1.0 : 0.0);
-      if (lam == 0.0) sg[q] = 2.0;  // unpenalised coordinate: always active, no sign constraint
-    }
-    bool settled = false;
-    for (int round = 0; round < 6 && !settled; ++round) {
-      for (int i = lane, q = 0; i < kx; i += 32, ++q) {
-        const double lam = Q.l1[i] * sc[i];
-        zf[i] = sg[q] == 0.0 ? 1.0 : 0.0;
-        t2[i] = sg[q] == 0.0 ? 0.0 : b0[i] - (sg[q] == 2.0 ? 0.0 : lam * sg[q]);
-      }
-      __syncwarp();
-      for (int i = lane; i < kx; i += 32)
-        for (int j = 0; j <= i; ++j)
-          L[i * ld + j] = (zf[i] != 0.0 || zf[j] != 0.0) ? (i == j ? 1.0 : 0.0) : Gc[i * ld + j];
-      __syncwarp();
-      factor();
-      substitute(t2);
-      bool chg = false;
-      for (int i = lane, q = 0; i < kx; i += 32, ++q) {
-        const double lam = Q.l1[i] * sc[i];
-        if (sg[q] == 2.0) continue;
-        if (sg[q] != 0.0) {
-          if (!((t2[i] > 0.0 && sg[q] > 0.0) || (t2[i] < 0.0 && sg[q] < 0.0))) {
-            sg[q] = 0.0;
-            chg = true;
-          }
-        } else {
-          double gdot = 0.0;
-          for (int j = 0; j < kx; ++j) gdot += Gc[i * ld + j] * t2[j];
-          const double res = b0[i] - gdot;
-          if (fabs(res) > lam * (1.0 + 1e-12)) {
-            sg[q] = res > 0.0 ? 1.0 : -1.0;
-            chg = true;
-          }
-        }
-      }
-      settled = !__any_sync(0xffffffffu, chg);
-    }
-    for (int i = lane; i < kx; i += 32) b[i] = t2[i];
-    __syncwarp();
-    if (!settled) {
-      for (int sweep = 0; sweep < 2000; ++sweep) {
-        double maxchg = 0.0, maxabs = 0.0;
-        for (int k = 0; k < kx; ++k) {
-          double part = 0.0;
-          for (int j = lane; j < kx; j += 32) part += Gc[k * ld + j] * b[j];
-          part = warp_sum(part);
-          const double gkk = Gc[k * ld + k], old = b[k];
-          const double r = b0[k] - (part - gkk * old);
-          const double lam = Q.l1[k] * sc[k];
-          const double mag = fabs(r) - lam;
-          const double nw = mag > 0.0 ? (r > 0.0 ? mag : -mag) / gkk : 0.0;
-          __syncwarp();
-          if (lane == 0) b[k] = nw;
-          __syncwarp();
-          maxchg = fmax(maxchg, fabs(nw - old));
-          maxabs = fmax(maxabs, fabs(nw));
-        }
-        if (maxchg <= 1e-11 * (1.0 + maxabs)) break;
-      }
-    }
   }
   bool fin = true;
   double stepmax = 0.0;
@@ -542,6 +375,10 @@ static int launch_pass(const GlmPass& P, cudaStream_t st) {
 }
 
 int kpad_for(int k);
+
+int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* offset, int family, double thres,
+                 bool has_nu, bool has_ridge, bool lasso, double tol, int maxiter, bool warm, const int* genelist_dev,
+                 int n_list);
 
 // Internal column layout of the pass kernel.  A contiguous block of design columns of which every
 // cell has at most one non-zero entry (one-hot treatment indicators, causarray/DR_learner.py builds
@@ -740,9 +577,36 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   h->family = family;
   h->thres = thres_disp;
   h->has_nu = (nu != nullptr) && family == CA_FAMILY_NB;
+  h->lay_kxi = kxi;
+  h->lay_t0 = lay.t0;
+  memcpy(h->lay_cmap, lay.cmap, sizeof h->lay_cmap);
+  h->mu_valid = false;
+  if (h->genelist.alloc(p)) return -1;
+  // ---- persistent per-octet IRLS (glm_irls_impl.cuh): one launch for the whole fit ----
+  bool done = false;
+  {
+    IrlsPlan ip;
+    if (plan_irls(X, n, kx, ip)) {
+      int nlist = 0;
+      if (gene_mask) {
+        k_glm_active_list<<<1, 1024, 0, st>>>(h->status.ptr, p, h->genelist.ptr, h->counter.ptr + 1);
+        CA_LAUNCH_CHECK();
+        CA_CUDA(cudaMemcpyAsync(&nlist, h->counter.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CA_CUDA(cudaStreamSynchronize(st));
+      }
+      const int rc = (gene_mask && nlist == 0)
+                         ? 0
+                         : glm_fit_irls(h, ip, X, offset, family, thres_disp, h->has_nu, ridge != nullptr, l1 != nullptr,
+                                        tol, maxiter, warm, gene_mask ? h->genelist.ptr : nullptr, nlist);
+      if (rc < 0) return rc;
+      done = rc == 0;
+    }
+  }
+  if (!done) {
   k_glm_consts<<<p, 256, 0, st>>>(h->Yt, h->ldn, n, h->has_nu ? h->nu.ptr : nullptr, family, thres_disp, h->ybar.ptr,
                                   h->cst.ptr);
   CA_LAUNCH_CHECK();
+  }
   GlmPass P;
   P.Yt = h->Yt;
   P.ldn = h->ldn;
@@ -771,7 +635,6 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   P.fm_tables = fastmath_tables();
   P.newton_step = l1 ? h->step.ptr : nullptr;
   CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
-  if (h->genelist.alloc(p)) return -1;
   const int solve_warps = 4;
   const size_t solve_sm =
       sizeof(double) * solve_warps * ((size_t)kx * (kx + 1) + 3 * kx + (l1 ? (size_t)kx * (kx + 1) + 3 * kx : 0));
@@ -815,7 +678,7 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   };
   int iters_done = 0;
   int nrun = p;  // genes still running (gene_mask refits start from the flagged subset)
-  for (int it = 1; it <= maxiter; ++it) {
+  for (int it = 1; it <= maxiter && !done; ++it) {
     // pass `it` accumulates, per running gene, the deviance terms at the current beta and the
     // normal equations of update `it`; the solve kernel then applies the convergence test of
     // update it-1 and, for genes that keep running, performs update `it`
@@ -858,19 +721,22 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
     nrun = nact;
     iters_done = it;
   }
-  // finalize: fitted means + deviance at the final beta for every gene
-  P.genelist = nullptr;
-  P.n_list = 0;
-  P.nsplit = 1;
-  P.finalize = 1;
-  P.iter = 2;  // never "first" in finalize
-  P.mu_t = h->mu_t.ptr;
-  if (launch_pass(P, st)) return -1;
-  Q.genelist = nullptr;
-  Q.nslots = p;
-  Q.nsplit = 1;
-  Q.finalize = 1;
-  if (launch_solve(p)) return -1;
+  if (!done) {
+    // finalize: fitted means + deviance at the final beta for every gene
+    P.genelist = nullptr;
+    P.n_list = 0;
+    P.nsplit = 1;
+    P.finalize = 1;
+    P.iter = 2;  // never "first" in finalize
+    P.mu_t = h->mu_t.ptr;
+    if (launch_pass(P, st)) return -1;
+    Q.genelist = nullptr;
+    Q.nslots = p;
+    Q.nsplit = 1;
+    Q.finalize = 1;
+    if (launch_solve(p)) return -1;
+    h->mu_valid = true;
+  }
   h->iters_done = iters_done;
   // genes still "running" after maxiter updates: n_iter = maxiter
   if (d_guard >= 0) {
@@ -895,8 +761,50 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
   return 0;
 }
 
+// Fitted means of the last fit, computed on demand (the persistent IRLS kernel does not write them:
+// only the residuals of the first initialisation fit and the dispersion estimate need them).
+static int glm_ensure_mu(ca_glm_t h) {
+  if (h->mu_valid) return 0;
+  CA_REQUIRE(h->fit_kx > 0 && h->X.ptr && h->beta.ptr, "fit first");
+  const int kxi = h->lay_kxi;
+  GlmPass P;
+  memset(&P, 0, sizeof P);
+  P.Yt = h->Yt;
+  P.ldn = h->ldn;
+  P.n = h->n;
+  P.p = h->p;
+  P.X = h->X.ptr;
+  P.kx = h->fit_kx;
+  P.ldx = 8 * ((kxi + 7) / 8) + 4;
+  P.kxi = kxi;
+  memcpy(P.cmap, h->lay_cmap, sizeof P.cmap);
+  P.t0 = h->lay_t0;
+  P.offset = h->offset.ptr;
+  P.nu = h->has_nu ? h->nu.ptr : nullptr;
+  P.family = h->family;
+  P.thres = h->thres;
+  P.beta = h->beta.ptr;
+  P.ybar = h->ybar.ptr;
+  P.status = h->status.ptr;
+  P.part = h->part.ptr;
+  P.part_ld = kxi * kxi + kxi + 4;
+  P.nsplit = 1;
+  P.mu_t = h->mu_t.ptr;
+  P.iter = 2;
+  P.finalize = 1;
+  P.genelist = nullptr;
+  P.n_list = 0;
+  P.fm_tables = fastmath_tables();
+  P.newton_step = nullptr;
+  CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
+  if (launch_pass(P, h->st)) return -1;
+  h->mu_valid = true;
+  return 0;
+}
+
 extern "C" int ca_glm_resid(ca_glm_t h, double* resid) {
   CA_REQUIRE(h && h->mu_t.ptr && resid, "fit first");
+  if (glm_ensure_mu(h)) return -1;
   const int n = h->n, p = h->p;
   DevBuf<double> out;
   if (out.alloc((size_t)n * p)) return -1;
@@ -911,6 +819,7 @@ extern "C" int ca_glm_resid(ca_glm_t h, double* resid) {
 
 extern "C" int ca_glm_resid_device(ca_glm_t h, void** dev_ptr) {
   CA_REQUIRE(h && h->mu_t.ptr && dev_ptr, "fit first");
+  if (glm_ensure_mu(h)) return -1;
   const int n = h->n, p = h->p;
   if (h->resid.alloc((size_t)n * p)) return -1;
   dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
@@ -924,6 +833,7 @@ extern "C" int ca_glm_resid_device(ca_glm_t h, void** dev_ptr) {
 
 extern "C" int ca_glm_fitted(ca_glm_t h, double* mu) {
   CA_REQUIRE(h && h->mu_t.ptr && mu, "fit first");
+  if (glm_ensure_mu(h)) return -1;
   const int n = h->n, p = h->p;
   DevBuf<double> out;
   if (out.alloc((size_t)n * p)) return -1;
@@ -935,6 +845,7 @@ extern "C" int ca_glm_fitted(ca_glm_t h, double* mu) {
 
 extern "C" int ca_glm_disp_moments(ca_glm_t h, const double* offset, double* disp) {
   CA_REQUIRE(h && h->mu_t.ptr && disp, "fit first");
+  if (glm_ensure_mu(h)) return -1;
   const int n = h->n, p = h->p;
   DevBuf<double> off, out;
   if (out.alloc(p)) return -1;
