@@ -152,41 +152,90 @@ def cpu_step(batch, n_jobs):
     return st
 
 
-def run_reference(args, rank, world):
-    """CPU arm: rank 0 only; bounded sample = gene subsample of the same batch shape."""
-    if rank != 0:
-        return
-    from oracle import cport
+def reference_step(batch):
+    """One batch through the REAL reference (staged oracle/_ref: numba alternating minimisation, the
+    reference's own fit_gcate / LFC; per-gene GLM through the statsmodels stand-in)."""
+    from oracle import refdrive
+    w = WORKLOAD
+    es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
+    res1, res2, df, est, st = refdrive.reference_fit_gcate_lfc(batch["Y"], batch["X"], batch["A"], batch["X_A"], w["r"],
+                                                               family=w["family"], disp=batch["disp"], es1=dict(es),
+                                                               es2=dict(es), usevar=w["usevar"])
+    return st
+
+
+def reference_arm(steps, warmup, p_s, kind):
+    """Times the CPU implementation of the step on this box's host cores on a gene subsample of the
+    same batch shape.  kind = "reference": the unmodified reference package (numba JIT warmed up
+    first, excluded from the timing); kind = "port": the C/OpenMP + numpy restatement of oracle/."""
     cores = os.cpu_count() or 1
-    cport.set_threads(cores)
-    p_s = args.cpu_genes
+    w = WORKLOAD
+    n = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
+    jit_s = None
+    if kind == "reference":
+        os.environ.setdefault("NUMBA_NUM_THREADS", str(cores))
+        from oracle import refdrive
+        jit_s = refdrive.warm_up_jit(w["family"])
+        step = reference_step
+        how = ("unmodified reference package (oracle/_ref): numba update_with_mask on %d threads, fit_glm over joblib "
+               "workers (n_jobs=-3) with the statsmodels stand-in of oracle/shims, its own LFC" % cores)
+    else:
+        from oracle import cport
+        cport.set_threads(cores)
+        step = lambda b: cpu_step(b, cores)
+        how = ("C/OpenMP restatement of the alternating iteration (%d threads) + per-gene numpy IRLS over %d processes"
+               % (cores, cores))
     times, upd = [], []
     stats = None
-    for s in range(args.warmup + args.steps):
+    for s in range(warmup + steps):
         batch = make_batch(1000 + s, p=p_s)
         t0 = time.perf_counter()
-        stats = cpu_step(batch, cores)
+        stats = step(batch)
         dt = time.perf_counter() - t0
-        if s >= args.warmup:
+        if s >= warmup:
             times.append(dt)
             upd.append(stats["cell_gene_updates"])
     T = sum(times)
     value = sum(upd) / T
+    sample = ("one batch of the same shape (n=%d cells, r=%d, %d perturbations) restricted to %d of %d genes; %s"
+              % (n, w["r"], w["n_perts"], p_s, w["p"], how))
+    return dict(value=value, ms_per_step=1e3 * T / max(1, len(times)), cores=cores, kind=kind, sample=sample,
+                jit_warmup_s=jit_s, n_genes_sample=p_s,
+                phases_s={k: round(v, 3) for k, v in stats.items() if k.startswith("t_")},
+                work_last_step={k: int(stats[k]) for k in ("alt_iters", "irls_gene_iters") if k in stats})
+
+
+def reference_kind():
+    from oracle import ref_shim
+    return "reference" if ref_shim.reference_available() else "port"
+
+
+def run_reference(args, rank, world):
+    """CPU arm: rank 0 only; bounded sample = gene subsample of the same batch shape."""
+    if rank != 0:
+        return
+    kind = args.cpu_impl or reference_kind()
+    nsteps = args.steps + args.warmup
+    p_s = args.cpu_genes
+    if p_s is None:
+        # about 200 s of CPU work in total: ~20 genes per second and step on 16 cores for the reference,
+        # ~70 for the port
+        rate = 20.0 if kind == "reference" else 70.0
+        p_s = int(max(64, min(WORKLOAD["p"], rate * (os.cpu_count() or 1) / 16.0 * 200.0 / max(1, nsteps))))
+        p_s = p_s // 8 * 8
+    r = reference_arm(args.steps, args.warmup, p_s, kind)
     w = WORKLOAD
     n = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
-    sample = ("one batch of the same shape (n=%d cells, r=%d, %d perturbations) restricted to %d of %d genes; "
-              "C/OpenMP alternating iteration on %d threads + per-gene numpy IRLS over %d processes"
-              % (n, w["r"], w["n_perts"], p_s, w["p"], cport.threads(), cores))
-    out = {"impl": "reference", "metric": "gcate_lfc_cell_gene_updates_per_s", "value": value,
+    out = {"impl": "reference", "metric": "gcate_lfc_cell_gene_updates_per_s", "value": r["value"],
            "unit": "cell*gene updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * T / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": w["name"], "n_cells": n, "n_genes_sample": p_s, "n_genes": w["p"], "r": w["r"],
                       "perturbations": w["n_perts"], "family": w["family"]},
-           "cpu_baseline": {"value": value, "unit": "cell*gene updates/s", "cores": cores, "kind": "port",
-                            "sample": sample},
-           "e2e": {"value": value, "unit": "cell*gene updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "phases_s": {k: round(v, 3) for k, v in stats.items() if k.startswith("t_")}}
+           "cpu_baseline": {"value": r["value"], "unit": "cell*gene updates/s", "cores": r["cores"], "kind": r["kind"],
+                            "sample": r["sample"], "jit_warmup_s_excluded": r["jit_warmup_s"]},
+           "e2e": {"value": r["value"], "unit": "cell*gene updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "phases_s": r["phases_s"], "work_last_step": r["work_last_step"]}
     emit_json(out)
 
 
@@ -196,7 +245,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-genes", type=int, default=400, help="gene subsample of the CPU arms")
+    ap.add_argument("--cpu-genes", type=int, default=None, help="gene subsample of the CPU arms")
+    ap.add_argument("--cpu-impl", default=None, choices=["reference", "port"],
+                    help="CPU arm: the staged reference package (default when present) or the oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--genes", type=int, default=None, help="override p (debug only; makes the number invalid)")
     args = ap.parse_args()
@@ -388,20 +439,25 @@ def main():
            "n_significant_last_step": stats_res[-1]["n_sig"]}
 
     if not args.no_cpu_baseline and world == 1:
-        from oracle import cport
-        cores = os.cpu_count() or 1
-        cport.set_threads(cores)
-        b = make_batch(1000, p=args.cpu_genes)
-        t0 = time.perf_counter()
-        st = cpu_step(b, cores)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {
-            "value": st["cell_gene_updates"] / dt, "unit": "cell*gene updates/s", "cores": cores, "kind": "port",
-            "seconds": round(dt, 2),
-            "sample": "one batch of the same shape (n=%d, r=%d, %d perturbations) restricted to %d of %d genes; "
-                      "C/OpenMP alternating iteration (%d threads) + per-gene numpy IRLS over %d processes"
-                      % (n, w["r"], w["n_perts"], args.cpu_genes, w["p"], cport.threads(), cores),
-            "phases_s": {k: round(v, 3) for k, v in st.items() if k.startswith("t_")}}
+        # CPU baseline in a child process (the reference brings numba / OpenMP pools of its own): the
+        # real reference when it is staged, and the oracle port beside it as a second, labelled number
+        def child(kind, genes):
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-impl", kind, "--steps", "1",
+                   "--warmup", "0", "--cpu-genes", str(genes)]
+            try:
+                res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
+                line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
+                j = json.loads(line)
+                cb = j["cpu_baseline"]
+                cb["seconds"] = round(j["ms_per_step"] * 1e-3, 2)
+                cb["phases_s"] = j.get("phases_s")
+                return cb
+            except Exception as e:  # noqa: BLE001
+                return {"error": "%s: %s" % (type(e).__name__, e)}
+        kind = reference_kind()
+        out["cpu_baseline"] = child(kind, args.cpu_genes or (320 if kind == "reference" else 400))
+        if kind == "reference":
+            out["cpu_baseline_port"] = child("port", args.cpu_genes or 400)
     emit_json(out)
     if world > 1:
         dist.destroy_process_group()

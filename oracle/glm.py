@@ -30,6 +30,8 @@ Poisson unit deviance 2[y log(clip(y/mu, eps)) - (y - mu)];
 NB unit deviance 2[y log(clip(y/mu, eps)) - (y + 1/alpha) log((y + 1/alpha)/(mu + 1/alpha))].
 Deviance residual sign(y - mu) sqrt(max(d_i, 0)).
 """
+import os
+
 import numpy as np
 
 FLOAT_EPS = np.finfo(float).eps
@@ -226,6 +228,16 @@ class _Results:
         return np.exp(eta)
 
 
+def _count_iterations(it):
+    """Work accounting for bench.py's CPU arm: with ``CA_ORACLE_ITER_DIR`` set, every process
+    appends the IRLS iteration count of each fit to its own file there (the reference fans the
+    per-gene fits out over joblib worker processes, so a module-level counter would not do)."""
+    d = os.environ.get("CA_ORACLE_ITER_DIR")
+    if d:
+        with open(os.path.join(d, "iters.%d" % os.getpid()), "a") as f:
+            f.write("%d\n" % it)
+
+
 class SMGLM:
     """Minimal ``sm.GLM`` stand-in: ``SMGLM(y, X, family=..., offset=...).fit(maxiter=)``."""
 
@@ -243,6 +255,7 @@ class SMGLM:
             res.predict = lambda exog, offset=None: np.asarray(exog) @ beta + (0 if offset is None else offset)
             return res
         beta, mu, dev, it, conv = irls(self.endog, self.exog, self.offset, self.family.alpha, maxiter=maxiter)
+        _count_iterations(it)
         return _Results(self, beta, mu, it, conv)
 
     def fit_regularized(self, alpha=0.0, cnvrg_tol=1e-5, L1_wt=1.0, **kw):
