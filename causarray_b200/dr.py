@@ -36,7 +36,7 @@ __version__ = "0.1.0"
 
 import concurrent.futures as _cf
 _PS_POOL = _cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix='causarray_ps')
-_PS_FIT_POOL = _cf.ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 1))), thread_name_prefix='causarray_psfit')
+_PS_FIT_POOL = _cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='causarray_psfit')
 
 
 class YhatFactors:
@@ -83,35 +83,62 @@ def _validate_clip(clip):
     return lo, hi
 
 
-_TP_CONTROLLER = None
-_PS_STATE = {'procs_failed': False}
+
+
+_LEAN_LOSS = None
+
+
+def _fit_logistic_lean(x, y, x_te, C, balanced, tol, max_iter):
+    """sklearn's binary ``LogisticRegression(solver='lbfgs', fit_intercept=False)`` without the
+    estimator plumbing: the SAME loss object (``LinearModelLoss(HalfBinomialLoss)``), sample weights,
+    start vector and ``scipy.optimize.minimize(method='L-BFGS-B')`` options as
+    ``sklearn/linear_model/_logistic.py::_logistic_regression_path`` -- identical function values, so
+    identical iterates and (bit for bit) identical probabilities
+    (``tests/test_host_api.py::test_lean_logistic_is_sklearn``) -- at a fifth of the cost per fit
+    (input validation, label encoding and parameter routing dominate sklearn's 5 ms on these
+    2 000 x 12 designs).  The reference's answer is defined by this solver and its ``tol=1e-4`` stop
+    (``causarray/DR_estimation.py:18-42``), which is why the fit stays on the host."""
+    global _LEAN_LOSS
+    import scipy.optimize
+    from scipy.special import expit
+    if _LEAN_LOSS is None:
+        from sklearn._loss.loss import HalfBinomialLoss
+        from sklearn.linear_model._linear_loss import LinearModelLoss
+        _LEAN_LOSS = LinearModelLoss(base_loss=HalfBinomialLoss(), fit_intercept=False)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = x.shape[0]
+    pos = np.asarray(y) == 1
+    target = np.ones(n)
+    target[~pos] = 0.0
+    if balanced:
+        cnt = np.array([n - pos.sum(), pos.sum()], dtype=np.float64)
+        cw = cnt.sum() / (2 * cnt)
+        sw = np.ones(n) * cw[pos.astype(np.intp)]
+        sw_sum = float(np.sum(sw))
+    else:
+        sw, sw_sum = None, n
+    res = scipy.optimize.minimize(_LEAN_LOSS.loss_gradient, np.zeros(x.shape[1]), method='L-BFGS-B', jac=True,
+                                  args=(x, target, sw, 1.0 / (C * sw_sum), 1),
+                                  options={'maxiter': max_iter, 'maxls': 50, 'gtol': tol,
+                                           'ftol': 64 * np.finfo(float).eps})
+    return expit((np.asarray(x_te, dtype=np.float64) @ res.x.reshape(1, -1).T).ravel())
+
+
+_LEAN_KEYS = {'fit_intercept', 'C', 'class_weight', 'random_state', 'tol', 'max_iter'}
 
 
 def _fit_logistic(lr_kw, x, y, x_te):
-    """One propensity fit.  The inner OpenMP / BLAS pools are held at one thread: on these small
-    designs (a few thousand cells x ~10 columns) sklearn's threaded loss loops only cost (190 ms
-    -> 110 ms for 15 sequential fits) and they oversubscribe the cores next to the worker pool."""
-    global _TP_CONTROLLER
-    try:
-        if _TP_CONTROLLER is None:
-            from threadpoolctl import ThreadpoolController
-            _TP_CONTROLLER = ThreadpoolController()
-        with _TP_CONTROLLER.limit(limits=1):
-            return LogisticRegression(**lr_kw).fit(x, y).predict_proba(x_te)[:, 1]
-    except ImportError:
-        return LogisticRegression(**lr_kw).fit(x, y).predict_proba(x_te)[:, 1]
-
-
-def _ps_procs():
-    try:
-        v = int(os.environ.get('CAUSARRAY_B200_PS_PROCS', '8'))
-    except ValueError:
-        v = 8
-    # one process per GPU (torchrun): the ranks of a node share the host cores; leave one core of the
-    # share to the main thread, which is inside the outcome GLM while the workers fit
-    from .inference import _cores_per_rank
-    share = _cores_per_rank()
-    return max(0, min(v, share if share >= (os.cpu_count() or 1) else max(1, share - 2)))
+    """One propensity fit: the lean path when the options are the plain L2 / lbfgs ones the reference
+    uses, sklearn's estimator for anything else."""
+    if (set(lr_kw) <= _LEAN_KEYS and lr_kw.get('fit_intercept') is False
+            and (lr_kw.get('class_weight') is None or lr_kw.get('class_weight') == 'balanced')
+            and not os.environ.get('CAUSARRAY_B200_PS_SKLEARN')):
+        try:
+            return _fit_logistic_lean(x, y, x_te, float(lr_kw.get('C', 1.0)), lr_kw.get('class_weight') == 'balanced',
+                                      float(lr_kw.get('tol', 1e-4)), int(lr_kw.get('max_iter', 100)))
+        except ImportError:      # sklearn moved its private loss modules: use the estimator
+            pass
+    return LogisticRegression(**lr_kw).fit(x, y).predict_proba(x_te)[:, 1]
 
 
 def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip=None, random_state=0,
@@ -179,31 +206,13 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
                 return None, np.mean(y)
             return (x, y), None
 
-        # The per-treatment fits are independent (shared controls, own cases).  sklearn's lbfgs path is
-        # Python-bound (150 ms for 15 treatments of a 4 000-cell batch, 56 ms over threads because of
-        # the GIL), so with four or more treatments they go to joblib's reusable worker processes
-        # (22 ms once the workers are up; CAUSARRAY_B200_PS_PROCS=0 keeps them in this process).
+        # The per-treatment fits are independent (shared controls, own cases): ~1 ms each on the lean
+        # path, spread over a few threads (the loss kernels and L-BFGS-B release the GIL).
         n_trt = A.shape[1]
         tasks = [task(j) for j in range(n_trt)]
         todo = [j for j in range(n_trt) if tasks[j][0] is not None]
         fits = [t[1] for t in tasks]
-        n_procs = _ps_procs()
-        res = None
-        if len(todo) >= 4 and n_procs > 1 and not _PS_STATE['procs_failed']:
-            try:
-                from joblib import Parallel, delayed
-                res = Parallel(n_jobs=n_procs, backend='loky')(
-                    delayed(_fit_logistic)(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo)
-            except ValueError:
-                raise
-            except Exception as exc:       # worker processes unavailable (sandbox, /dev/shm ...): threads
-                _PS_STATE['procs_failed'] = True
-                warnings.warn(f'propensity fits: worker processes unavailable ({exc!r}); using threads',
-                              RuntimeWarning, stacklevel=2)
-                res = None
-        if res is not None:
-            pass
-        elif len(todo) > 2:
+        if len(todo) > 2:
             res = list(_PS_FIT_POOL.map(lambda j: _fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te), todo))
         else:
             res = [_fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo]
@@ -271,16 +280,29 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
                     pg['offset'] = pg['offset'][tr]
                 B, _, _, off_tr, _ = _glm_mod.fit_glm(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True,
                                                       **pg)
-                # Reference behaviour, kept for identical results: ``fit_glm(..., impute=X_test)`` rebuilds
-                # its prediction design from the TRAINING rows (``X_test = np.c_[X, zeros]`` overwrites the
-                # ``impute`` array, causarray/gcate_glm.py:160-165) and predicts with the training offsets,
-                # so the (n_train, p, a) imputations of the training cells are what
-                # ``cross_fitting`` writes into the test rows (DR_estimation.py:612-613) -- which only
-                # broadcasts when both folds have the same size (K = 2, even n).
-                if len(tr) != len(te):
-                    raise ValueError('could not broadcast input array from shape (%d,%d,%d) into shape (%d,%d,%d)'
-                                     % (len(tr), Yn.shape[1], A.shape[1], len(te), Yn.shape[1], A.shape[1]))
-                Y_hat[te] = YhatFactors(X[tr], B[:, :d], B[:, d:], off_tr, cap=np.inf).materialize()
+                if not _glm_mod._USE_FAST_BACKEND:
+                    # backend="original" only -- the reference's statsmodels route, kept for identical
+                    # results: ``fit_glm(..., impute=X_test)`` rebuilds its prediction design from the
+                    # TRAINING rows (``X_test = np.c_[X, zeros]`` overwrites the ``impute`` array,
+                    # causarray/gcate_glm.py:160-165) and predicts with the training offsets, so the
+                    # imputations of the training cells are what ``cross_fitting`` writes into the test
+                    # rows (DR_estimation.py:612-613) -- which only broadcasts when both folds have the
+                    # same size (K = 2, even n).
+                    if len(tr) != len(te):
+                        raise ValueError('could not broadcast input array from shape (%d,%d,%d) into shape (%d,%d,%d)'
+                                         % (len(tr), Yn.shape[1], A.shape[1], len(te), Yn.shape[1], A.shape[1]))
+                    Y_hat[te] = YhatFactors(X[tr], B[:, :d], B[:, d:], off_tr, cap=np.inf).materialize()
+                else:
+                    # default route (the reference's batched backend, nb_glm_fast.py:273-297): the model
+                    # fitted on the training fold predicts the HELD-OUT rows with their own offsets
+                    off_all = params_glm.get('offset')
+                    if isinstance(off_all, np.ndarray):
+                        off_te = off_all[te]
+                    elif off_all is True:
+                        raise ValueError('cross-fitting needs the offset as an array (offset=True is fold dependent)')
+                    else:
+                        off_te = None
+                    Y_hat[te] = YhatFactors(X[te], B[:, :d], B[:, d:], off_te, cap=np.inf).materialize()
             Y_hat = np.clip(Y_hat, None, 1e5)
         else:
             with phase('lfc_outcome_glm'):
@@ -550,6 +572,13 @@ def LFC(Y, W, A, W_A=None, family='nb', offset=False, Y_hat=None, pi_hat=None, c
             names_full = list(Y.columns) if isinstance(Y, pd.DataFrame) else None
             Yf = Y.values if isinstance(Y, pd.DataFrame) else (Y.toarray() if hasattr(Y, 'tocsr') else np.asarray(Y))
             p_total = Yf.shape[1]
+            if fdx or K != 1 or (Y_hat is not None and not isinstance(Y_hat, YhatFactors)):
+                raise NotImplementedError('gene_shard=True supports the in-sample fused path only '
+                                          '(no fdx, K = 1, no dense Y_hat)')
+            if type(offset) == bool and offset is True:
+                # median-of-ratios size factors are a per-cell median over ALL genes: compute them from
+                # the full matrix before the columns are sliced (every rank gets the same offsets)
+                offset = np.log(comp_size_factor(Yf, **_filter_params(comp_size_factor, kwargs)))
             lo, hi = gene_bounds(p_total, world)[rank]
             if kwargs.get('_glm') is None or kwargs['_glm'].p != p_total:
                 Y = np.ascontiguousarray(Yf[:, lo:hi])
@@ -670,6 +699,10 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
     import math as _math
     _rank, _world = _par.dist_info()
     if _world > 1:
+        if warm_start_U:
+            # U of batch i-1 would come from a different rank: the result would depend on WORLD_SIZE
+            raise ValueError('warm_start_U=True chains the batches and cannot be combined with batch sharding '
+                             'over several ranks; run it on one rank or pass warm_start_U=False')
         _nb = n_batches if n_batches is not None else _math.ceil(A_np.shape[1] / batch_size)
         _nb = max(1, min(_nb, A_np.shape[1]))
         skip = set(skip) | _par.foreign_batches(_nb, _rank, _world)

@@ -308,6 +308,36 @@ def golden_lfc_fit(ca, seed, tag, cross_est):
     print("lfc_fit", tag, "sig", int(np.nansum(df["padj"] < 0.05)), "filtered", int(np.isinf(df["std"]).sum()))
 
 
+def golden_lfc_crossfit(ca, seed, tag, K, n_ctrl):
+    """Proper cross-fitting (the reference's batched-backend semantics, ``DR_estimation.py:590-613``
+    with ``nb_glm_fast.py:273-297``: fit on the training fold, predict the HELD-OUT rows with their
+    own offsets) for fold shapes the statsmodels route cannot run (odd n, K = 3).  The fold-wise
+    outcome model is the IRLS restatement (``oracle/glm.py``); everything downstream of ``Y_hat`` --
+    cross-fitted propensities, AIPW, the estimand, BH -- is the REAL reference's ``LFC``."""
+    from sklearn.model_selection import KFold
+    from oracle import glm as og
+    sim = simulate_screen(n_ctrl=n_ctrl, n_perts=2, cells_per_pert=40, p=60, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=0.5, base_hi=2.5)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    W = np.c_[Xc, sim["U"]]
+    off = np.log(ca.comp_size_factor(Y))
+    n, p = Y.shape
+    a, d = Atr.shape[1], W.shape[1]
+    Y_hat = np.zeros((n, p, a, 2))
+    for tr, te in KFold(n_splits=K, random_state=0, shuffle=True).split(W):
+        B = og.fit_glm_original(Y[tr], W[tr], Atr[tr], family="nb", disp_glm=sim["disp"], offset=off[tr], maxiter=1000)[0]
+        eta0 = W[te] @ B[:, :d].T + off[te][:, None]
+        Y_hat[te, :, :, 0] = np.exp(eta0)[:, :, None]
+        Y_hat[te, :, :, 1] = np.exp(eta0[:, :, None] + B[:, d:][None, :, :])
+    df, est = ca.LFC(Y.copy(), W, Atr, W_A=W, family="nb", offset=off, Y_hat=Y_hat.copy(), K=K, usevar="unequal")
+    out = dict(Y=Y, W=W, A=Atr, offset=off, disp=sim["disp"], K=K, pi_hat=est["pi_hat"], Y_hat=np.clip(Y_hat, None, 1e5),
+               estimable=df["estimable"].to_numpy().astype(np.uint8))
+    for c in ["tau", "std", "stat", "pvalue", "padj", "mean_control", "mean_treated"]:
+        out["df_" + c] = df[c].to_numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "lfc_crossfit_%s.npz" % tag), **out)
+    print("lfc_crossfit", tag, "n", n, "K", K, "sig", int(np.nansum(df["padj"] < 0.05)))
+
+
 def golden_more(ca, seed):
     """fit_gcate_batch with pert-cell subsampling and the warm start of U across batches, and
     fit_glm with its own dispersion estimate and imputation, through the REAL reference."""
@@ -481,7 +511,7 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options", "gcate_options"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options", "gcate_options", "lfc_crossfit"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
@@ -492,6 +522,9 @@ if __name__ == "__main__":
         golden_lfc_options(ca, 81)
     if "more" in which:
         golden_more(ca, 71)
+    if "lfc_crossfit" in which:
+        golden_lfc_crossfit(ca, 63, "k2_odd", 2, 121)
+        golden_lfc_crossfit(ca, 64, "k3", 3, 120)
     if "lfc_fit" in which:
         golden_lfc_fit(ca, 61, "k1", False)
         golden_lfc_fit(ca, 62, "k2", True)

@@ -200,3 +200,25 @@ def test_typed_upload_codes_match_header():
         assert _NARROW_DTYPES[np.dtype(t).str] == codes[name]
     assert device_dtype(np.zeros((2, 2), dtype=np.int32)) and device_dtype(np.zeros((2, 2)))
     assert not device_dtype(np.zeros((2, 2), dtype=np.int16)) and not device_dtype([[1, 2]])
+
+
+def test_lean_logistic_is_sklearn():
+    """The lean propensity fit (same loss object, weights, start and L-BFGS-B options as sklearn's
+    lbfgs path) returns sklearn's probabilities bit for bit -- the reference's propensity model is
+    ``LogisticRegression(fit_intercept=False, C=1, class_weight='balanced')``
+    (causarray/DR_estimation.py:18-42)."""
+    from sklearn.linear_model import LogisticRegression
+    from causarray_b200 import dr
+    rng = np.random.default_rng(3)
+    for n, d, frac, cw in ((900, 4, 0.3, 'balanced'), (2133, 12, 0.06, 'balanced'), (500, 3, 0.5, None)):
+        X = np.c_[np.ones(n), rng.standard_normal((n, d - 1))]
+        y = (rng.random(n) < frac).astype(float)
+        Xte = rng.standard_normal((50, d))
+        kw = dict(fit_intercept=False, C=1.0, class_weight=cw, random_state=0)
+        lean = dr._fit_logistic(kw, X, y, Xte)
+        ref = LogisticRegression(**kw).fit(X, y).predict_proba(Xte)[:, 1]
+        assert np.array_equal(lean, ref)
+    # options outside the plain regime go through the estimator itself
+    kw = dict(fit_intercept=True, C=0.5, class_weight='balanced', random_state=0)
+    np.testing.assert_array_equal(dr._fit_logistic(kw, X, y, Xte),
+                                  LogisticRegression(**kw).fit(X, y).predict_proba(Xte)[:, 1])
