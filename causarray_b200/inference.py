@@ -158,48 +158,68 @@ def bh_correction_multi(tvalues, df=None):
 
 
 def multiplier_bootstrap(eta, B):
-    """Gaussian multiplier bootstrap statistics ``(B, p)`` of the scaled influence values."""
-    n, p = eta.shape
-    G = np.random.normal(size=(int(B), n))
-    return G @ eta
+    """Gaussian multiplier bootstrap statistics ``z = G eta`` with ``G (B, n)`` standard normal
+    (``causarray/DR_inference.py:8-31`` draws the rows of ``G`` one by one from the same global
+    numpy stream, so a seeded call reproduces the reference's statistics) -- one GEMM instead of
+    ``B`` weighted column sums."""
+    G = np.random.normal(size=(int(B), eta.shape[0]))
+    return G @ np.asarray(eta, dtype=np.float64)
 
 
 def step_down(tvalues_init, z_init, alpha):
-    p = z_init.shape[1]
-    V = np.zeros(p,)
-    z = z_init.copy()
-    t = tvalues_init.copy()
-    while True:
-        i = np.argmax(np.abs(t))
-        t_max = np.abs(t[i])
-        quan = np.quantile(np.max(np.abs(z), axis=1), 1 - alpha, method='lower')
-        if t_max < quan or quan == 0:
-            break
-        t[i] = 0
-        z[:, i] = 0
-        V[i] = 1
+    """Step-down max-|z| procedure (``causarray/DR_inference.py:34-70``): hypotheses leave in order
+    of decreasing ``|t|`` while the largest remaining ``|t|`` reaches the ``1 - alpha`` quantile (lower
+    interpolation) of the bootstrap maxima over the REMAINING hypotheses.
+
+    The removal order is known in advance (descending ``|t|``, first index on ties -- what the
+    reference's repeated ``argmax`` does), so the maxima over the remaining set are a reversed
+    running maximum along that order and all thresholds come from one quantile call; the reference
+    rescans the ``(B, p)`` matrix once per discovery.  Returns ``(V, tvalues, z)`` with the removed
+    entries zeroed, like the reference."""
+    t = np.array(tvalues_init, dtype=float)
+    z = np.array(z_init, dtype=float)
+    p = t.shape[0]
+    V = np.zeros(p)
+    if p == 0 or z.shape[0] == 0:
+        return V, t, z
+    order = np.argsort(-np.abs(t), kind='stable')
+    absz = np.abs(z[:, order])
+    rem_max = np.maximum.accumulate(absz[:, ::-1], axis=1)[:, ::-1]   # max over positions >= k of the order
+    thr = np.quantile(rem_max, 1 - alpha, axis=0, method='lower')
+    at = np.abs(t[order])
+    stop = (at < thr) | (thr == 0)
+    k = int(np.argmax(stop)) if stop.any() else p      # hypotheses order[:k] are discoveries
+    hit = order[:k]
+    V[hit] = 1
+    t[hit] = 0
+    z[:, hit] = 0
     return V, t, z
 
 
 def augmentation(V, tvalues, c):
+    """Augmentation step of FDX control (``causarray/DR_inference.py:73-99``): with ``|V|``
+    step-down discoveries, the ``floor(c |V| / (1 - c))`` largest remaining ``|t|`` are added."""
     if c > 0:
         num_add = int(np.floor(c * np.sum(V) / (1 - c)))
         if num_add >= 1:
-            srt = np.sort(np.abs(tvalues), axis=None)[::-1]
-            for i in np.arange(num_add):
-                V[np.abs(tvalues) == srt[i]] = 1
+            at = np.abs(np.asarray(tvalues)).ravel()
+            top = np.sort(at)[::-1][:num_add]
+            V[np.isin(at, top)] = 1      # every hypothesis tied with one of the top values joins, as in the reference
     return V
 
 
 def fdx_control(tau_est, tvalues_init, eta_est, std_est, fdx, B, alpha, c, min_var=1e-8, min_diff=0.1):
-    """FDX (FDP exceedance) control by multiplier bootstrap + step-down + augmentation."""
+    """FDX (FDP exceedance) control: ``P(FDP > c) < alpha`` by multiplier bootstrap, step-down and
+    augmentation (``causarray/DR_inference.py:102-150``).  Hypotheses with ``std < min_var`` are not
+    tested; they count as discoveries when ``|tau| > min_diff``."""
     if not fdx:
-        return np.zeros(tvalues_init.shape[0])
-    ok = std_est >= min_var
-    z = multiplier_bootstrap(eta_est / std_est[None, :], B)
-    z[:, ~ok] = 0.
-    t = tvalues_init.copy()
-    t[~ok] = 0.
+        return np.zeros(np.shape(tvalues_init)[0])
+    std_est = np.asarray(std_est, dtype=float)
+    testable = std_est >= min_var
+    with np.errstate(divide='ignore', invalid='ignore'):
+        z = multiplier_bootstrap(np.asarray(eta_est) / std_est[None, :], B)
+    z[:, ~testable] = 0.
+    t = np.where(testable, tvalues_init, 0.)
     V, t, z = step_down(t, z, alpha)
-    V[(~ok) & (np.abs(tau_est) > min_diff)] = 1.
+    V[~testable & (np.abs(tau_est) > min_diff)] = 1.
     return augmentation(V, t, c)

@@ -28,7 +28,7 @@ def _init_AB(rng, X, r, p, scale=0.1):
     return A0, B0
 
 
-def golden_kernels(ca, family, seed, tag):
+def golden_kernels(ca, family, seed, tag, C=None):
     """nll / grad / update_with_mask (stage 1 and stage 2) on one tiny problem."""
     import scipy.linalg
     from causarray.gcate_opt import update_with_mask, update
@@ -53,7 +53,14 @@ def golden_kernels(ca, family, seed, tag):
     out["nll"] = nll(Yn, A0, B0, family, nu, Ys, thres)
     out["grad_B"] = grad(Yn, A0, B0, family, nu, thres)
     out["grad_A"] = grad(np.ascontiguousarray(Yn.T), B0, A0, family, np.ascontiguousarray(nu.T), thres)
-    C = 1e3 if family == "nb" else 1e5
+    if C is None:
+        C = 1e3 if family == "nb" else 1e5
+    else:
+        # a radius small enough that project_norm_ball (causarray/gcate_opt.py:10-26) rescales rows
+        gA_, gB_ = out["grad_A"][:, d:], out["grad_B"][:, d:]
+        print("  rows clipped at 2C = %g: cells %d / %d, genes %d / %d"
+              % (2 * C, int((np.abs(gA_).max(1) > 2 * C).sum()), n, int((np.abs(gB_).max(1) > 2 * C).sum()), p))
+    out["C"] = C
     Q1 = scipy.linalg.qr(X, mode="economic")[0]
     gene_active = rng.random(p) < 0.9
     cell_active = rng.random(n) < 0.9
@@ -338,6 +345,55 @@ def golden_lfc_crossfit(ca, seed, tag, K, n_ctrl):
     print("lfc_crossfit", tag, "n", n, "K", K, "sig", int(np.nansum(df["padj"] < 0.05)))
 
 
+def golden_fdx(ca, seed):
+    """FDX control (multiplier bootstrap + step-down + augmentation, causarray/DR_inference.py:8-150)
+    from the REAL reference: the function on synthetic statistics (ties, untestable hypotheses, several
+    alpha / c) and LFC(fdx=True) end to end with the nuisances supplied.  The bootstrap draws come from
+    the global numpy stream, seeded right before each call."""
+    from causarray import DR_inference as ri
+    rng = np.random.default_rng(seed)
+    out = {}
+    cases = []
+    for ci, (n, p, nsig, alpha, c, B) in enumerate([(150, 200, 25, 0.05, 0.1, 300), (150, 200, 60, 0.1, 0.3, 300),
+                                                    (80, 120, 0, 0.05, 0.1, 200), (150, 200, 40, 0.05, 0.0, 300)]):
+        std = np.abs(rng.standard_normal(p)) * 0.1 + 0.05
+        eta = rng.standard_normal((n, p)) * std[None, :] / np.sqrt(n)
+        tau = rng.standard_normal(p) * std
+        idx = rng.choice(p, nsig, replace=False)
+        tau[idx] += rng.choice([-1.0, 1.0], nsig) * rng.uniform(4, 9, nsig) * std[idx]
+        if ci == 1:
+            std[3:7] = 1e-9                        # below min_var: not tested, discovery iff |tau| > min_diff
+            tau[3], tau[4] = 0.5, 0.01
+            tau[10] = tau[11] = 6 * std[10]
+            std[11] = std[10]                      # an exact tie in |t|
+        t = tau / std
+        np.random.seed(100 + ci)
+        V = ri.fdx_control(tau, t.copy(), eta, std, True, B, alpha, c)
+        out.update({"c%d_tau" % ci: tau, "c%d_t" % ci: t, "c%d_eta" % ci: eta, "c%d_std" % ci: std,
+                    "c%d_par" % ci: np.array([B, alpha, c, 100 + ci]), "c%d_V" % ci: V})
+        cases.append(int(V.sum()))
+    sim = simulate_screen(n_ctrl=200, n_perts=2, cells_per_pert=100, p=80, r=2, d_cov=1, family="nb", seed=seed,
+                          base_lo=1.0, base_hi=3.0, frac_nonnull=0.25)
+    Y, Xc, Atr = sim["Y"], sim["X"], sim["A"]
+    W = np.c_[Xc, sim["U"]]
+    sf = ca.comp_size_factor(Y)
+    n, p = Y.shape
+    a = Atr.shape[1]
+    # outcome model close to the truth: control-cell mean per gene, true effects, size factors
+    ctrl = Atr.sum(1) == 0
+    mu0 = (Y[ctrl] / sf[ctrl, None]).mean(0)[None, :] * sf[:, None] + 1e-3
+    Y_hat = np.stack([np.repeat(mu0[:, :, None], a, axis=2), mu0[:, :, None] * np.exp(sim["tau"].T[None, :, :])], axis=-1)
+    pi = np.clip(np.repeat(Atr.mean(0)[None, :] / (Atr.mean(0)[None, :] + ctrl.mean()), n, axis=0)
+                 * rng.uniform(0.8, 1.2, (n, a)), 0.01, 0.99)
+    np.random.seed(321)
+    df, est = ca.LFC(Y.copy(), W, Atr, W_A=W, family="nb", offset=np.log(sf), Y_hat=Y_hat.copy(), pi_hat=pi.copy(),
+                     usevar="unequal", fdx=True, fdx_alpha=0.1, fdx_c=0.2)
+    out.update(dict(Y=Y, W=W, A=Atr, offset=np.log(sf), Y_hat=Y_hat, pi=pi, lfc_rej=df["rej"].to_numpy().astype(np.float64),
+                    lfc_tau=df["tau"].to_numpy().astype(np.float64), lfc_padj=df["padj"].to_numpy().astype(np.float64)))
+    np.savez_compressed(os.path.join(HERE, "fdx.npz"), **out)
+    print("fdx discoveries per case", cases, "LFC rej", int(df["rej"].sum()))
+
+
 def golden_more(ca, seed):
     """fit_gcate_batch with pert-cell subsampling and the warm start of U across batches, and
     fit_glm with its own dispersion estimate and imputation, through the REAL reference."""
@@ -511,7 +567,7 @@ def golden_batch(ca, seed):
 
 if __name__ == "__main__":
     ca = ref_shim.import_reference()
-    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options", "gcate_options", "lfc_crossfit"]
+    which = sys.argv[1:] or ["kernels", "alter_min", "lfc", "misc", "pipeline", "estimate_r", "batch", "lfc_fit", "more", "lfc_options", "gcate_options", "lfc_crossfit", "fdx", "kernels_clip"]
     if "estimate_r" in which:
         golden_estimate_r(ca, 41)
     if "batch" in which:
@@ -522,6 +578,8 @@ if __name__ == "__main__":
         golden_lfc_options(ca, 81)
     if "more" in which:
         golden_more(ca, 71)
+    if "fdx" in which:
+        golden_fdx(ca, 95)
     if "lfc_crossfit" in which:
         golden_lfc_crossfit(ca, 63, "k2_odd", 2, 121)
         golden_lfc_crossfit(ca, 64, "k3", 3, 120)
@@ -531,6 +589,8 @@ if __name__ == "__main__":
     if "kernels" in which:
         golden_kernels(ca, "nb", 11, "nb")
         golden_kernels(ca, "poisson", 12, "poisson")
+    if "kernels_clip" in which:
+        golden_kernels(ca, "nb", 13, "nb_clip", C=0.01)
     if "alter_min" in which:
         golden_alter_min(ca, "nb", 21, "nb")
         golden_alter_min(ca, "poisson", 22, "poisson")

@@ -35,11 +35,14 @@ def test_nll_grad_golden(golden_dir, fam):
     np.testing.assert_allclose(gA, g["grad_A"], rtol=1e-10, atol=1e-12)
 
 
-@pytest.mark.parametrize("fam", ["nb", "poisson"])
+@pytest.mark.parametrize("fam", ["nb", "poisson", "nb_clip"])
 def test_update_with_mask_golden(golden_dir, fam):
+    """(nb_clip: the golden was produced with C = 0.01, i.e. a norm-ball radius of 0.02 that rescales most
+    cell and gene gradients -- project_norm_ball, causarray/gcate_opt.py:10-26)"""
     g = np.load(os.path.join(golden_dir, "kernels_%s.npz" % fam))
     d, a, r = int(g["d"]), int(g["a"]), int(g["r"])
-    C = 1e3 if fam == "nb" else 1e5
+    C = float(g["C"]) if "C" in g else (1e3 if fam == "nb" else 1e5)
+    fam = fam.split("_")[0]
     # stage 1 (P1), masks + per-gene alpha, three consecutive iterations
     dev = _dev(g, fam)
     dev.set_factors(g["A0"], g["B0"])

@@ -1,5 +1,6 @@
 """GPU edge cases of the three seams: empty masks, tiny / ragged shapes, degenerate designs,
 wide designs, and the error behaviour of the C ABI (return codes, no exceptions across it)."""
+import os
 import numpy as np
 import pytest
 import scipy.linalg
@@ -205,3 +206,22 @@ def test_fit_gcate_input_validation():
         q1, q2 = cb.fit_gcate(np.round(Yf), X, A, 1, **kw)
     q2.pop("_ws").close()
     np.testing.assert_array_equal(r2["B_Gamma"], q2["B_Gamma"])
+
+
+@pytest.mark.gpu
+def test_lfc_with_fdx_control_golden():
+    """LFC(fdx=True) through the dense influence-value path against the REAL reference
+    (tests/golden/make_golden.py::golden_fdx): same seeded bootstrap stream, identical ``rej`` column."""
+    import warnings
+    import causarray_b200 as cb
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fdx.npz"))
+    np.random.seed(321)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df, est = cb.LFC(g["Y"].copy(), g["W"], g["A"], W_A=g["W"], family="nb", offset=g["offset"],
+                         Y_hat=g["Y_hat"].copy(), pi_hat=g["pi"].copy(), usevar="unequal", fdx=True, fdx_alpha=0.1,
+                         fdx_c=0.2)
+    np.testing.assert_array_equal(df["rej"].to_numpy().astype(float), g["lfc_rej"])
+    np.testing.assert_allclose(df["tau"].to_numpy().astype(float), g["lfc_tau"], rtol=1e-9, atol=1e-12)
+    a, b = df["padj"].to_numpy().astype(float), g["lfc_padj"]
+    np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-12, equal_nan=True)

@@ -173,8 +173,10 @@ def test_benchmark_cells_vs_oracle_pipeline():
     rt = np.abs(tau_g[fin] - tau_c[fin]) / np.maximum(np.abs(tau_c[fin]), 1e-12)
     rs = np.abs(std_g[fin] - std_c[fin]) / std_c[fin]
     print("tau rel max", rt.max(), "median", np.median(rt), "std rel max", rs.max())
-    # (a gene whose IRLS stops one iteration apart -- |dev change| within rounding of 1e-8 -- moves by ~1e-6;
-    # that is about one gene in several thousand, so the bound on the maximum still leaves room for it)
+    # north_star tolerance: LFC estimates and standard errors within 1e-6 relative.  (The convergence test
+    # of the per-gene IRLS sums per-cell unit deviances on both sides, so the stop decisions agree; the
+    # full-size records against the real reference -- profiles/r02_config{1,2,3}_ref_parity.json -- show
+    # 3e-10 at worst with identical IRLS iteration totals.)
     assert np.quantile(rt, 0.99) <= 1e-8 and np.quantile(rs, 0.99) <= 1e-8
-    assert rt.max() <= 1e-4 and rs.max() <= 1e-5
+    assert rt.max() <= 1e-6 and rs.max() <= 1e-6
     assert np.array_equal(padj_g < 0.05, l["padj"] < 0.05)

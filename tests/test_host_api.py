@@ -222,3 +222,23 @@ def test_lean_logistic_is_sklearn():
     kw = dict(fit_intercept=True, C=0.5, class_weight='balanced', random_state=0)
     np.testing.assert_array_equal(dr._fit_logistic(kw, X, y, Xte),
                                   LogisticRegression(**kw).fit(X, y).predict_proba(Xte)[:, 1])
+
+
+def test_fdx_control_matches_reference_golden():
+    """FDX control (multiplier bootstrap as one GEMM, step-down thresholds from a reversed running
+    maximum, augmentation) against the REAL reference's loop implementation
+    (causarray/DR_inference.py:8-150; tests/golden/make_golden.py::golden_fdx): same seeded numpy
+    stream, identical discovery sets -- ties in |t|, untestable hypotheses, c = 0, no signal."""
+    from causarray_b200 import inference as inf
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fdx.npz"))
+    for ci in range(4):
+        B, alpha, c, seed = g["c%d_par" % ci]
+        np.random.seed(int(seed))
+        V = inf.fdx_control(g["c%d_tau" % ci], g["c%d_t" % ci].copy(), g["c%d_eta" % ci], g["c%d_std" % ci], True,
+                            int(B), float(alpha), float(c))
+        np.testing.assert_array_equal(V, g["c%d_V" % ci])
+    assert [int(g["c%d_V" % ci].sum()) for ci in range(4)] == [24, 87, 0, 39]
+    # fdx=False: no discoveries, no random draws
+    st = np.random.get_state()[1][:4].copy()
+    assert inf.fdx_control(g["c0_tau"], g["c0_t"], g["c0_eta"], g["c0_std"], False, 10, 0.05, 0.1).sum() == 0
+    assert np.array_equal(np.random.get_state()[1][:4], st)

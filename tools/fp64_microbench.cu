@@ -20,26 +20,33 @@ __global__ void k_dfma(double* out, double a, double b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// NOTE: the four chains must not share operands AND start values: the first version passed the same
+// (fa, fb) to four zero-initialised accumulators, ptxas merged them into ONE chain (the SASS held
+// ITERS DMMAs, not 4 ITERS) and the printed rate was 4x too high (146 instead of 36.5 TFLOP/s).
 __global__ void k_dmma884(double* out, double a, double b) {
-  double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+  double c0[2] = {0, 1}, c1[2] = {2, 3}, c2[2] = {4, 5}, c3[2] = {6, 7};
   double fa = a + threadIdx.x, fb = b + threadIdx.x;
+  double fa1 = fa + 1, fa2 = fa + 2, fa3 = fa + 3;
+#pragma unroll 4
   for (int i = 0; i < ITERS; ++i) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(fa), "d"(fb));
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(fa), "d"(fb));
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(fa), "d"(fb));
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(fa), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(fa1), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(fa2), "d"(fb));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(fa3), "d"(fb));
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
 }
 
 // m16n8k8: A 16x8 (4 regs), B 8x8 (2 regs), C 16x8 (4 regs)
 __global__ void k_dmma1688(double* out, double a, double b) {
-  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
+  double c0[4] = {0, 1, 2, 3}, c1[4] = {4, 5, 6, 7}, c2[4] = {8, 9, 10, 11}, c3[4] = {12, 13, 14, 15};
   double fa0 = a + threadIdx.x, fa1 = fa0 + 1, fa2 = fa0 + 2, fa3 = fa0 + 3, fb0 = b + threadIdx.x, fb1 = fb0 + 1;
+  const double fq1 = fa0 + 1.5, fq2 = fa0 + 2.5, fq3 = fa0 + 3.5;
+#pragma unroll 4
   for (int i = 0; i < ITERS; ++i) {
-#define MMA(c) asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
-      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(fa0), "d"(fa1), "d"(fa2), "d"(fa3), "d"(fb0), "d"(fb1));
-    MMA(c0) MMA(c1) MMA(c2) MMA(c3)
+#define MMA(c, q) asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(q), "d"(fa1), "d"(fa2), "d"(fa3), "d"(fb0), "d"(fb1));
+    MMA(c0, fa0) MMA(c1, fq1) MMA(c2, fq2) MMA(c3, fq3)
 #undef MMA
   }
   double s = 0;
@@ -49,12 +56,14 @@ __global__ void k_dmma1688(double* out, double a, double b) {
 
 // m16n8k4
 __global__ void k_dmma1684(double* out, double a, double b) {
-  double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, c3[4] = {0, 0, 0, 0};
+  double c0[4] = {0, 1, 2, 3}, c1[4] = {4, 5, 6, 7}, c2[4] = {8, 9, 10, 11}, c3[4] = {12, 13, 14, 15};
   double fa0 = a + threadIdx.x, fa1 = fa0 + 1, fb0 = b + threadIdx.x;
+  const double fq1 = fa0 + 1.5, fq2 = fa0 + 2.5, fq3 = fa0 + 3.5;
+#pragma unroll 4
   for (int i = 0; i < ITERS; ++i) {
-#define MMA(c) asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};" \
-      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(fa0), "d"(fa1), "d"(fb0));
-    MMA(c0) MMA(c1) MMA(c2) MMA(c3)
+#define MMA(c, q) asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};" \
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3]) : "d"(q), "d"(fa1), "d"(fb0));
+    MMA(c0, fa0) MMA(c1, fq1) MMA(c2, fq2) MMA(c3, fq3)
 #undef MMA
   }
   double s = 0;
