@@ -59,11 +59,15 @@ WORKLOAD = dict(name="replogle_k562_gcate_lfc_batch", n_ctrl=2000, n_perts=15, c
                 counts_dtype="int32")     # host storage type of the UMI counts
 
 
-def make_batch(seed, p=None):
+def make_batch(seed, p=None, cells_frac=1.0):
+    """One synthetic batch of the workload shape; ``p`` / ``cells_frac`` shrink it for the bounded
+    samples of the CPU arms (fewer genes; control and per-perturbation cell counts scaled together)."""
     from causarray_b200.synth import simulate_screen
     from causarray_b200.prep import prep_causarray_data
     w = WORKLOAD
-    sim = simulate_screen(n_ctrl=w["n_ctrl"], n_perts=w["n_perts"], cells_per_pert=w["cells_per_pert"],
+    n_ctrl = max(50, int(round(w["n_ctrl"] * cells_frac)))
+    cpp = max(10, int(round(w["cells_per_pert"] * cells_frac)))
+    sim = simulate_screen(n_ctrl=n_ctrl, n_perts=w["n_perts"], cells_per_pert=cpp,
                           p=p or w["p"], r=w["r"], d_cov=1, family=w["family"], seed=seed, base_lo=-1.5, base_hi=1.5)
     Y, A = sim["Y"], sim["A"]
     _, _, X, X_A = prep_causarray_data(Y, A)
@@ -142,6 +146,58 @@ def gpu_step(batch, resident_ws=None):
     return df, stats
 
 
+FULL_CALL = dict(n_ctrl=2000, n_perts=200, cells_per_pert=390, batch_size=15, max_cells=2000)
+
+
+def full_call(rank, world, barrier):
+    """The north_star's quoted call: ONE public ``gcate_lfc_batch(Y, X, A, 10, W_A=X_A, batch_size=15,
+    max_cells=2000, n_ctrl=2000, family='nb', ...)`` on the 200-perturbation screen exactly as
+    SURVEY.md section 8d (C3) spells it -- control subsampling, 14 batches, concatenated frame --
+    wall-clock, host arrays in, DataFrame out, batches sharded over the ranks."""
+    import causarray_b200 as cb
+    from causarray_b200.synth import simulate_screen_fast
+    from causarray_b200.prep import prep_causarray_data
+    w, f = WORKLOAD, FULL_CALL
+    t0 = time.perf_counter()
+    sim = simulate_screen_fast(n_ctrl=f["n_ctrl"], n_perts=f["n_perts"], cells_per_pert=f["cells_per_pert"], p=w["p"],
+                               r=w["r"], family=w["family"], seed=7, base_lo=-1.5, base_hi=1.5)
+    Y, A = sim["Y"], sim["A"]
+    Yc, _, X, X_A = prep_causarray_data(Y, A)
+    Yc = np.ascontiguousarray(Yc.astype(w["counts_dtype"]))
+    t_gen = time.perf_counter() - t0
+    es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
+    kw = dict(W_A=X_A, batch_size=f["batch_size"], max_cells=f["max_cells"], n_ctrl=f["n_ctrl"], family=w["family"],
+              lfc_kwargs=dict(usevar=w["usevar"]),
+              gcate_kwargs=dict(disp_glm=sim["disp"], kwargs_es_1=dict(es), kwargs_es_2=dict(es)), random_state=0)
+    barrier()
+    t0 = time.perf_counter()
+    df = cb.gcate_lfc_batch(Yc, X, A, w["r"], **kw)
+    barrier()
+    dt = time.perf_counter() - t0
+    n_batches = -(-f["n_perts"] // f["batch_size"])
+    out = {"seconds": round(dt, 3), "n_cells_total": int(Y.shape[0]), "n_genes": int(Y.shape[1]),
+           "perturbations": f["n_perts"], "batches": n_batches, "n_gpus": world,
+           "call": "gcate_lfc_batch(Y, X, A, 10, W_A=X_A, batch_size=15, max_cells=2000, n_ctrl=2000, family='nb', "
+                   "lfc_kwargs=dict(usevar='unequal'), gcate_kwargs=dict(disp_glm=..., kwargs_es_1/2=dict(rel_tol=2e-4, "
+                   "max_iters=30)), random_state=0)",
+           "h2d_bytes": int(n_batches * (f["n_ctrl"] + f["batch_size"] * min(f["cells_per_pert"], f["max_cells"] // f["batch_size"]))
+                            * Y.shape[1] * Yc.dtype.itemsize),
+           "data_generation_s_untimed": round(t_gen, 1)}
+    if rank == 0 and df is not None:
+        out["result_rows"] = int(df.shape[0])
+        out["n_significant"] = int(np.nansum(df["padj"].to_numpy() < 0.05))
+    ref = full_size_reference_record()
+    if ref is not None:
+        cpu_s = ref["seconds_per_batch"] * n_batches
+        out["cpu_reference_extrapolated_s"] = round(cpu_s, 0)
+        out["cpu_reference_note"] = ("%d batches x %.1f s: the unmodified reference timed on ONE full-size batch "
+                                     "(%d cells x %d genes) on %d host cores of a B200 box, %s; batches are independent "
+                                     "and equally sized" % (n_batches, ref["seconds_per_batch"], ref["n_cells"],
+                                                           ref["n_genes"], ref["cores"], ref["source"]))
+        out["speedup_vs_cpu_reference"] = round(cpu_s / dt, 1)
+    return out
+
+
 def cpu_step(batch, n_jobs):
     from oracle import pipeline as op
     w = WORKLOAD
@@ -164,13 +220,15 @@ def reference_step(batch):
     return st
 
 
-def reference_arm(steps, warmup, p_s, kind):
-    """Times the CPU implementation of the step on this box's host cores on a gene subsample of the
-    same batch shape.  kind = "reference": the unmodified reference package (numba JIT warmed up
-    first, excluded from the timing); kind = "port": the C/OpenMP + numpy restatement of oracle/."""
+def reference_arm(steps, warmup, p_s, cells_frac, kind):
+    """Times the CPU implementation of the step on this box's host cores on a bounded sample of the
+    same batch shape (fewer genes, and -- when the budget per step is small -- a quarter of the
+    cells: both the per-cell and the per-gene loops of the reference carry a fixed cost per row, so a
+    sample that keeps both dimensions in the hundreds stays close to the full-size throughput).
+    kind = "reference": the unmodified reference package (numba JIT warmed up first, excluded from the
+    timing); kind = "port": the C/OpenMP + numpy restatement of oracle/."""
     cores = os.cpu_count() or 1
     w = WORKLOAD
-    n = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
     jit_s = None
     if kind == "reference":
         os.environ.setdefault("NUMBA_NUM_THREADS", str(cores))
@@ -187,8 +245,10 @@ def reference_arm(steps, warmup, p_s, kind):
                % (cores, cores))
     times, upd = [], []
     stats = None
+    n = None
     for s in range(warmup + steps):
-        batch = make_batch(1000 + s, p=p_s)
+        batch = make_batch(1000 + s, p=p_s, cells_frac=cells_frac)
+        n = batch["Y"].shape[0]
         t0 = time.perf_counter()
         stats = step(batch)
         dt = time.perf_counter() - t0
@@ -197,12 +257,44 @@ def reference_arm(steps, warmup, p_s, kind):
             upd.append(stats["cell_gene_updates"])
     T = sum(times)
     value = sum(upd) / T
-    sample = ("one batch of the same shape (n=%d cells, r=%d, %d perturbations) restricted to %d of %d genes; %s"
-              % (n, w["r"], w["n_perts"], p_s, w["p"], how))
+    sample = ("one batch of the workload shape (r=%d, %d perturbations) restricted to %d of %d cells and %d of %d genes; %s"
+              % (w["r"], w["n_perts"], n, w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"], p_s, w["p"], how))
     return dict(value=value, ms_per_step=1e3 * T / max(1, len(times)), cores=cores, kind=kind, sample=sample,
-                jit_warmup_s=jit_s, n_genes_sample=p_s,
+                jit_warmup_s=jit_s, n_genes_sample=p_s, n_cells_sample=n,
                 phases_s={k: round(v, 3) for k, v in stats.items() if k.startswith("t_")},
                 work_last_step={k: int(stats[k]) for k in ("alt_iters", "irls_gene_iters") if k in stats})
+
+
+def full_size_reference_record():
+    """The reference timed at the FULL batch size on a B200 box's host cores (tools/ref_parity.py,
+    committed record): context for the bounded samples above."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_config3_ref_parity.json")) as f:
+            r = json.load(f)
+        return {"source": "profiles/r02_config3_ref_parity.json (tools/ref_parity.py --config 3)",
+                "n_cells": r["n"], "n_genes": r["p"], "seconds_per_batch": r["reference_seconds"],
+                "cores": r["reference_cores"], "updates_per_s": r["reference_updates_per_s"],
+                "tau_rel_max_vs_device": r["tau_rel_max"], "std_rel_max_vs_device": r["std_rel_max"],
+                "rejections_differ": r["rejections_differ"]}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def sample_shape(kind, nsteps, genes=None, cells_frac=None):
+    """Sample of the CPU arms: about 240 s of CPU work over all steps (reference: ~7e6 updates/s on 16
+    cores, ~90 update-equivalents per cell and gene of a step)."""
+    w = WORKLOAD
+    if genes is not None:
+        return int(genes), (1.0 if cells_frac is None else float(cells_frac))
+    cores = os.cpu_count() or 1
+    rate = (7.0e6 if kind == "reference" else 2.5e7) * cores / 16.0
+    units = 240.0 / max(1, nsteps) * rate / 90.0
+    n_full = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
+    if cells_frac is None:
+        cells_frac = 1.0 if units >= n_full * 1000 else 0.25
+    n_s = n_full * cells_frac
+    p_s = int(max(256, min(w["p"], units / n_s))) // 8 * 8
+    return p_s, cells_frac
 
 
 def reference_kind():
@@ -215,25 +307,20 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     kind = args.cpu_impl or reference_kind()
-    nsteps = args.steps + args.warmup
-    p_s = args.cpu_genes
-    if p_s is None:
-        # about 200 s of CPU work in total: ~20 genes per second and step on 16 cores for the reference,
-        # ~70 for the port
-        rate = 20.0 if kind == "reference" else 70.0
-        p_s = int(max(64, min(WORKLOAD["p"], rate * (os.cpu_count() or 1) / 16.0 * 200.0 / max(1, nsteps))))
-        p_s = p_s // 8 * 8
-    r = reference_arm(args.steps, args.warmup, p_s, kind)
+    p_s, cf = sample_shape(kind, args.steps + args.warmup, args.cpu_genes, args.cpu_cells_frac)
+    r = reference_arm(args.steps, args.warmup, p_s, cf, kind)
     w = WORKLOAD
     n = w["n_ctrl"] + w["n_perts"] * w["cells_per_pert"]
     out = {"impl": "reference", "metric": "gcate_lfc_cell_gene_updates_per_s", "value": r["value"],
            "unit": "cell*gene updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": w["name"], "n_cells": n, "n_genes_sample": p_s, "n_genes": w["p"], "r": w["r"],
+           "config": {"workload": w["name"], "n_cells": n, "n_cells_sample": r["n_cells_sample"],
+                      "n_genes_sample": p_s, "n_genes": w["p"], "r": w["r"],
                       "perturbations": w["n_perts"], "family": w["family"]},
            "cpu_baseline": {"value": r["value"], "unit": "cell*gene updates/s", "cores": r["cores"], "kind": r["kind"],
-                            "sample": r["sample"], "jit_warmup_s_excluded": r["jit_warmup_s"]},
+                            "sample": r["sample"], "jit_warmup_s_excluded": r["jit_warmup_s"],
+                            "full_size_record": full_size_reference_record()},
            "e2e": {"value": r["value"], "unit": "cell*gene updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "phases_s": r["phases_s"], "work_last_step": r["work_last_step"]}
     emit_json(out)
@@ -246,9 +333,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-genes", type=int, default=None, help="gene subsample of the CPU arms")
+    ap.add_argument("--cpu-cells-frac", type=float, default=None, help="cell subsample of the CPU arms")
     ap.add_argument("--cpu-impl", default=None, choices=["reference", "port"],
                     help="CPU arm: the staged reference package (default when present) or the oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-call", action="store_true", help="skip the whole-screen gcate_lfc_batch measurement")
     ap.add_argument("--genes", type=int, default=None, help="override p (debug only; makes the number invalid)")
     args = ap.parse_args()
     capture_stdout()
@@ -338,6 +427,12 @@ def main():
     t_e2e = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler is not None else None
+    e2e_full = None
+    if not args.no_full_call and args.genes is None:
+        try:
+            e2e_full = full_call(rank, world, barrier)
+        except Exception as exc:  # noqa: BLE001  (never lose the main line over the extra measurement)
+            e2e_full = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # max over ranks of the times, sum over ranks of the work
     if world > 1:
@@ -433,6 +528,7 @@ def main():
                    "h2d_bytes_per_step": int(batches[0]["Y"].nbytes + batches[0]["X"].nbytes
                                              + batches[0]["A"].nbytes + batches[0]["X_A"].nbytes),
                    "d2h_bytes_per_step": d2h},
+           "e2e_full": e2e_full,
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
            "phases_ms_per_step": phases,
            "work_per_step": {k: v / args.steps for k, v in st_sum.items()},
@@ -441,9 +537,9 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         # CPU baseline in a child process (the reference brings numba / OpenMP pools of its own): the
         # real reference when it is staged, and the oracle port beside it as a second, labelled number
-        def child(kind, genes):
+        def child(kind, genes, frac):
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--cpu-impl", kind, "--steps", "1",
-                   "--warmup", "0", "--cpu-genes", str(genes)]
+                   "--warmup", "0", "--cpu-genes", str(genes), "--cpu-cells-frac", str(frac)]
             try:
                 res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
                 line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
@@ -455,9 +551,11 @@ def main():
             except Exception as e:  # noqa: BLE001
                 return {"error": "%s: %s" % (type(e).__name__, e)}
         kind = reference_kind()
-        out["cpu_baseline"] = child(kind, args.cpu_genes or (320 if kind == "reference" else 400))
+        # ~25 s of CPU work: a quarter of the cells x 2000 genes for the reference, all cells x 400 genes for the port
+        out["cpu_baseline"] = (child(kind, args.cpu_genes or 2000, args.cpu_cells_frac or 0.25) if kind == "reference"
+                               else child(kind, args.cpu_genes or 400, args.cpu_cells_frac or 1.0))
         if kind == "reference":
-            out["cpu_baseline_port"] = child("port", args.cpu_genes or 400)
+            out["cpu_baseline_port"] = child("port", args.cpu_genes or 400, args.cpu_cells_frac or 1.0)
     emit_json(out)
     if world > 1:
         dist.destroy_process_group()
