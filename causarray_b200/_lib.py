@@ -106,6 +106,7 @@ _SIGNATURES = {
     "ca_test_fastmath": [_D, _c_int, _c_int, _D],
     "ca_host_bh_rows": [_D, _c_int, _c_int, _D],
     "ca_host_median_mad_rows": [_D, _c_int, _c_int, _D, _D],
+    "ca_inference_tail": [_D, _D, _c_int, _c_int, _D, _D, _D, _D, _D],
 }
 _RESTYPE = {"ca_last_error": ctypes.c_char_p, "ca_profile_class_name": ctypes.c_char_p,
             "ca_launch_count": ctypes.c_int64}

@@ -28,7 +28,7 @@ from sklearn.model_selection import KFold
 
 from . import glm as _glm_mod
 from .device import GlmDevice, aipw_lfc, aipw_lfc_yhat
-from .inference import bh_correction, bh_correction_multi, fdx_control
+from .inference import bh_correction, bh_correction_device, bh_correction_multi, fdx_control
 from .prep import comp_size_factor, _filter_params, reset_random_seeds
 from ._timing import phase
 
@@ -493,7 +493,7 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
             std_all = np.sqrt(var_all)
             t_all = tau_all / std_all
         t_all[np.isinf(std_all)] = np.nan
-        pv, qv, pva, qva = bh_correction_multi(t_all, df=df_all)
+        pv, qv, pva, qva = bh_correction_device(t_all, df=df_all)
         gn = np.asarray(list(gene_names))
         cols = {'gene_names': _repeated_labels(gn, np.tile(np.arange(p), n_trt)), 'tau': tau_all.ravel(),
                 'std': std_all.ravel(),

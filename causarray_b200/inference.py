@@ -136,6 +136,22 @@ def _tail_parallel(x, dfa):
     return out.reshape(np.shape(x))
 
 
+def bh_correction_device(tvalues, df=None):
+    """``bh_correction`` of every row of ``tvalues (a, p)`` -- one BH family per treatment, as the
+    reference loops over treatments (``causarray/DR_learner.py:225-231``) -- on the device
+    (``ca_inference_tail``, ``csrc/inference.cu``): Student-t / normal tails, per-row bitonic sorts for
+    the BH step-up and the median / MAD of the empirical null.  Raises without a CUDA device."""
+    from . import _lib as L
+    lib = L.load()
+    t = np.ascontiguousarray(tvalues, dtype=np.float64)
+    if t.ndim != 2:
+        raise ValueError('tvalues must be (a, p)')
+    dfa = None if df is None else np.ascontiguousarray(np.broadcast_to(np.asarray(df, dtype=np.float64), t.shape))
+    out = [np.empty_like(t) for _ in range(4)]
+    L.check(lib.ca_inference_tail(L.dptr(t), L.dptr(dfa), t.shape[0], t.shape[1], *(L.dptr(o) for o in out), None))
+    return tuple(out)
+
+
 def bh_correction_multi(tvalues, df=None):
     """``bh_correction`` applied to every row of ``tvalues (a, p)`` (one BH family per treatment, as
     the reference loops over treatments).  The tail probabilities call ``scipy.special.stdtr`` /

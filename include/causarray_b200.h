@@ -242,6 +242,15 @@ int ca_aipw_lfc_yhat(int n, int p, int a, const double* Y, const double* Yhat, c
 int ca_host_bh_rows(const double* p, int a, int m, double* q);
 int ca_host_median_mad_rows(const double* t, int a, int m, double* med, double* mad);
 
+/* The same tail on the device, all treatments in one call (replaces the per-treatment
+ * bh_correction loop of causarray/DR_learner.py:225-231 / DR_inference.py:153-201).
+ * t, df: (a, p) row-major HOST arrays of test statistics (NaN = not tested) and degrees of freedom
+ * (df == NULL: normal tails, scipy.stats.norm.sf; else Student-t, scipy.stats.t.sf); outputs (a, p)
+ * host arrays: two-sided p-values, BH q-values within each row, and both after the empirical-null
+ * standardisation (t - median) / (MAD / Phi^-1(3/4)) (NaN rows when MAD == 0); med_mad (a, 2) or NULL. */
+int ca_inference_tail(const double* t, const double* df, int a, int p, double* pvalue, double* padj,
+                      double* pvalue_adj, double* padj_adj, double* med_mad);
+
 /* ------------------------------------------------------------------------
  * Measurement hooks (bench.py): per-kernel-class device time from CUDA events
  * recorded on the launching stream, and the number of kernels launched so far.

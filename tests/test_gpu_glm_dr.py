@@ -157,3 +157,36 @@ def test_aipw_lfc_golden(golden_dir, usevar):
     np.testing.assert_allclose(out2["tau"].reshape(-1), g["df_tau"], rtol=1e-9, atol=1e-12)
     std2 = np.sqrt(out2["var"]).reshape(-1)
     np.testing.assert_allclose(std2[fin], g["df_std"][fin], rtol=1e-9)
+
+
+def test_inference_tail_device_vs_scipy_and_host_bh():
+    """Device inference tail (csrc/inference.cu: Student-t / normal two-sided tails by the incomplete
+    beta continued fraction, per-treatment BH by bitonic sort + reverse running minimum, median / MAD
+    empirical null) against scipy.stats.t.sf / norm.sf and the reference-equivalent host path
+    (causarray/DR_inference.py:153-201; inference.bh_correction is pinned on the reference golden in
+    tests/test_oracle_golden.py::test_misc_golden)."""
+    import scipy.stats
+    from causarray_b200 import inference as inf
+    rng = np.random.default_rng(5)
+    a, p = 7, 3001
+    t = rng.standard_normal((a, p)) * 1.3
+    t[:, :200] += rng.choice([-1.0, 1.0], (a, 200)) * rng.uniform(3, 12, (a, 200))
+    t[1, 5:40] = np.nan                      # not tested
+    t[2, :] = np.nan                         # a treatment with nothing to test
+    t[3, 10] = t[3, 11]                      # tie
+    t[4, :] = 0.25                           # MAD = 0: adjusted columns stay NaN
+    t[5, 7] = 38.0                           # p-value ~ 1e-100 territory
+    df = rng.uniform(1.5, 4000.0, (a, p))
+    df[np.isnan(t)] = np.nan
+    for dfa in (df, None):
+        pv, qv, pva, qva = inf.bh_correction_device(t, df=dfa)
+        with np.errstate(invalid="ignore"):
+            ref_p = (scipy.stats.t.sf(np.abs(t), dfa) if dfa is not None else scipy.stats.norm.sf(np.abs(t))) * 2
+        np.testing.assert_allclose(pv, ref_p, rtol=1e-10, atol=1e-300, equal_nan=True)
+        for j in range(a):
+            hp, hq, hpa, hqa = inf.bh_correction(t[j], df=None if dfa is None else dfa[j])
+            np.testing.assert_allclose(qv[j], hq, rtol=1e-10, atol=1e-300, equal_nan=True)
+            np.testing.assert_allclose(pva[j], hpa, rtol=1e-9, atol=1e-300, equal_nan=True)
+            np.testing.assert_allclose(qva[j], hqa, rtol=1e-9, atol=1e-300, equal_nan=True)
+            assert np.array_equal(qv[j] < 0.05, hq < 0.05)
+    assert np.isnan(pva[4]).all() and np.isnan(qva[2]).all()
