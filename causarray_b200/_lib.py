@@ -103,6 +103,8 @@ _SIGNATURES = {
     "ca_profile_class_name": [_c_int],
     "ca_profile_get": [_c_int, _D, ctypes.POINTER(ctypes.c_int64)],
     "ca_launch_count": [],
+    "ca_nvtx_push": [ctypes.c_char_p],
+    "ca_nvtx_pop": [],
     "ca_test_fastmath": [_D, _c_int, _c_int, _D],
     "ca_host_bh_rows": [_D, _c_int, _c_int, _D],
     "ca_host_median_mad_rows": [_D, _c_int, _c_int, _D, _D],

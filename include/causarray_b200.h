@@ -261,6 +261,10 @@ int ca_profile_num_classes(void);
 const char* ca_profile_class_name(int cls);
 int ca_profile_get(int cls, double* total_ms, int64_t* launches);
 int64_t ca_launch_count(void);
+/* NVTX ranges for the host-side phases (size factors, GLM initialisation, alternating minimisation,
+ * propensities, AIPW, inference); the kernel classes push their own ranges inside the library. */
+int ca_nvtx_push(const char* name);
+int ca_nvtx_pop(void);
 /* Test hook: out[i] = fm_exp(x[i]) (op 0, -700 <= x <= 100) or fm_log(x[i]) (op 1, x > 0 normal),
  * the table-driven FP64 functions of csrc/fastmath.cuh. */
 int ca_test_fastmath(const double* x, int n, int op, double* out);
