@@ -200,8 +200,8 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   const int n = h->n, p = h->p, kx = L.kx, kde = L.kde;
   cudaStream_t st = h->st;
   const size_t smem = glm_irls_smem_bytes(kde, kx, lasso);
-  if (smem > 200 * 1024) return 1;
-  const int ldxd = (kde + 2) & ~1;
+  if (smem > 226 * 1024) return 1;   // (227 KB of dynamic shared memory per CTA on sm_100a)
+  const int ldxd = (kde + 1) | 1;
   // ---- counts in the sorted padded cell order (cached across the fits of a batch) ----
   const long ldp = L.npad;
   if (h->perm_host != L.perm || !h->Yp.ptr || h->Yp_src != h->Yt) {

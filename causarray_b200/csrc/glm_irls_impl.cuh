@@ -92,7 +92,8 @@ struct IrlsShape {
   static constexpr int NTW = NB * KDE - 8 * (NB * (NB - 1) / 2);  // strip tiles: sum_b (KDE - 8 b)
   static constexpr int NT = NTW + NB;                  // + right-hand-side tiles
   static constexpr int FLT = NB + 1;                   // tiles flushed per group: (b, U) for every b, rhs(NB - 1)
-  static constexpr int LDXD = (KDE + 2) & ~1;          // dense columns + offset, even
+  static constexpr int LDXD = (KDE + 1) | 1;           // dense columns + offset; odd: a half-warp reading one
+                                                       // row per lane then touches 16 distinct bank pairs
   __host__ __device__ static constexpr int tw(int b, int j) { return b * KDE - 8 * (b * (b - 1) / 2) + (j - 8 * b); }
 };
 
@@ -100,9 +101,11 @@ inline size_t glm_irls_smem_bytes(int kde, int kx, bool lasso) {
   const int nb = (kde + 7) / 8;
   const int ntw = nb * kde - 8 * (nb * (nb - 1) / 2);
   const int nt = ntw + nb;
-  const int ldxd = (kde + 2) & ~1;
+  const int ldxd = (kde + 1) | 1;
   size_t d = 0;
-  d += (size_t)IRLS_WARPS * 2 * (IRLS_CHUNK * ldxd + 8);      // staging (+ slack for the masked row-block reads)
+  d += (size_t)IRLS_WARPS * 2 * (((IRLS_CHUNK * ldxd + 8) + 1) & ~1);  // staging (+ slack for the masked row-block reads)
+  d += (size_t)IRLS_WARPS * 2 * IRLS_CHUNK * 9;               // weights / weighted responses handed from the evaluation to the DMMA phase
+  d += (size_t)8 * (kde + 4);                                 // dense coefficients, nu, ybar, flags of the octet
   d += (size_t)nt * 64;                                       // dense totals
   d += (size_t)IRLS_WARPS * 8;                                // deviance partials
   d += (size_t)8 * kx;                                        // coefficients of the octet
@@ -115,7 +118,8 @@ template <int KDE, bool NBF>
 __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_constant__ GlmIrls P) {
   using S = IrlsShape<KDE>;
   constexpr int NB = S::NB, U = S::U, NTW = S::NTW, NT = S::NT, FLT = S::FLT, LDXD = S::LDXD;
-  constexpr int STG = IRLS_CHUNK * LDXD + 8;
+  constexpr int STG = ((IRLS_CHUNK * LDXD + 8) + 1) & ~1;   // even: every stage starts 16-byte aligned (bulk copies)
+  constexpr int WLD = 9;                                    // row stride of the weight hand-off buffers (odd)
   extern __shared__ __align__(16) double smem[];
   const int kx = P.kx;
   const bool lasso = P.l1 != nullptr;
@@ -125,11 +129,17 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
   double* betas = Dp + IRLS_WARPS * 8;                     // 8 * kx
   double* work_all = betas + 8 * kx;
   const size_t work_d = glm_solve_work_doubles(kx, lasso);
-  double* s_tab = work_all + IRLS_WARPS * work_d;
+  double* wbuf_all = work_all + IRLS_WARPS * work_d;       // IRLS_WARPS * 2 * IRLS_CHUNK * WLD
+  double* bdense = wbuf_all + IRLS_WARPS * 2 * IRLS_CHUNK * WLD;  // 8 * KDE
+  double* s_nu = bdense + 8 * KDE;                         // 8
+  double* s_ybar = s_nu + 8;                               // 8
+  double* s_flag = s_ybar + 8;                             // 8: bit 0 Poisson branch, bit 1 observed-information weights
+  double* s_tab = s_flag + 16;
   __shared__ __align__(8) unsigned long long bars[IRLS_WARPS * 2];
   __shared__ int s_octet, s_nrun;
   __shared__ int s_gene[8], s_status[8], s_niter[8];
   __shared__ double s_devprev[8], s_dev[8], s_step[8];
+  __shared__ signed char s_gcol[64];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lr = lane >> 2, lc = lane & 3;
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
     mbar_init(bar + 1, 1);
   }
   for (int i = lane; i < 2 * STG; i += 32) xs[i] = 0.0;
+  if (tid < 64) s_gcol[tid] = P.gcol[tid];
   if (tid == 0) mbar_fence_init();
   __syncthreads();
   fence_proxy_async();
@@ -174,31 +185,50 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
       betas[e] = (g >= 0 && P.iter0) ? P.beta[(size_t)g * kx + (e % kx)] : 0.0;
     }
     __syncthreads();
-    const int my_gene = s_gene[lr];
-    const int row_gene = my_gene >= 0 ? my_gene : (s_gene[0] >= 0 ? s_gene[0] : 0);
-    const double* yrow = P.Yp + (size_t)row_gene * P.ldp;
-    double nu = 1.0;
-    bool pois = true;
-    if (NBF && P.nu) {
-      nu = P.nu[row_gene];
-      pois = nu > P.thres;
+    // per-gene constants of the octet (a padding slot of the last octet borrows gene 0's row and is never stored)
+    if (tid < 8) {
+      const int g = s_gene[tid] >= 0 ? s_gene[tid] : (s_gene[0] >= 0 ? s_gene[0] : 0);
+      double nu = 1.0;
+      bool pois = true;
+      if (NBF && P.nu) {
+        nu = P.nu[g];
+        pois = nu > P.thres;
+      }
+      s_nu[tid] = nu;
+      s_ybar[tid] = P.ybar[g];
+      s_flag[tid] = pois ? 1.0 : 0.0;
     }
-    const double ybar = P.ybar[row_gene];
+    __syncthreads();
+    const double* ybase = P.Yp + (size_t)(c_lo < c_hi ? c_lo : 0) * IRLS_CHUNK + lane;
+    long yoff[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      yoff[g] = (long)(s_gene[g] >= 0 ? s_gene[g] : (s_gene[0] >= 0 ? s_gene[0] : 0)) * P.ldp;
+    double* wbuf = wbuf_all + warp * 2 * IRLS_CHUNK * WLD;   // w, then w z: [cell of the chunk][gene], row stride WLD
+    double* wzbuf = wbuf + IRLS_CHUNK * WLD;
 
     for (int it = 1;; ++it) {
       const int iter = it + P.iter0;            // 1: the pass from mu0 = (y + ybar) / 2
       const bool first = iter == 1;
-      const bool newton = NBF && lasso && !first && !pois && s_step[lr] <= 1e-2;
+      // dense coefficients of the 8 genes in the internal column order; observed-information switch
+      for (int e = tid; e < 8 * KDE; e += IRLS_THREADS) {
+        const int g = e / KDE, i = e - g * KDE;
+        bdense[e] = P.dcol[i] >= 0 ? betas[g * kx + P.dcol[i]] : 0.0;
+      }
+      if (tid < 8) {
+        const bool pois = ((int)s_flag[tid] & 1) != 0;
+        const bool nwt = NBF && lasso && !first && !pois && s_step[tid] <= 1e-2;
+        s_flag[tid] = (pois ? 1.0 : 0.0) + (nwt ? 2.0 : 0.0);
+      }
+      __syncthreads();
       // ---------------- pass over this warp's chunks ----------------
-      double bd[KDE];
-#pragma unroll
-      for (int i = 0; i < KDE; ++i) bd[i] = P.dcol[i] >= 0 ? betas[lr * kx + P.dcol[i]] : 0.0;
       double acc[NT][2];
 #pragma unroll
       for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
-      double dsum = 0.0;
+      double dacc[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) dacc[g] = 0.0;
       int gcur = -1, seg = P.seg_ptr[warp];
-      double bg = 0.0;
       auto issue = [&](int c, int stage) {
         const unsigned bytes = (unsigned)(IRLS_CHUNK * LDXD * sizeof(double));
         mbar_expect_tx(bar + stage, bytes);
@@ -219,75 +249,56 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
         if (c_lo < c_hi) issue(c_lo, 0);
         if (c_lo + 1 < c_hi) issue(c_lo + 1, 1);
       }
+      // counts of this lane's cell of the chunk, one per gene (256 contiguous bytes per gene and load)
       double ycur[8], ynext[8];
       if (c_lo < c_hi) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ycur[q] = yrow[(size_t)c_lo * IRLS_CHUNK + q * 4 + lc];
+        for (int g = 0; g < 8; ++g) ycur[g] = ybase[yoff[g]];
       }
       for (int c = c_lo; c < c_hi; ++c) {
         const int stage = (c - c_lo) & 1;
         if (c + 1 < c_hi) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) ynext[q] = yrow[(size_t)(c + 1) * IRLS_CHUNK + q * 4 + lc];
+          for (int g = 0; g < 8; ++g) ynext[g] = ybase[yoff[g] + (size_t)(c + 1 - c_lo) * IRLS_CHUNK];
         }
         mbar_wait(bar + stage, (fphase >> stage) & 1u);
         fphase ^= 1u << stage;
         const double* xc = xs + stage * STG;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const int g = __ldg(P.gpair + c * 4 + q);
-          if (g != gcur) {
-            if (gcur >= 0) flush();
-            gcur = g;
-            bg = g > 0 ? betas[lr * kx + P.gcol[g]] : 0.0;
-          }
-          double wv[2], wzv[2], xv[2][LDXD];
+        // ===== evaluation: lane = cell of the chunk, the 8 genes are 8 independent chains =====
+        {
+          const double* xr = xc + lane * LDXD;
+          double x[KDE];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const double* xr = xc + ((2 * q + h) * 4 + lc) * LDXD;
+          for (int i = 0; i < KDE; ++i) x[i] = xr[i];
+          const double off = xr[KDE];
+          const double vld = x[U];                 // 1 for a cell, 0 for a padding row
+          const int grp = __ldg(P.gpair + c * 4 + (lane >> 3));
+          const int gc = grp > 0 ? (int)s_gcol[grp] : -1;
 #pragma unroll
-            for (int i = 0; i < LDXD; i += 2) {
-              const double2 t = *reinterpret_cast<const double2*>(xr + i);
-              xv[h][i] = t.x;
-              xv[h][i + 1] = t.y;
-            }
-          }
-          // counts of this pair-step: the chunk's eight values are shifted through ycur (a register
-          // array indexed by the loop variable would live in local memory)
-          const double yv[2] = {ycur[0], ycur[1]};
-#pragma unroll
-          for (int i = 0; i < 6; ++i) ycur[i] = ycur[i + 2];
-          double etav[2], ecv[2], muv[2];
-          if (first) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              muv[h] = 0.5 * (yv[h] + ybar);
-              etav[h] = fm_log(muv[h], FT.log_t);
-              ecv[h] = etav[h];
-            }
-          } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              double ea = bg + xv[h][KDE], eb = 0.0;
+          for (int g = 0; g < 8; ++g) {
+            const double y = ycur[g];
+            const double nu = s_nu[g];
+            const int fl = (int)s_flag[g];
+            const bool pois = (fl & 1) != 0;
+            double eta, ec, mu;
+            if (first) {
+              mu = 0.5 * (y + s_ybar[g]);
+              eta = fm_log(mu, FT.log_t);
+              ec = eta;
+            } else {
+              const double* bg = bdense + g * KDE;
+              double ea = off + (gc >= 0 ? betas[g * kx + gc] : 0.0), eb = 0.0;
 #pragma unroll
               for (int i = 0; i + 1 < KDE; i += 2) {
-                ea = fma(xv[h][i], bd[i], ea);
-                eb = fma(xv[h][i + 1], bd[i + 1], eb);
+                ea = fma(x[i], bg[i], ea);
+                eb = fma(x[i + 1], bg[i + 1], eb);
               }
-              if (KDE & 1) ea = fma(xv[h][KDE - 1], bd[KDE - 1], ea);
-              const double eta = ea + eb;
-              double ec = eta < 700.0 ? eta : 700.0;
+              if (KDE & 1) ea = fma(x[KDE - 1], bg[KDE - 1], ea);
+              eta = ea + eb;
+              ec = eta < 700.0 ? eta : 700.0;
               ec = ec > -700.0 ? ec : -700.0;
-              etav[h] = eta;
-              ecv[h] = ec;
-              muv[h] = fm_exp(ec, FT.exp_t);
+              mu = fm_exp(ec, FT.exp_t);
             }
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const double y = yv[h], eta = etav[h], ec = ecv[h], mu = muv[h];
-            const double off = xv[h][KDE];
-            const double vld = xv[h][U];           // 1 for a cell, 0 for a padding row
             // unit deviance / 2 : y log(max(y / mu, eps)) - (y - mu)                          (Poisson)
             //                     y log(max(y / mu, eps)) - (y + nu) log((y + nu) / (mu + nu)) (NB)
             const double ly = fm_log(y > 0.0 ? y : 1.0, FT.log_t);
@@ -302,23 +313,34 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
               d2 = pois ? d2 : (y + nu) * lt;
               wgt = pois ? mu : mu * nu * rc;
             }
-            dsum = fma(vld, fma(y, lrat, -d2), dsum);
+            dacc[g] = fma(vld, fma(y, lrat, -d2), dacc[g]);
             const double z = (eta - off) + (y - mu) * fm_rcp(mu);
             double w = wgt, wz = wgt * z;
-            if (NBF && newton) {
+            if (NBF && (fl & 2)) {
               // observed information of the NB2 log-likelihood: nu mu (nu + y) / (nu + mu)^2;
               // rhs = w (eta - off) + score (same minimiser, quadratic tail; lasso refit only)
               const double wn = mu * nu * rc * ((nu + y) * rc);
               w = wn;
               wz = fma(wn, eta - off, (y - mu) * (nu * rc));
             }
-            wv[h] = w;
-            wzv[h] = wz;
+            wbuf[lane * WLD + g] = w;
+            wzbuf[lane * WLD + g] = wz;
           }
-          // ---- Gram strips and right-hand side on the FP64 tensor cores ----
+        }
+        __syncwarp();
+        // ===== Gram strips and right-hand side on the FP64 tensor cores: lane = (cell lc of a step, gene lr) =====
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const int g = __ldg(P.gpair + c * 4 + q);
+          if (g != gcur) {
+            if (gcur >= 0) flush();
+            gcur = g;
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const double* xr = xc + ((2 * q + h) * 4 + lc) * LDXD;
+            const int cell = (2 * q + h) * 4 + lc;
+            const double* xr = xc + cell * LDXD;
+            const double w = wbuf[cell * WLD + lr], wz = wzbuf[cell * WLD + lr];
             double xa[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
@@ -327,25 +349,27 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
             }
 #pragma unroll
             for (int j = 0; j < KDE; ++j) {
-              const double bw = wv[h] * xv[h][j];
+              const double bw = w * xr[j];
 #pragma unroll
               for (int b = 0; b < NB; ++b)
                 if (j >= 8 * b) dmma884(acc[S::tw(b, j)][0], acc[S::tw(b, j)][1], xa[b], bw);
             }
 #pragma unroll
-            for (int b = 0; b < NB; ++b) dmma884(acc[NTW + b][0], acc[NTW + b][1], xa[b], wzv[h]);
+            for (int b = 0; b < NB; ++b) dmma884(acc[NTW + b][0], acc[NTW + b][1], xa[b], wz);
           }
         }
         __syncwarp();
         if (lane == 0 && c + 2 < c_hi) issue(c + 2, stage);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ycur[i] = ynext[i];
+        for (int g = 0; g < 8; ++g) ycur[g] = ynext[g];
       }
       if (gcur >= 0) flush();
       // ---------------- combine the warps (fixed order) ----------------
-      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
-      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-      if (lc == 0) Dp[warp * 8 + lr] = dsum;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const double v = warp_sum(dacc[g]);
+        if (lane == g) Dp[warp * 8 + g] = v;
+      }
       for (int w = 0; w < IRLS_WARPS; ++w) {
         if (warp == w) {
           double* dst = Tt + lr * 8 + 2 * lc;
@@ -405,9 +429,95 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
           }
         }
         if (run) {
+          const double* sc0 = scratch + g;   // column g of every flushed tile
+          int newst = 0;
+          if (!lasso) {
+            // Arrow structure of the normal equations: dense block D (KDE columns) + one diagonal entry
+            // d_g per one-hot group, coupled through c_g = (the (i, unit) products of group g):
+            //   G_DD b_D + sum_g c_g b_g = r_D,   c_g^T b_D + d_g b_g = r_g
+            // => (G_DD - sum_g c_g c_g^T / d_g) b_D = r_D - sum_g c_g r_g / d_g,  b_g = (r_g - c_g^T b_D) / d_g:
+            // an 11 x 11 Cholesky instead of a 26 x 26 one for [1, U(10) | A(15)] (the full solve and the
+            // kx^2 assembly were 32 % of the kernel's time, all of it with the FP64 pipe idle).
+            const int nd = P.dcol[U] >= 0 ? KDE : KDE - 1;     // an appended unit column is not a coefficient
+            const int ngr = P.ngroups - 1;
+            double* wk = work_all + (size_t)g * work_d;
+            const GlmSolveWork W = glm_solve_carve(wk, nd);
+            double* cg = wk + glm_solve_work_doubles(nd, false);  // ngr x (KDE + 1): c_g[0..KDE-1] (entry U = d_g), r_g
+            const int ld = nd + 1;
+            const int CL = KDE + 1;
+            for (int e = lane; e < ngr * CL; e += 32) {
+              const int gg = e / CL + 1, i = e - (gg - 1) * CL;
+              double v = 0.0;
+              const int off = i < KDE ? (i >> 3) * 64 + (i & 7) * 8 : NB * 64 + (U & 7) * 8;
+              for (int q = P.gseg_ptr[gg]; q < P.gseg_ptr[gg + 1]; ++q) v += sc0[(size_t)P.gseg_list[q] * (FLT * 64) + off];
+              if (i == U && P.ridge) v += P.ridge[P.gcol[gg]];
+              cg[e] = v;
+            }
+            for (int e = lane; e < nd * nd; e += 32) {
+              const int i = e / nd, j = e - i * nd;
+              const int a = i < j ? i : j, bb = i < j ? j : i;
+              double v = 0.0;
+              if (bb == U) {
+                for (int s2 = 0; s2 < P.nseg_tot; ++s2) v += sc0[(size_t)s2 * (FLT * 64) + (a >> 3) * 64 + (a & 7) * 8];
+              } else {
+                v = Tt[S::tw(a >> 3, bb) * 64 + (a & 7) * 8 + g];
+              }
+              if (P.ridge && i == j) v += P.ridge[P.dcol[i]];
+              W.L[i * ld + j] = v;
+            }
+            for (int i = lane; i < nd; i += 32) {
+              double v = 0.0;
+              if ((i >> 3) == NB - 1) {
+                for (int s2 = 0; s2 < P.nseg_tot; ++s2) v += sc0[(size_t)s2 * (FLT * 64) + NB * 64 + (i & 7) * 8];
+              } else {
+                v = Tt[(NTW + (i >> 3)) * 64 + (i & 7) * 8 + g];
+              }
+              W.b[i] = v;
+            }
+            __syncwarp();
+            bool bad = false;
+            for (int gg = lane; gg < ngr; gg += 32)
+              if (!(cg[gg * CL + U] > 0.0)) bad = true;
+            bad = __any_sync(0xffffffffu, bad);
+            if (!bad) {
+              for (int e = lane; e < nd * nd; e += 32) {
+                const int i = e / nd, j = e - i * nd;
+                double v = W.L[i * ld + j];
+                for (int gg = 0; gg < ngr; ++gg) v = fma(-cg[gg * CL + i] / cg[gg * CL + U], cg[gg * CL + j], v);
+                W.L[i * ld + j] = v;
+              }
+              for (int i = lane; i < nd; i += 32) {
+                double v = W.b[i];
+                for (int gg = 0; gg < ngr; ++gg) v = fma(-cg[gg * CL + i] / cg[gg * CL + U], cg[gg * CL + KDE], v);
+                W.b[i] = v;
+              }
+              __syncwarp();
+              bad = glm_solve_system(W, nd, nullptr, lane);
+            }
+            if (bad) {
+              newst = 2;
+            } else {
+              bool fin = true;
+              for (int i = lane; i < nd; i += 32) {
+                const double v = W.b[i] * W.sc[i];
+                W.b[i] = v;
+                betas[g * kx + P.dcol[i]] = v;
+                fin = fin && (v == v) && !isinf(v);
+              }
+              __syncwarp();
+              for (int gg = lane; gg < ngr; gg += 32) {
+                double v = cg[gg * CL + KDE];
+                for (int i = 0; i < nd; ++i) v = fma(-cg[gg * CL + i], W.b[i], v);
+                v /= cg[gg * CL + U];
+                betas[g * kx + P.gcol[gg + 1]] = v;
+                fin = fin && (v == v) && !isinf(v);
+              }
+              fin = __all_sync(0xffffffffu, fin);
+              if (!fin) newst = 2;
+            }
+          } else {
           const GlmSolveWork W = glm_solve_carve(work_all + (size_t)g * work_d, kx);
           const int ld = kx + 1;
-          const double* sc0 = scratch + g;   // column g of every flushed tile
           for (int e = lane; e < kx * kx; e += 32) {
             const int ci = e / kx, cj = e - ci * kx;
             const int di = P.cdense[ci], dj = P.cdense[cj];
@@ -447,7 +557,6 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
             W.b[c] = v;
           }
           __syncwarp();
-          int newst = 0;
           if (glm_solve_system(W, kx, P.l1, lane)) {
             newst = 2;
           } else {
@@ -464,6 +573,7 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
             if (lane == 0) s_step[g] = stepmax;
             fin = __all_sync(0xffffffffu, fin);
             if (!fin) newst = 2;
+          }
           }
           if (lane == 0) {
             if (newst) {
