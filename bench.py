@@ -198,6 +198,67 @@ def full_call(rank, world, barrier):
     return out
 
 
+def gene_shard_record(rank, world, barrier):
+    """Gene-sharded alternating minimisation on the driver's record (north_star: "partitioned across
+    the 8xB200 box by gene shards ... the cell-factor update all-reduces the per-cell gradient"):
+    ONE problem -- the benchmark batch with four times the cells (15,980 x 8,000, k = 26) -- with its
+    genes split over the N ranks, stage-1 iterations of ``update_with_mask`` (causarray/gcate_opt.py:
+    148-206): the gene step is local, the cell step all-reduces the (n x r) gradient block, the n
+    per-cell log-likelihoods and the n candidate objectives of every line-search round over NVLink.
+    Strong scaling: the N = 1 line of the same bench run at --gpus 1 is the baseline."""
+    import scipy.linalg
+    import torch
+    import torch.distributed as dist
+    from causarray_b200.device import GcateDevice, comm_unique_id
+    from causarray_b200.synth import simulate_screen_fast
+    w = WORKLOAD
+    sim = simulate_screen_fast(n_ctrl=4 * w["n_ctrl"], n_perts=w["n_perts"], cells_per_pert=4 * w["cells_per_pert"],
+                               p=w["p"], r=w["r"], family=w["family"], seed=11, base_lo=-1.5, base_hi=1.5)
+    Y, A = sim["Y"], sim["A"]
+    n, p = Y.shape
+    Xf = np.c_[np.ones((n, 1)), A]
+    d, r = Xf.shape[1], w["r"]
+    rng = np.random.default_rng(0)
+    A0 = np.c_[Xf, rng.standard_normal((n, r)) * 0.05]
+    B0 = np.c_[np.log(Y.mean(0) + 0.05)[:, None], rng.standard_normal((p, d - 1 + r)) * 0.05]
+    Q1 = scipy.linalg.qr(Xf, mode="economic")[0]
+    ls = np.log(np.maximum(Y.sum(1), 1))
+    sf = np.exp(ls - ls.mean())
+    edges = np.linspace(0, p, world + 1).astype(int)
+    lo, hi = int(edges[rank]), int(edges[rank + 1])
+    dev = GcateDevice(n, hi - lo, d, r, w["family"], 100.0)
+    if world > 1:
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        dev.set_shard(rank, world, p, box[0])
+    dev.load_counts(np.ascontiguousarray(Y[:, lo:hi], dtype=np.float64), sf, np.ascontiguousarray(sim["disp"][lo:hi]))
+    dev.set_factors(A0, np.ascontiguousarray(B0[lo:hi]))
+    dev.set_stage(P1=Q1, P2=None, lam=None, a=d)
+    for _ in range(3):
+        f = dev.update(1e3, 0.1, 0.5, 20, 1e-4)
+    barrier()
+    iters = 20
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        f = dev.update(1e3, 0.1, 0.5, 20, 1e-4)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / iters
+    barrier()
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    ldg = (r + 3) // 4 * 4
+    return {"workload": "alternating iteration (stage 1) of ONE fit, genes split over the ranks",
+            "n_cells": int(n), "n_genes": int(p), "k": int(d + r), "n_gpus": world, "genes_per_rank": int(hi - lo),
+            "ms_per_alt_iteration": round(1e3 * dt, 4), "cell_gene_updates_per_s": n * p / dt, "scaling": "strong",
+            "objective_after_23_iterations": float(f),
+            "allreduce_doubles_per_iteration": {"cell_gradient_and_loglik": int(n * (ldg + 1)),
+                                                "line_search_objectives_per_round": int(n), "scalars": 2},
+            "transport": ("single GPU" if world == 1 else
+                          "k_peer_allreduce over NVLink peer memory (2 ranks) / NCCL (CA_PEER_REDUCE unset, > 2 ranks)")}
+
+
 def cpu_step(batch, n_jobs):
     from oracle import pipeline as op
     w = WORKLOAD
@@ -338,6 +399,7 @@ def main():
                     help="CPU arm: the staged reference package (default when present) or the oracle port")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-call", action="store_true", help="skip the whole-screen gcate_lfc_batch measurement")
+    ap.add_argument("--no-gene-shard", action="store_true", help="skip the gene-sharded strong-scaling sub-record")
     ap.add_argument("--genes", type=int, default=None, help="override p (debug only; makes the number invalid)")
     args = ap.parse_args()
     capture_stdout()
@@ -433,6 +495,12 @@ def main():
             e2e_full = full_call(rank, world, barrier)
         except Exception as exc:  # noqa: BLE001  (never lose the main line over the extra measurement)
             e2e_full = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    gene_shard = None
+    if not args.no_gene_shard and args.genes is None:
+        try:
+            gene_shard = gene_shard_record(rank, world, barrier)
+        except Exception as exc:  # noqa: BLE001
+            gene_shard = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # max over ranks of the times, sum over ranks of the work
     if world > 1:
@@ -528,7 +596,7 @@ def main():
                    "h2d_bytes_per_step": int(batches[0]["Y"].nbytes + batches[0]["X"].nbytes
                                              + batches[0]["A"].nbytes + batches[0]["X_A"].nbytes),
                    "d2h_bytes_per_step": d2h},
-           "e2e_full": e2e_full,
+           "e2e_full": e2e_full, "gene_shard": gene_shard,
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
            "phases_ms_per_step": phases,
            "work_per_step": {k: v / args.steps for k, v in st_sum.items()},

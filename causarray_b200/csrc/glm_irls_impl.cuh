@@ -36,6 +36,7 @@
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "glm_solve.cuh"
+#include <type_traits>
 
 namespace ca {
 
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
   double* s_flag = s_ybar + 8;                             // 8: bit 0 Poisson branch, bit 1 observed-information weights
   double* s_tab = s_flag + 16;
   __shared__ __align__(8) unsigned long long bars[IRLS_WARPS * 2];
-  __shared__ int s_octet, s_nrun;
+  __shared__ int s_octet, s_nrun, s_anynewton;
   __shared__ int s_gene[8], s_status[8], s_niter[8];
   __shared__ double s_devprev[8], s_dev[8], s_step[8];
   __shared__ signed char s_gcol[64];
@@ -215,12 +216,16 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
         const int g = e / KDE, i = e - g * KDE;
         bdense[e] = P.dcol[i] >= 0 ? betas[g * kx + P.dcol[i]] : 0.0;
       }
+      if (tid == 0) s_anynewton = 0;
+      __syncthreads();
       if (tid < 8) {
         const bool pois = ((int)s_flag[tid] & 1) != 0;
         const bool nwt = NBF && lasso && !first && !pois && s_step[tid] <= 1e-2;
         s_flag[tid] = (pois ? 1.0 : 0.0) + (nwt ? 2.0 : 0.0);
+        if (nwt) s_anynewton = 1;
       }
       __syncthreads();
+      const bool any_newton = s_anynewton != 0;
       // ---------------- pass over this warp's chunks ----------------
       double acc[NT][2];
 #pragma unroll
@@ -265,6 +270,9 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
         fphase ^= 1u << stage;
         const double* xc = xs + stage * STG;
         // ===== evaluation: lane = cell of the chunk, the 8 genes are 8 independent chains =====
+        // (one straight-line body per mode -- first pass / regular / observed-information weights --
+        // so that ptxas interleaves the eight chains: with the mode tests inside the gene loop every
+        // gene was its own basic block and the chains ran one after the other)
         {
           const double* xr = xc + lane * LDXD;
           double x[KDE];
@@ -273,59 +281,72 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
           const double off = xr[KDE];
           const double vld = x[U];                 // 1 for a cell, 0 for a padding row
           const int grp = __ldg(P.gpair + c * 4 + (lane >> 3));
-          const int gc = grp > 0 ? (int)s_gcol[grp] : -1;
+          const int gc = grp > 0 ? (int)s_gcol[grp] : 0;
+          const double gsel = grp > 0 ? 1.0 : 0.0;
+          auto eval8 = [&](auto first_c, auto newton_c) {
+            constexpr bool FIRST = decltype(first_c)::value;
+            constexpr bool NEWTON = decltype(newton_c)::value;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const double y = ycur[g];
-            const double nu = s_nu[g];
-            const int fl = (int)s_flag[g];
-            const bool pois = (fl & 1) != 0;
-            double eta, ec, mu;
-            if (first) {
-              mu = 0.5 * (y + s_ybar[g]);
-              eta = fm_log(mu, FT.log_t);
-              ec = eta;
-            } else {
-              const double* bg = bdense + g * KDE;
-              double ea = off + (gc >= 0 ? betas[g * kx + gc] : 0.0), eb = 0.0;
+            for (int g = 0; g < 8; ++g) {
+              const double y = ycur[g];
+              const double nu = s_nu[g];
+              const int fl = (int)s_flag[g];
+              const bool pois = (fl & 1) != 0;
+              double eta, ec, mu;
+              if (FIRST) {
+                mu = 0.5 * (y + s_ybar[g]);
+                eta = fm_log(mu, FT.log_t);
+                ec = eta;
+              } else {
+                const double* bg = bdense + g * KDE;
+                double ea = fma(gsel, betas[g * kx + gc], off), eb = 0.0;
 #pragma unroll
-              for (int i = 0; i + 1 < KDE; i += 2) {
-                ea = fma(x[i], bg[i], ea);
-                eb = fma(x[i + 1], bg[i + 1], eb);
+                for (int i = 0; i + 1 < KDE; i += 2) {
+                  ea = fma(x[i], bg[i], ea);
+                  eb = fma(x[i + 1], bg[i + 1], eb);
+                }
+                if (KDE & 1) ea = fma(x[KDE - 1], bg[KDE - 1], ea);
+                eta = ea + eb;
+                ec = eta < 700.0 ? eta : 700.0;
+                ec = ec > -700.0 ? ec : -700.0;
+                mu = fm_exp(ec, FT.exp_t);
               }
-              if (KDE & 1) ea = fma(x[KDE - 1], bg[KDE - 1], ea);
-              eta = ea + eb;
-              ec = eta < 700.0 ? eta : 700.0;
-              ec = ec > -700.0 ? ec : -700.0;
-              mu = fm_exp(ec, FT.exp_t);
+              // unit deviance / 2 : y log(max(y / mu, eps)) - (y - mu)                          (Poisson)
+              //                     y log(max(y / mu, eps)) - (y + nu) log((y + nu) / (mu + nu)) (NB)
+              const double ly = fm_log(y > 0.0 ? y : 1.0, FT.log_t);
+              double lrat = ly - ec;
+              lrat = lrat > LOG_EPS ? lrat : LOG_EPS;
+              double d2 = y - mu;
+              double wgt = mu;
+              double rc = 0.0;
+              if (NBF) {
+                rc = fm_rcp(nu + mu);
+                const double lt = fm_log((y + nu) * rc, FT.log_t);
+                d2 = pois ? d2 : (y + nu) * lt;
+                wgt = pois ? mu : mu * nu * rc;
+              }
+              dacc[g] = fma(vld, fma(y, lrat, -d2), dacc[g]);
+              const double z = (eta - off) + (y - mu) * fm_rcp(mu);
+              double w = wgt, wz = wgt * z;
+              if (NBF && NEWTON) {
+                // observed information of the NB2 log-likelihood: nu mu (nu + y) / (nu + mu)^2;
+                // rhs = w (eta - off) + score (same minimiser, quadratic tail; lasso refit only)
+                const double wn = mu * nu * rc * ((nu + y) * rc);
+                const double wzn = fma(wn, eta - off, (y - mu) * (nu * rc));
+                const bool nw = (fl & 2) != 0;
+                w = nw ? wn : w;
+                wz = nw ? wzn : wz;
+              }
+              wbuf[lane * WLD + g] = w;
+              wzbuf[lane * WLD + g] = wz;
             }
-            // unit deviance / 2 : y log(max(y / mu, eps)) - (y - mu)                          (Poisson)
-            //                     y log(max(y / mu, eps)) - (y + nu) log((y + nu) / (mu + nu)) (NB)
-            const double ly = fm_log(y > 0.0 ? y : 1.0, FT.log_t);
-            double lrat = ly - ec;
-            lrat = lrat > LOG_EPS ? lrat : LOG_EPS;
-            double d2 = y - mu;
-            double wgt = mu;
-            double rc = 0.0;
-            if (NBF) {
-              rc = fm_rcp(nu + mu);
-              const double lt = fm_log((y + nu) * rc, FT.log_t);
-              d2 = pois ? d2 : (y + nu) * lt;
-              wgt = pois ? mu : mu * nu * rc;
-            }
-            dacc[g] = fma(vld, fma(y, lrat, -d2), dacc[g]);
-            const double z = (eta - off) + (y - mu) * fm_rcp(mu);
-            double w = wgt, wz = wgt * z;
-            if (NBF && (fl & 2)) {
-              // observed information of the NB2 log-likelihood: nu mu (nu + y) / (nu + mu)^2;
-              // rhs = w (eta - off) + score (same minimiser, quadratic tail; lasso refit only)
-              const double wn = mu * nu * rc * ((nu + y) * rc);
-              w = wn;
-              wz = fma(wn, eta - off, (y - mu) * (nu * rc));
-            }
-            wbuf[lane * WLD + g] = w;
-            wzbuf[lane * WLD + g] = wz;
-          }
+          };
+          if (first)
+            eval8(std::true_type{}, std::false_type{});
+          else if (any_newton)
+            eval8(std::false_type{}, std::true_type{});
+          else
+            eval8(std::false_type{}, std::false_type{});
         }
         __syncwarp();
         // ===== Gram strips and right-hand side on the FP64 tensor cores: lane = (cell lc of a step, gene lr) =====
