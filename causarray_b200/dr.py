@@ -36,7 +36,6 @@ __version__ = "0.1.0"
 
 import concurrent.futures as _cf
 _PS_POOL = _cf.ThreadPoolExecutor(max_workers=1, thread_name_prefix='causarray_ps')
-_PS_FIT_POOL = _cf.ThreadPoolExecutor(max_workers=2, thread_name_prefix='causarray_psfit')
 
 
 class YhatFactors:
@@ -85,26 +84,27 @@ def _validate_clip(clip):
 
 
 
-_LEAN_LOSS = None
+_LEAN_CLOSS = None
 
 
 def _fit_logistic_lean(x, y, x_te, C, balanced, tol, max_iter):
     """sklearn's binary ``LogisticRegression(solver='lbfgs', fit_intercept=False)`` without the
-    estimator plumbing: the SAME loss object (``LinearModelLoss(HalfBinomialLoss)``), sample weights,
-    start vector and ``scipy.optimize.minimize(method='L-BFGS-B')`` options as
+    estimator plumbing: the SAME pointwise loss kernel (``HalfBinomialLoss().closs``), sample
+    weights, start vector, objective arithmetic (``LinearModelLoss.loss_gradient``:
+    ``sum(loss) / sw_sum + l2 / 2 w.w``, gradient ``X^T (g / sw_sum) + l2 w``) and
+    ``scipy.optimize.minimize(method='L-BFGS-B')`` options as
     ``sklearn/linear_model/_logistic.py::_logistic_regression_path`` -- identical function values, so
     identical iterates and (bit for bit) identical probabilities
-    (``tests/test_host_api.py::test_lean_logistic_is_sklearn``) -- at a fifth of the cost per fit
-    (input validation, label encoding and parameter routing dominate sklearn's 5 ms on these
-    2 000 x 12 designs).  The reference's answer is defined by this solver and its ``tol=1e-4`` stop
-    (``causarray/DR_estimation.py:18-42``), which is why the fit stays on the host."""
-    global _LEAN_LOSS
+    (``tests/test_host_api.py::test_lean_logistic_is_sklearn``) -- at a fraction of the cost per fit
+    (input validation, label encoding, parameter routing and array-API dispatch dominate sklearn's
+    5 ms on these 2 000 x 12 designs).  The reference's answer is defined by this solver and its
+    ``tol=1e-4`` stop (``causarray/DR_estimation.py:18-42``), which is why the fit stays on the host."""
+    global _LEAN_CLOSS
     import scipy.optimize
     from scipy.special import expit
-    if _LEAN_LOSS is None:
+    if _LEAN_CLOSS is None:
         from sklearn._loss.loss import HalfBinomialLoss
-        from sklearn.linear_model._linear_loss import LinearModelLoss
-        _LEAN_LOSS = LinearModelLoss(base_loss=HalfBinomialLoss(), fit_intercept=False)
+        _LEAN_CLOSS = HalfBinomialLoss().closs
     x = np.ascontiguousarray(x, dtype=np.float64)
     n = x.shape[0]
     pos = np.asarray(y) == 1
@@ -117,8 +117,21 @@ def _fit_logistic_lean(x, y, x_te, C, balanced, tol, max_iter):
         sw_sum = float(np.sum(sw))
     else:
         sw, sw_sum = None, n
-    res = scipy.optimize.minimize(_LEAN_LOSS.loss_gradient, np.zeros(x.shape[1]), method='L-BFGS-B', jac=True,
-                                  args=(x, target, sw, 1.0 / (C * sw_sum), 1),
+    l2 = 1.0 / (C * sw_sum)
+    xt = x.T
+    loss_out, grad_out = np.empty(n), np.empty(n)
+    closs = _LEAN_CLOSS
+
+    def func(w):
+        raw = x @ w + 0.0
+        closs.loss_gradient(y_true=target, raw_prediction=raw, sample_weight=sw, loss_out=loss_out,
+                            gradient_out=grad_out, n_threads=1)
+        loss = float(np.sum(loss_out) / sw_sum)
+        loss += 0.5 * l2 * (w @ w)
+        gp = grad_out / sw_sum
+        return loss, xt @ gp + l2 * w
+
+    res = scipy.optimize.minimize(func, np.zeros(x.shape[1]), method='L-BFGS-B', jac=True,
                                   options={'maxiter': max_iter, 'maxls': 50, 'gtol': tol,
                                            'ftol': 64 * np.finfo(float).eps})
     return expit((np.asarray(x_te, dtype=np.float64) @ res.x.reshape(1, -1).T).ravel())
@@ -193,11 +206,11 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
             """Inputs of treatment j's fit, or the constant prediction of a degenerate design."""
             elig = mask[tr, j] if mask is not None else (ctrl | (A_tr[:, j] == 1))
             y = A_tr[elig, j]
-            if y.size == 0 or np.unique(y).size != 2:
+            if y.size == 0 or not (np.any(y == 1) and np.any(y == 0)):
                 raise ValueError(f'Treatment {j} needs at least one eligible control and case in every '
                                  'training fold')
             x = X_tr[elig]
-            if np.all(np.ptp(x, axis=0) == 0):
+            if np.all(x.max(axis=0) == x.min(axis=0)):
                 if class_weight == 'balanced':
                     return None, 0.5
                 if isinstance(class_weight, dict):
@@ -212,10 +225,10 @@ def estimate_propensity_scores(A, X_A, K=1, ps_model='logistic', mask=None, clip
         tasks = [task(j) for j in range(n_trt)]
         todo = [j for j in range(n_trt) if tasks[j][0] is not None]
         fits = [t[1] for t in tasks]
-        if len(todo) > 2:
-            res = list(_PS_FIT_POOL.map(lambda j: _fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te), todo))
-        else:
-            res = [_fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo]
+        # (sequential on purpose: the fits are Python-bound -- L-BFGS-B calling back into the loss -- so
+        # threads only trade the GIL back and forth; in LFC the whole estimator already runs on a
+        # background thread next to the outcome GLM on the device)
+        res = [_fit_logistic(lr_kw, tasks[j][0][0], tasks[j][0][1], X_te) for j in todo]
         for j, r in zip(todo, res):
             fits[j] = r
         for j in range(n_trt):
