@@ -70,6 +70,7 @@ _SIGNATURES = {
     "ca_gcate_load_counts": [_P, _D, _D, _D],
     "ca_gcate_upload_counts": [_P, _D] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_upload_counts_typed": [_P, ctypes.c_void_p, _c_int] + [ctypes.POINTER(ctypes.c_int64)] * 3,
+    "ca_gcate_upload_counts_rows": [_P, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), _c_int] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_upload_counts_csr": [_P, ctypes.POINTER(ctypes.c_int64), _I32, _D, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_size_factor_medians": [_P, _D],
     "ca_gcate_prepare": [_P, _D, _D],

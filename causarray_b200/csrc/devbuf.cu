@@ -139,4 +139,53 @@ int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   return 0;
 }
 
+// Same pipeline, but the source is `nrows` rows (row_bytes each) of a larger host matrix picked by
+// `rows` (row i of the destination = row rows[i] of the source, leading dimension ld_bytes): the
+// gather happens inside the threaded copy into the pinned buffer, so a perturbation batch goes from
+// the full count matrix to the device without an intermediate host copy (numpy's fancy-index copy of
+// one 4 000 x 8 000 batch cost 30 ms, as much as the upload itself).
+int h2d_staged_rows(void* dst, const void* src, size_t ld_bytes, const int64_t* rows, size_t nrows, size_t row_bytes,
+                    cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  if (!g_stage.ok) {
+    for (int b = 0; b < 2; ++b) {
+      CA_CUDA(cudaHostAlloc(&g_stage.buf[b], STAGE_CHUNK, cudaHostAllocDefault));
+      CA_CUDA(cudaEventCreateWithFlags(&g_stage.ev[b], cudaEventDisableTiming));
+    }
+    g_stage.ok = true;
+  }
+  if (row_bytes == 0 || nrows == 0) return 0;
+  if (row_bytes > STAGE_CHUNK) {
+    set_error("row longer than the staging buffer");
+    return -2;
+  }
+  const int nt = std::max(1, std::min(8, (int)std::thread::hardware_concurrency() / 2));
+  const char* s = static_cast<const char*>(src);
+  char* d = static_cast<char*>(dst);
+  const size_t rows_per_chunk = STAGE_CHUNK / row_bytes;
+  int i = 0;
+  for (size_t r0 = 0; r0 < nrows; r0 += rows_per_chunk, ++i) {
+    const int b = i & 1;
+    const size_t nr = std::min(rows_per_chunk, nrows - r0);
+    if (g_stage.used[b]) CA_CUDA(cudaEventSynchronize(g_stage.ev[b]));
+    char* pin = static_cast<char*>(g_stage.buf[b]);
+    auto work = [=](size_t lo, size_t hi) {
+      for (size_t r = lo; r < hi; ++r) memcpy(pin + r * row_bytes, s + (size_t)rows[r0 + r] * ld_bytes, row_bytes);
+    };
+    const size_t piece = (nr + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int w = 1; w < nt; ++w) {
+      const size_t lo = (size_t)w * piece;
+      if (lo >= nr) break;
+      th.emplace_back(work, lo, std::min(nr, lo + piece));
+    }
+    work(0, std::min(nr, piece));
+    for (auto& t : th) t.join();
+    CA_CUDA(cudaMemcpyAsync(d + r0 * row_bytes, pin, nr * row_bytes, cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaEventRecord(g_stage.ev[b], st));
+    g_stage.used[b] = true;
+  }
+  return 0;
+}
+
 }  // namespace ca

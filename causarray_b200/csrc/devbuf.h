@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 #include "common.cuh"
 
 namespace ca {
@@ -20,6 +21,9 @@ void pool_release_all();
 // chunk uploads pipelined behind it (a plain cudaMemcpy of pageable memory ran at ~12 GB/s: 21 ms
 // for the 256 MB of one batch).  Asynchronous on `st` like cudaMemcpyAsync; returns 0 or -1.
 int h2d_staged(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// rows[i] selects the source row (leading dimension ld_bytes) of destination row i; see devbuf.cu
+int h2d_staged_rows(void* dst, const void* src, size_t ld_bytes, const int64_t* rows, size_t nrows, size_t row_bytes,
+                    cudaStream_t st);
 
 template <typename T>
 struct DevBuf {

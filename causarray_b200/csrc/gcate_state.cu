@@ -277,6 +277,30 @@ extern "C" int ca_gcate_upload_counts_typed(ca_gcate_t h, const void* Y, int dty
   return 0;
 }
 
+extern "C" int ca_gcate_upload_counts_rows(ca_gcate_t h, const void* Y, int64_t ld, const int64_t* rows, int dtype,
+                                           int64_t* n_nonint, int64_t* n_nonfinite, int64_t* n_empty_genes) {
+  CA_REQUIRE(h && Y && rows, "null argument");
+  static const size_t width[6] = {8, 4, 4, 8, 2, 1};
+  CA_REQUIRE(dtype >= 0 && dtype <= CA_U8, "unknown element type");
+  const int n = h->n, p = h->p;
+  CA_REQUIRE(ld >= p, "leading dimension smaller than the number of genes");
+  const size_t count = (size_t)n * p, wd = width[dtype];
+  if (h->Yraw.alloc(count) || h->Yraw_t.alloc((size_t)p * h->ldn)) return -1;
+  if (dtype == CA_F64) {
+    if (h2d_staged_rows(h->Yraw.ptr, Y, (size_t)ld * wd, rows, (size_t)n, (size_t)p * wd, h->st)) return -1;
+    if (int rc = finish_upload(h, n_nonint, n_nonfinite, n_empty_genes)) return rc;
+    CA_CUDA(cudaStreamSynchronize(h->st));
+    return 0;
+  }
+  DevBuf<unsigned char> narrow;
+  if (narrow.alloc(count * wd)) return -1;
+  if (h2d_staged_rows(narrow.ptr, Y, (size_t)ld * wd, rows, (size_t)n, (size_t)p * wd, h->st)) return -1;
+  if (launch_widen_counts(narrow.ptr, dtype, (long)count, h->Yraw.ptr, h->st)) return -1;
+  if (int rc = finish_upload(h, n_nonint, n_nonfinite, n_empty_genes)) return rc;
+  CA_CUDA(cudaStreamSynchronize(h->st));  // the narrow staging copy goes out of scope
+  return 0;
+}
+
 extern "C" int ca_gcate_upload_counts_csr(ca_gcate_t h, const int64_t* indptr, const int32_t* indices, const double* data,
                                           int64_t nnz, int64_t* n_nonint, int64_t* n_nonfinite,
                                           int64_t* n_empty_genes) {

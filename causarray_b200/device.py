@@ -16,6 +16,36 @@ def device_dtype(Y):
     return isinstance(Y, np.ndarray) and (Y.dtype == np.float64 or Y.dtype.str in _NARROW_DTYPES)
 
 
+class RowsView:
+    """``base[idx]`` without the copy: the rows ``idx`` of a C-contiguous host count matrix, as the
+    batch drivers select them (``causarray/gcate.py:525-560``).  The device upload gathers the rows
+    itself (``ca_gcate_upload_counts_rows``); anything else that needs the numbers gets the ordinary
+    fancy-indexed copy through ``__array__`` / ``materialize``."""
+
+    def __init__(self, base, idx):
+        self.base = base
+        self.idx = np.ascontiguousarray(idx, dtype=np.int64)
+        self.shape = (int(self.idx.size), int(base.shape[1]))
+        self.dtype = base.dtype
+        self.ndim = 2
+        self.direct = (isinstance(base, np.ndarray) and base.ndim == 2 and base.strides[1] == base.itemsize
+                       and base.strides[0] >= base.shape[1] * base.itemsize
+                       and (base.dtype == np.float64 or base.dtype.str in _NARROW_DTYPES))
+        self._dense = None
+
+    def materialize(self):
+        if self._dense is None:
+            self._dense = self.base[self.idx]
+        return self._dense
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialize()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __len__(self):
+        return self.shape[0]
+
+
 class GcateDevice:
     """Device-resident GCATE problem (``ca_gcate_t``): S1 seam of SURVEY.md section 8b."""
 
@@ -56,6 +86,21 @@ class GcateDevice:
         L.check(self.lib.ca_gcate_load_counts(self.h, L.dptr(Y), L.dptr(sf), L.dptr(nu)))
 
     def upload_counts(self, Y, check=True):
+        if isinstance(Y, RowsView) and Y.direct:
+            # rows of a larger host matrix: gathered inside the staged upload, no host copy of the batch
+            c = [ctypes.c_int64(0) for _ in range(3)]
+            refs = [ctypes.byref(x) for x in c] if check else [None, None, None]
+            assert Y.shape == (self.n, self.p)
+            code = 0 if Y.base.dtype == np.float64 else _NARROW_DTYPES[Y.base.dtype.str]
+            L.check(self.lib.ca_gcate_upload_counts_rows(
+                self.h, ctypes.c_void_p(Y.base.ctypes.data), int(Y.base.strides[0] // Y.base.itemsize),
+                Y.idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), code, *refs))
+            return tuple(int(x.value) for x in c)
+        if isinstance(Y, RowsView):
+            Y = np.asarray(Y)
+        return self._upload_counts(Y, check)
+
+    def _upload_counts(self, Y, check=True):
         """H2D of the raw counts (dense array, or a scipy.sparse matrix uploaded as CSR and expanded
         on the device); returns (#non-integer entries, #non-finite, #all-zero genes)."""
         c = [ctypes.c_int64(0) for _ in range(3)]

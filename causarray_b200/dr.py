@@ -27,7 +27,7 @@ from sklearn.linear_model import LogisticRegression
 from sklearn.model_selection import KFold
 
 from . import glm as _glm_mod
-from .device import GlmDevice, aipw_lfc, aipw_lfc_yhat
+from .device import RowsView, GlmDevice, aipw_lfc, aipw_lfc_yhat
 from .inference import bh_correction, bh_correction_device, bh_correction_multi, fdx_control
 from .prep import comp_size_factor, _filter_params, reset_random_seeds
 from ._timing import phase
@@ -388,6 +388,8 @@ def compute_causal_estimand(estimand, Y, W, A, W_A=None, family='nb', offset=Fal
         # host needs the dense form; otherwise densify like the reference does
         if _glm is None or K != 1 or Y_hat is not None:
             Y = np.asarray(Y.toarray(), dtype=float)
+    elif isinstance(Y, RowsView) and _glm is not None and K == 1 and Y_hat is None:
+        pass      # rows of a larger matrix whose device copy is at hand: only the shape is needed here
     else:
         Y = np.asarray(Y)
         # (integer / float32 counts whose device copy is at hand need no float64 copy on the host)
@@ -721,36 +723,48 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
         skip = set(skip) | _par.foreign_batches(_nb, _rank, _world)
     # one batch at a time: GCATE fit -> LFC on the same device-resident counts
     from .estimators import iter_gcate_batches
-    for br in iter_gcate_batches(Y_np, X_np, A, r, batch_size=batch_size, n_batches=n_batches, max_cells=max_cells,
-                                 n_ctrl=n_ctrl, family=family, offset=offset, warm_start_U=warm_start_U,
-                                 skip_batches=skip, random_state=random_state, verbose=verbose,
-                                 **{**kwargs, **gcate_kwargs}):
-        if br.get('skipped'):
-            continue
-        batch_i, cell_idx, res_2 = br['batch_i'], br['cell_idx'], br['res_2']
-        ws = res_2.pop('_ws', None)
-        U_b = res_2['U'].copy()
-        off_b = np.log(res_2['kwargs_glm']['size_factor'])
-        Y_b_np = Y_np[cell_idx]            # (a sparse slice stays sparse: the counts are on the device already)
-        Y_b = pd.DataFrame(Y_b_np, columns=gene_names) if (gene_names is not None and not sparse_in) else Y_b_np
-        X_b = X_np[cell_idx]
-        cols = [col_of[name] for name in br['pert_names']]
-        A_b = A_np[np.ix_(cell_idx, cols)]
-        W_b = np.c_[X_b, U_b]
-        W_A_b = np.c_[W_A_np[cell_idx], U_b] if W_A_np is not None else W_b
-        df_b, est_b = LFC(Y_b, W_b, pd.DataFrame(A_b, columns=br['pert_names']), W_A_b, family=family,
-                          offset=off_b, verbose=verbose, _glm=None if ws is None else ws.glm,
-                          _trusted=ws is not None, **{**kwargs, **lfc_kwargs})
-        df_b['batch'] = batch_i
-        new[batch_i] = df_b
-        if cache_path is not None and _world == 1:
-            _cache_put(cache_path, batch_i, df_b, family, int(A_np.shape[1]))
-        del est_b
-        if ws is not None:
-            ws.close()
-        br['res_1'] = None
-        br['res_2'] = None
-        gc.collect()
+    # Python's cyclic collector is paused for the loop (the reference calls gc.collect() after every
+    # batch, causarray/DR_learner.py:846; with the result frames of the finished batches alive a full
+    # collection -- explicit or triggered by the allocations of a batch -- costs ~50 ms, a quarter of a
+    # batch): device memory is released deterministically by ws.close(), host arrays by reference counts.
+    _gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        for br in iter_gcate_batches(Y_np, X_np, A, r, batch_size=batch_size, n_batches=n_batches, max_cells=max_cells,
+                                     n_ctrl=n_ctrl, family=family, offset=offset, warm_start_U=warm_start_U,
+                                     skip_batches=skip, random_state=random_state, verbose=verbose,
+                                     **{**kwargs, **gcate_kwargs}):
+            if br.get('skipped'):
+                continue
+            batch_i, cell_idx, res_2 = br['batch_i'], br['cell_idx'], br['res_2']
+            ws = res_2.pop('_ws', None)
+            U_b = res_2['U'].copy()
+            off_b = np.log(res_2['kwargs_glm']['size_factor'])
+            # (the counts are on the device already: a sparse slice stays sparse, a dense one stays a view)
+            if gene_names is not None and not sparse_in:
+                Y_b = pd.DataFrame(Y_np[cell_idx], columns=gene_names)
+            else:
+                Y_b = RowsView(Y_np, cell_idx) if (ws is not None and not sparse_in) else Y_np[cell_idx]
+            X_b = X_np[cell_idx]
+            cols = [col_of[name] for name in br['pert_names']]
+            A_b = A_np[np.ix_(cell_idx, cols)]
+            W_b = np.c_[X_b, U_b]
+            W_A_b = np.c_[W_A_np[cell_idx], U_b] if W_A_np is not None else W_b
+            df_b, est_b = LFC(Y_b, W_b, pd.DataFrame(A_b, columns=br['pert_names']), W_A_b, family=family,
+                              offset=off_b, verbose=verbose, _glm=None if ws is None else ws.glm,
+                              _trusted=ws is not None, **{**kwargs, **lfc_kwargs})
+            df_b['batch'] = batch_i
+            new[batch_i] = df_b
+            if cache_path is not None and _world == 1:
+                _cache_put(cache_path, batch_i, df_b, family, int(A_np.shape[1]))
+            del est_b
+            if ws is not None:
+                ws.close()
+            br['res_1'] = None
+            br['res_2'] = None
+    finally:
+        if _gc_was_on:
+            gc.enable()
     if _world > 1:
         new = _par.gather_frames(new)
         if new is None:

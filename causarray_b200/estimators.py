@@ -20,6 +20,7 @@ from scipy.special import gammaln
 
 from . import glm as _glm_mod
 from .optim import alter_min, BatchWorkspace, type_f
+from .device import RowsView
 from .prep import comp_size_factor, _filter_params, subsample_ctrl_cells, subsample_pert_cells
 from ._timing import phase
 
@@ -144,7 +145,8 @@ def fit_gcate(Y, X, A, r, family='nb', disp_glm=None, disp_family=None, offset=T
     ctx = _glm_mod._backend_override(backend) if backend != "auto" else contextlib.nullcontext()
     with ctx:
         with phase('gcate_upload_checks_sizefactors'):
-            Y, kwargs_glm, lam1, ws = _check_input(Y if _sp.issparse(Y) else np.asarray(Y), X, family, disp_glm,
+            Y, kwargs_glm, lam1, ws = _check_input(Y if (_sp.issparse(Y) or isinstance(Y, RowsView)) else np.asarray(Y),
+                                                   X, family, disp_glm,
                                                    disp_family, offset, c1, _ws=_ws, r=int(r), **shard_kw, **kwargs)
         res_1, res_2 = estimate(Y, X, int(r), a, lam1, kwargs_glm, kwargs_ls_1, kwargs_es_1, kwargs_ls_2,
                                 kwargs_es_2, A_init=A_init, _ws=ws, **kwargs)
@@ -284,7 +286,8 @@ def iter_gcate_batches(Y, X, A, r, batch_size=10, n_batches=None, max_cells=2000
 
     def rows(idx, dense=True):
         if not sparse_in:
-            return Y_np[idx]
+            # dense=False: a view (the device upload gathers the rows itself, see RowsView)
+            return Y_np[idx] if dense else RowsView(Y_np, idx)
         return np.asarray(Y_np[idx].toarray(), dtype=np.float64) if dense else Y_np[idx]
     X_np = np.asarray(X)
     if isinstance(A, pd.DataFrame):

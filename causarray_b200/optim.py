@@ -17,7 +17,7 @@ import numpy as np
 import scipy.linalg
 
 from . import glm as _glm_mod
-from .device import GcateDevice, GlmDevice, device_dtype
+from .device import GcateDevice, GlmDevice, RowsView, device_dtype
 from .svd import topr_svd_device, lowrank_product_svd
 from ._timing import phase
 
@@ -116,7 +116,7 @@ class BatchWorkspace:
     """
 
     def __init__(self, Y, size_factor, disp, family, d, r, thres_disp=100., _defer=False, shard=None):
-        if not hasattr(Y, "tocsr"):          # a scipy.sparse matrix is uploaded as CSR
+        if not hasattr(Y, "tocsr") and not isinstance(Y, RowsView):   # a scipy.sparse matrix is uploaded as CSR
             Y = np.asarray(Y)
             if not device_dtype(Y):          # int32 / float32 / ... are widened on the device
                 Y = np.asarray(Y, dtype=np.float64)
@@ -160,8 +160,8 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     kwargs_glm, kwargs_ls, kwargs_es, total_gene_updates, total_cell_updates,
     X_U, B_Gamma, U``.
     """
-    if not hasattr(Y, "tocsr"):              # (sparse counts live on the device only: _ws holds them)
-        Y = np.asarray(Y)
+    if not hasattr(Y, "tocsr") and not (isinstance(Y, RowsView) and _ws is not None):
+        Y = np.asarray(Y)                    # (sparse counts / row views live on the device only: _ws holds them)
     n, p = Y.shape
     d = X.shape[1]
     assert d > 0

@@ -69,6 +69,13 @@ int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_total, const
  *   prepare: normalisation by the size factors + constant-term sums. */
 int ca_gcate_upload_counts(ca_gcate_t h, const double* Y, int64_t* n_nonint, int64_t* n_nonfinite,
                            int64_t* n_empty_genes);
+/* Rows `rows[0..n)` of a larger host matrix (leading dimension ld elements, element type dtype as in
+ * ca_gcate_upload_counts_typed; CA_F64 allowed) become the n x p count matrix of the handle: the batch
+ * drivers (causarray/gcate.py:525-560 build Y[cell_idx] on the host) hand over the full matrix and the
+ * cell indices of a perturbation batch; the gather runs inside the pinned-buffer staging copy. */
+int ca_gcate_upload_counts_rows(ca_gcate_t h, const void* Y, int64_t ld, const int64_t* rows, int dtype,
+                                int64_t* n_nonint, int64_t* n_nonfinite, int64_t* n_empty_genes);
+
 /* Same from a CSR matrix of the counts (scipy.sparse layout: indptr n+1 int64, indices nnz int32,
  * data nnz double, no duplicate entries): only nnz * 12 bytes cross the bus, the dense copy is
  * expanded on the device.  Replaces the host-side densification of a batch slice

@@ -153,6 +153,8 @@ def _worker_sharded_lfc(rank, world, port, q):
         return out
 
     dr.GlmDevice, dr.cross_fitting, dr.aipw_lfc = FakeGlm, fake_cross_fitting, fake_aipw_lfc
+    from causarray_b200 import inference as _inf
+    dr.bh_correction_device = _inf.bh_correction_multi     # host form of the same tail (no GPU in this test)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         df_full, _ = dr.LFC(Y, W, A, family="poisson", offset=np.zeros(n), _trusted=True)
