@@ -122,6 +122,7 @@ def gpu_step(batch, resident_ws=None):
     es = dict(rel_tol=w["es_rel_tol"], max_iters=w["es_max_iters"])
     cglm.COUNTERS["irls_gene_iters"] = 0
     cglm.COUNTERS["gram_flops"] = 0.0
+    cglm.COUNTERS["gram_flops_structured"] = 0.0
     Y, X, A, X_A = batch["Y"], batch["X"], batch["A"], batch["X_A"]
     res1, res2 = cb.fit_gcate(Y, X, A, w["r"], family=w["family"], disp_glm=batch["disp"], offset=True,
                               kwargs_es_1=dict(es), kwargs_es_2=dict(es), _ws=resident_ws)
@@ -141,7 +142,7 @@ def gpu_step(batch, resident_ws=None):
                  cell_evals=res1["line_search_evals"][0] + res2["line_search_evals"][0],
                  gene_evals=res1["line_search_evals"][1] + res2["line_search_evals"][1],
                  loop_seconds=res1["loop_seconds"] + res2["loop_seconds"], n=n, p=p,
-                 gram_flops=cglm.COUNTERS["gram_flops"],
+                 gram_flops=cglm.COUNTERS["gram_flops"], gram_flops_structured=cglm.COUNTERS["gram_flops_structured"],
                  n_sig=int(np.nansum(df["padj"].to_numpy() < 0.05)))
     return df, stats
 
@@ -524,7 +525,8 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     # per-kernel-class algorithmic bytes over the timed resident steps (rank 0)
     st_sum = {k: sum(s[k] for s in stats_res) for k in ("cell_updates", "gene_rows", "cell_evals", "gene_evals",
-                                                         "irls_gene_iters", "alt_iters", "gram_flops")}
+                                                         "irls_gene_iters", "alt_iters", "gram_flops",
+                                                         "gram_flops_structured")}
     alg_bytes = {
         # Y read once per active row: cells x p + genes x n doubles
         "rowpass_grad": 8.0 * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
@@ -539,36 +541,72 @@ def main():
         kern[name] = {"ms": round(ms, 3), "launches": cnt, "share": round(ms / tot_ms, 4)}
         if name in alg_bytes and ms > 0:
             kern[name]["achieved_gbs"] = round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1)
-    fp64_peak_tflops = 36.5   # DMMA m8n8k4 / DFMA peak measured on this pool's B200 (tools/fp64_microbench.cu)
+    # FP64 peak: DMMA (mma.sync m8n8k4.f64) and DFMA measured on this pool's B200 with tools/fp64_microbench
+    # (both 36.6-37.1 TFLOP/s: the FP64 tensor path and the FP64 ALU share one pipe at one rate);
+    # MEASURED_PEAKS.json holds no FP64 figure and tcgen05 has no FP64 kind
+    fp64_peak_tflops, fp64_src = 36.5, "hard-coded round-1 measurement"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_fp64_microbench.json")) as f:
+            mb = json.load(f)
+        fp64_peak_tflops = float(min(mb["dfma_tflops"], mb["dmma_m8n8k4_tflops"]))
+        fp64_src = "profiles/r02_fp64_microbench.json (tools/fp64_microbench.cu: min of DFMA and DMMA m8n8k4)"
+    except (OSError, ValueError, KeyError):
+        pass
+    k_tot = d + w["r"]
+    # Algorithmic FP64 work per matrix entry.  A likelihood evaluation needs the
+    # linear predictor (2 k flop), one exp, one log1p and the NB / Poisson arithmetic: 27 FP64
+    # instructions = 54 flop-equivalents in the leanest straight-line form we found; a gradient pass adds
+    # the reciprocal of the NB weight (6 instructions) and the contraction of dl with the r (or a)
+    # moving columns (2 x 16 flop).
+    flops_eval = 2.0 * k_tot + 54.0
+    flops_grad = 2.0 * k_tot + 54.0 + 12.0 + 32.0
+    alg_flops = {
+        "search": flops_eval * (st_sum["cell_evals"] * p + st_sum["gene_evals"] * n),
+        "rowpass_grad": flops_grad * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
+        # IRLS: the round-1 formula 2 n [kx(kx+1)/2 + 2 kx] per gene-iteration, kept so that the
+        # fraction is comparable between rounds; the structure-aware count is reported beside it
+        "glm_pass": st_sum["gram_flops"],
+    }
     if prof.get("glm_pass", (0, 0))[0] > 0:
         kern["glm_pass"]["achieved_tflops_fp64"] = round(st_sum["gram_flops"] / (prof["glm_pass"][0] * 1e-3) / 1e12, 2)
     dom = max((k for k in alg_bytes if prof.get(k, (0, 0))[0] > 0), key=lambda k: prof[k][0], default=None)
     # DRAM bytes of one captured launch per kernel class (ncu --set full, committed next to its summary)
     traffic = {}
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f)
-    except (OSError, ValueError):
-        pass
+    for fn in ("r01_traffic.json", "r02_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                traffic.update(json.load(f))
+        except (OSError, ValueError):
+            pass
 
     def kernel_roofline(name):
         ms, cnt = prof[name]
         tr = traffic.get(name)
+        ach = alg_flops[name] / (ms * 1e-3) / 1e12
+        r = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": round(fp64_peak_tflops, 2),
+             "unit": "TFLOP/s", "frac": round(ach / fp64_peak_tflops, 4),
+             "peak_source": "FP64 pipe (DMMA mma.sync m8n8k4.f64 = DFMA rate) measured on this pool's B200: " + fp64_src
+                            + "; MEASURED_PEAKS.json holds only bf16 tensor and HBM figures, tcgen05 has no FP64 kind",
+             "hbm_view": {"achieved_gbs": round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak,
+                          "frac": round(alg_bytes[name] / (ms * 1e-3) / 1e9 / hbm_peak, 4),
+                          "algorithmic_bytes": "8 B per cell*gene entry and pass (one read of Y)",
+                          "peak_source": peak_src}}
         if name == "glm_pass":
-            ach = st_sum["gram_flops"] / (ms * 1e-3) / 1e12
-            r = {"kernel": name, "bound": "tensor", "achieved": round(ach, 2), "peak": fp64_peak_tflops,
-                 "unit": "TFLOP/s", "frac": round(ach / fp64_peak_tflops, 4),
-                 "peak_source": "FP64 DMMA (mma.sync m8n8k4.f64) peak measured with tools/fp64_microbench.cu on this "
-                                "pool's B200; MEASURED_PEAKS.json only holds the bf16 tensor and HBM figures and "
-                                "tcgen05 has no FP64 kind",
-                 "algorithmic_flops_per_cell_gene_iter": "2 [kx(kx+1)/2 + 2 kx]",
-                 "hbm_view": {"achieved_gbs": round(alg_bytes[name] / (ms * 1e-3) / 1e9, 1), "peak_gbs": hbm_peak}}
+            r["algorithmic_flops"] = ("2 n [kx(kx+1)/2 + 2 kx] per gene and IRLS iteration (round-1 / SURVEY 8d formula; "
+                                      "it counts the products with the one-hot treatment block that the kernel no longer forms)")
+            sa = st_sum.get("gram_flops_structured", 0.0)
+            if sa:
+                r["structure_aware"] = {"achieved": round(sa / (ms * 1e-3) / 1e12, 2),
+                                        "frac": round(sa / (ms * 1e-3) / 1e12 / fp64_peak_tflops, 4),
+                                        "algorithmic_flops": "2 n [kd(kd+1)/2 + 2 kd + 65] per gene-iteration, kd = dense "
+                                                             "design columns (pair products, right-hand side, linear "
+                                                             "predictor, ~65 flop-equivalents of exp / log / reciprocals)"}
+        elif name == "search":
+            r["algorithmic_flops"] = "(2 k + 54) per evaluated entry of a line-search candidate, k = %d" % k_tot
         else:
-            ach = alg_bytes[name] / (ms * 1e-3) / 1e9
-            r = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                 "frac": round(ach / hbm_peak, 4), "peak_source": peak_src,
-                 "note": "FP64-pipe / latency bound kernel (DMMA + table-driven exp/log share the FP64 units, ncu: "
-                         "~50 % of that pipe); see DESIGN.md section 4"}
+            r["algorithmic_flops"] = "(2 k + 98) per entry of a gradient pass, k = %d" % k_tot
+        r["note"] = ("bound by the shared FP64 pipe (DMMA + DFMA + table-driven exp / log), not by HBM: the HBM view is "
+                     "listed for reference; ncu pipe utilisation in profiles/")
         r["avg_launch_ms"] = round(ms / max(1, cnt), 4)
         r["launches"] = cnt
         r["traffic"] = tr["dram_bytes"] if tr else None

@@ -35,7 +35,7 @@ _FAST_MAX_COEF = 1e4
 _CRISPYX_AVAILABLE = False   # the device backend replaces crispyx; kept for API compatibility
 
 last_fit_info = {}
-COUNTERS = {'irls_gene_iters': 0, 'fits': 0, 'gram_flops': 0.0}
+COUNTERS = {'irls_gene_iters': 0, 'fits': 0, 'gram_flops': 0.0, 'gram_flops_structured': 0.0}
 
 
 @contextlib.contextmanager
@@ -94,9 +94,33 @@ def _device_fit(dev, Xf, family, offsets, disp, thres_disp, maxiter, d_guard, al
     _kx = Xf.shape[1]
     # algorithmic FLOPs of the IRLS passes: 2 n [kx(kx+1)/2 + 2 kx] per gene and iteration
     COUNTERS['gram_flops'] += 2.0 * n * float(n_iter.sum()) * (_kx * (_kx + 1) / 2 + 2 * _kx)
+    # the same with the one-hot block of the design (at most one non-zero 0/1 entry per cell) taken out:
+    # only the dense columns form pair products (csrc/glm_irls_impl.cuh)
+    _kd = _dense_width(Xf)
+    COUNTERS['gram_flops_structured'] += 2.0 * n * float(n_iter.sum()) * (_kd * (_kd + 1) / 2 + 2 * _kd + 65)
     last_fit_info.update(n_genes=int(B.shape[0]), n_refit=int(bad.sum()), max_iter=int(n_iter.max(initial=0)),
                          irls_gene_iters=int(n_iter.sum()))
     return GlmFit(dev, B, dv, n_iter, status, bad)
+
+
+_DENSE_WIDTH_CACHE = {}
+
+
+def _dense_width(Xf):
+    """Number of design columns outside the largest contiguous one-hot block (bench accounting only)."""
+    key = (Xf.shape, float(Xf[:, -1].sum()), float(np.abs(Xf[0]).sum()))
+    if key not in _DENSE_WIDTH_CACHE:
+        binary = np.all((Xf == 0) | (Xf == 1), axis=0) & ~np.all(Xf == 1, axis=0)
+        best, lo = 0, 0
+        kx = Xf.shape[1]
+        while lo < kx:
+            hi = lo
+            while hi < kx and binary[hi] and np.all(Xf[:, lo:hi + 1].sum(axis=1) <= 1):
+                hi += 1
+            best = max(best, hi - lo)
+            lo = max(hi, lo + 1)
+        _DENSE_WIDTH_CACHE[key] = kx - (best if best >= 2 else 0)
+    return _DENSE_WIDTH_CACHE[key]
 
 
 def _as_device(Y, _glm):
