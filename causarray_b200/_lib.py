@@ -91,6 +91,7 @@ _SIGNATURES = {
     "ca_glm_fit": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _c_int, _D, _D, _I32, _I32],
     "ca_glm_fit_ex": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _c_int, _D, _U8, _D, _D, _I32, _I32],
     "ca_glm_refit_l1": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _D, _U8, _D, _D, _I32, _I32],
+    "ca_glm_fit_treatment": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _D, _D, _I32, _I32],
     "ca_glm_resid": [_P, _D],
     "ca_glm_resid_device": [_P, ctypes.POINTER(_P)],
     "ca_glm_fitted": [_P, _D],

@@ -191,9 +191,10 @@ int peer_setup(void* comm, int rank, int world, cudaStream_t st, PeerArena** out
   if (!comm || world < 2 || world > PEER_MAX_WORLD || (world & (world - 1)) != 0 || !g_api.all_gather) return 0;
   const char* env = getenv("CA_PEER_REDUCE");
   if (env && env[0] == '0') return 0;
-  // validated on two GPUs (tests/test_gpu_sharded.py); the 4- and 8-rank instantiations have not run
-  // on hardware yet and stay opt-in (CA_PEER_REDUCE=1) until they have
-  if (world > 2 && !(env && env[0] == '1')) return 0;
+  // validated on two and on four GPUs (tests/mgpu/sharded_altmin.py and sharded_fit_gcate.py under
+  // torchrun, round 2: identical iteration counts and factors on 4 ranks with CA_PEER_REDUCE=1 and =0);
+  // the 8-rank instantiation stays opt-in (CA_PEER_REDUCE=1) until it has run on hardware
+  if (world > 4 && !(env && env[0] == '1')) return 0;
   PeerArena* a = new PeerArena();
   a->rank = rank;
   a->world = world;

@@ -377,8 +377,8 @@ static int launch_pass(const GlmPass& P, cudaStream_t st) {
 int kpad_for(int k);
 
 int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* offset, int family, double thres,
-                 bool has_nu, bool has_ridge, bool lasso, double tol, int maxiter, bool warm, const int* genelist_dev,
-                 int n_list);
+                 bool has_nu, bool has_ridge, bool lasso, double tol, int maxiter, bool warm, bool freeze_dense,
+                 const int* genelist_dev, int n_list);
 
 // Internal column layout of the pass kernel.  A contiguous block of design columns of which every
 // cell has at most one non-zero entry (one-hot treatment indicators, causarray/DR_learner.py builds
@@ -501,7 +501,8 @@ extern "C" int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const
 
 static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                         double thres_disp, int maxiter, double tol, int d_guard, const double* ridge, const double* l1,
-                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status);
+                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status,
+                        bool freeze_dense = false);
 
 extern "C" int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                              double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
@@ -518,9 +519,17 @@ extern "C" int ca_glm_refit_l1(ca_glm_t h, int family, const double* X, int kx, 
                       n_iter, status);
 }
 
+extern "C" int ca_glm_fit_treatment(ca_glm_t h, int family, const double* X, int kx, const double* offset,
+                                    const double* nu, double thres_disp, int maxiter, double tol, double* B, double* dev,
+                                    int32_t* n_iter, int32_t* status) {
+  return glm_fit_impl(h, family, X, kx, offset, nu, thres_disp, maxiter, tol, -1, nullptr, nullptr, nullptr, true, B, dev,
+                      n_iter, status, true);
+}
+
 static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                         double thres_disp, int maxiter, double tol, int d_guard, const double* ridge, const double* l1,
-                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status) {
+                        const uint8_t* gene_mask, bool warm, double* B, double* dev, int32_t* n_iter, int32_t* status,
+                        bool freeze_dense) {
   CA_REQUIRE(h && h->Yt && X && B, "load counts first");
   CA_REQUIRE(kx > 0 && kx <= 64, "design width must be in [1, 64]");
   CA_REQUIRE(family == CA_FAMILY_POISSON || family == CA_FAMILY_NB, "Family not recognized");
@@ -567,7 +576,10 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
     CA_CUDA(cudaMemcpy(h->beta.ptr, hb.data(), sizeof(double) * (size_t)p * kx, cudaMemcpyHostToDevice));
     CA_CUDA(cudaMemcpy(h->status.ptr, st0.data(), sizeof(int) * p, cudaMemcpyHostToDevice));
   } else {
-    CA_CUDA(cudaMemsetAsync(h->beta.ptr, 0, h->beta.bytes(), st));
+    if (freeze_dense)   // the caller's coefficients: the dense ones are kept, the group ones are the starting point
+      CA_CUDA(cudaMemcpyAsync(h->beta.ptr, B, sizeof(double) * (size_t)p * kx, cudaMemcpyHostToDevice, st));
+    else
+      CA_CUDA(cudaMemsetAsync(h->beta.ptr, 0, h->beta.bytes(), st));
     CA_CUDA(cudaMemsetAsync(h->status.ptr, 0, h->status.bytes(), st));
     CA_CUDA(cudaMemsetAsync(h->n_iter.ptr, 0, h->n_iter.bytes(), st));
   }
@@ -597,11 +609,13 @@ static int glm_fit_impl(ca_glm_t h, int family, const double* X, int kx, const d
       const int rc = (gene_mask && nlist == 0)
                          ? 0
                          : glm_fit_irls(h, ip, X, offset, family, thres_disp, h->has_nu, ridge != nullptr, l1 != nullptr,
-                                        tol, maxiter, warm, gene_mask ? h->genelist.ptr : nullptr, nlist);
+                                        tol, maxiter, warm, freeze_dense, gene_mask ? h->genelist.ptr : nullptr, nlist);
       if (rc < 0) return rc;
       done = rc == 0;
     }
   }
+  CA_REQUIRE(done || !freeze_dense,
+             "the treatment-only fit needs a design with a one-hot block of at least two columns and at most 16 others");
   if (!done) {
   k_glm_consts<<<p, 256, 0, st>>>(h->Yt, h->ldn, n, h->has_nu ? h->nu.ptr : nullptr, family, thres_disp, h->ybar.ptr,
                                   h->cst.ptr);

@@ -195,8 +195,9 @@ static int launch_irls(const GlmIrls& P, int grid, size_t smem, cudaStream_t st)
 // handle: beta (warm start or zeros), nu, ridge (ridge | l1), status / n_iter prepared by the caller.
 // Returns 1 when the design does not fit this path (the caller then runs the per-iteration loop).
 int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* offset, int family, double thres,
-                 bool has_nu, bool has_ridge, bool lasso, double tol, int maxiter, bool warm, const int* genelist_dev,
-                 int n_list) {
+                 bool has_nu, bool has_ridge, bool lasso, double tol, int maxiter, bool warm, bool freeze_dense,
+                 const int* genelist_dev, int n_list) {
+  if (freeze_dense && L.ngroups < 2) return 1;
   const int n = h->n, p = h->p, kx = L.kx, kde = L.kde;
   cudaStream_t st = h->st;
   const size_t smem = glm_irls_smem_bytes(kde, kx, lasso);
@@ -278,6 +279,7 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   P.steptol = 1e-8;
   P.maxiter = maxiter;
   P.iter0 = warm ? 1 : 0;
+  P.freeze_dense = freeze_dense ? 1 : 0;
   P.genelist = genelist_dev;
   P.n_list = n_list;
   P.counter = h->counter.ptr;

@@ -73,6 +73,9 @@ struct GlmIrls {
   const double* l1;                    // kx or nullptr (lasso refit)
   double tol, steptol;
   int maxiter;
+  int freeze_dense;                    // 1: the dense coefficients stay at their input values; only the one-hot
+                                       // group coefficients are updated (two-stage fit: per-perturbation 1-D
+                                       // fits against the covariate offset, causarray/nb_glm_fast.py:500-567)
   int iter0;                           // 0: cold start (first pass from mu0 = (y + ybar) / 2); 1: warm start from beta
   const int* genelist;                 // genes to fit (nullptr: all p genes)
   int n_list;
@@ -500,7 +503,14 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
             for (int gg = lane; gg < ngr; gg += 32)
               if (!(cg[gg * CL + U] > 0.0)) bad = true;
             bad = __any_sync(0xffffffffu, bad);
-            if (!bad) {
+            if (P.freeze_dense) {
+              // the dense block keeps its coefficients: W.b carries them (unscaled) into the group update
+              for (int i = lane; i < nd; i += 32) {
+                W.b[i] = betas[g * kx + P.dcol[i]];
+                W.sc[i] = 1.0;
+              }
+              __syncwarp();
+            } else if (!bad) {
               for (int e = lane; e < nd * nd; e += 32) {
                 const int i = e / nd, j = e - i * nd;
                 double v = W.L[i * ld + j];

@@ -272,6 +272,24 @@ class GlmDevice:
                                        L.dptr(B), L.dptr(dev), L.i32ptr(n_iter), L.i32ptr(status)))
         return B, dev, n_iter, status
 
+    def fit_treatment(self, family, X, B_cov, offset=None, nu=None, thres_disp=100.0, maxiter=50, tol=1e-8):
+        """Treatment-effect fits against the covariate offset (``ca_glm_fit_treatment``): ``X (n, kx)``
+        holds the covariates and a one-hot treatment block; the coefficients of the non-treatment
+        columns are taken from ``B_cov (p, kx)`` (treatment entries = starting values) and kept."""
+        X = L.f64(X)
+        kx = X.shape[1]
+        off = None if offset is None else L.f64(np.ravel(offset))
+        nu = None if nu is None else L.f64(np.ravel(nu))
+        B = np.array(B_cov, dtype=np.float64, order="C", copy=True)
+        assert B.shape == (self.p, kx)
+        dev = np.zeros(self.p)
+        n_iter = np.zeros(self.p, dtype=np.int32)
+        status = np.zeros(self.p, dtype=np.int32)
+        L.check(self.lib.ca_glm_fit_treatment(self.h, L.FAMILY[family], L.dptr(X), kx, L.dptr(off), L.dptr(nu),
+                                              float(thres_disp), int(maxiter), float(tol), L.dptr(B), L.dptr(dev),
+                                              L.i32ptr(n_iter), L.i32ptr(status)))
+        return B, dev, n_iter, status
+
     def refit_l1(self, family, X, l1, gene_mask, offset=None, nu=None, thres_disp=100.0, maxiter=100, tol=1e-8):
         """Lasso refit (``ca_glm_refit_l1``) of the genes flagged in ``gene_mask``, warm-started from the
         previous fit; ``l1`` (kx,) = n * alpha_k."""

@@ -291,7 +291,7 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
                 pg = dict(params_glm)
                 if isinstance(pg.get('offset'), np.ndarray):
                     pg['offset'] = pg['offset'][tr]
-                B, _, _, off_tr, _ = _glm_mod.fit_glm(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True,
+                B, _, _, off_tr, _ = _glm_mod.fit_glm_auto(Yn[tr], X[tr], A[tr], family=family, alpha=glm_alpha, _lazy=True,
                                                       **pg)
                 if not _glm_mod._USE_FAST_BACKEND:
                     # backend="original" only -- the reference's statsmodels route, kept for identical
@@ -319,7 +319,7 @@ def cross_fitting(Y, A, X, X_A, family='poisson', K=1, glm_alpha=1e-4, ps_model=
             Y_hat = np.clip(Y_hat, None, 1e5)
         else:
             with phase('lfc_outcome_glm'):
-                B, fit, disp, offsets, _ = _glm_mod.fit_glm(Y, X, A, family=family, alpha=glm_alpha, _glm=_glm,
+                B, fit, disp, offsets, _ = _glm_mod.fit_glm_auto(Y, X, A, family=family, alpha=glm_alpha, _glm=_glm,
                                                             _lazy=True, **params_glm)
             Y_hat = YhatFactors(X, np.ascontiguousarray(B[:, :d]), np.ascontiguousarray(B[:, d:]), offsets)
             Y_hat.disp_glm = disp

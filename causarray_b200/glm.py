@@ -30,6 +30,8 @@ from .device import GlmDevice
 from .prep import comp_size_factor, _filter_params
 
 _USE_FAST_BACKEND = True
+_FAST_ROUTE = False        # set inside _backend_override("fast"): fit_glm_auto takes the two-stage route
+_FAST_MIN_P = 50
 _FAST_MAX_D = 50
 _FAST_MAX_COEF = 1e4
 _CRISPYX_AVAILABLE = False   # the device backend replaces crispyx; kept for API compatibility
@@ -41,16 +43,16 @@ COUNTERS = {'irls_gene_iters': 0, 'fits': 0, 'gram_flops': 0.0, 'gram_flops_stru
 @contextlib.contextmanager
 def _backend_override(backend):
     """Scoped ``"fast"`` / ``"original"`` / ``"auto"`` switch (all run the same device IRLS)."""
-    global _USE_FAST_BACKEND
-    old = _USE_FAST_BACKEND
+    global _USE_FAST_BACKEND, _FAST_ROUTE
+    old, old_route = _USE_FAST_BACKEND, _FAST_ROUTE
     if backend == "fast":
-        _USE_FAST_BACKEND = True
+        _USE_FAST_BACKEND, _FAST_ROUTE = True, True
     elif backend == "original":
-        _USE_FAST_BACKEND = False
+        _USE_FAST_BACKEND, _FAST_ROUTE = False, False
     try:
         yield
     finally:
-        _USE_FAST_BACKEND = old
+        _USE_FAST_BACKEND, _FAST_ROUTE = old, old_route
 
 
 class GlmFit:
@@ -232,14 +234,142 @@ def fit_glm_auto(Y, X, A=None, family='gaussian', disp_family='poisson',
                  disp_glm=None, impute=False, offset=None, offset_test=None, shrinkage=False,
                  alpha=1e-4, maxiter=1000, thres_disp=100., n_jobs=-3, random_state=0,
                  verbose=False, mem_limit_gb=None, **kwargs):
-    """Backend router of the reference; every route ends in the device IRLS."""
+    """Backend router of the reference (``causarray/gcate_glm.py:365-457``): ``backend="fast"`` (the
+    ``_backend_override("fast")`` scope) with at least ``_FAST_MIN_P`` genes and at most ``_FAST_MAX_D``
+    design columns takes the two-stage batched route (:func:`fit_glm_fast`) and falls back to the joint
+    fit when a coefficient exceeds ``_FAST_MAX_COEF`` in magnitude or is not finite, as the reference
+    does; everything else -- including ``"auto"``, which is what the reference runs where crispyx is not
+    installed -- is the joint per-gene MLE (:func:`fit_glm`)."""
+    if _FAST_ROUTE and family in ('poisson', 'nb') and Y.shape[1] >= _FAST_MIN_P \
+            and np.asarray(X).shape[1] + (0 if A is None else np.atleast_2d(np.asarray(A).T).shape[0]) <= _FAST_MAX_D \
+            and not shrinkage:
+        try:
+            out = fit_glm_fast(Y, X, A=A, family=family, disp_family=disp_family, disp_glm=disp_glm, impute=impute,
+                               offset=offset, offset_test=offset_test, alpha=alpha, maxiter=maxiter,
+                               thres_disp=thres_disp, random_state=random_state, verbose=verbose,
+                               mem_limit_gb=mem_limit_gb, **kwargs)
+            if np.all(np.isfinite(out[0])) and np.max(np.abs(out[0]), initial=0.0) <= _FAST_MAX_COEF:
+                return out
+            warnings.warn('fast GLM route produced non-finite or very large coefficients; using the joint fit',
+                          RuntimeWarning, stacklevel=2)
+        except NotImplementedError:
+            pass
     return fit_glm(Y, X, A=A, family=family, disp_family=disp_family, disp_glm=disp_glm, impute=impute,
                    offset=offset, offset_test=offset_test, shrinkage=shrinkage, alpha=alpha, maxiter=maxiter,
                    thres_disp=thres_disp, n_jobs=n_jobs, random_state=random_state, verbose=verbose,
                    mem_limit_gb=mem_limit_gb, **kwargs)
 
 
-fit_glm_fast = fit_glm_auto
+_N_STAGE1 = 3000        # cells of the global covariate fit (causarray/nb_glm_fast.py:418)
+
+
+def fit_glm_fast(Y, X, A=None, family='gaussian', disp_family='poisson', disp_glm=None, impute=False, offset=None,
+                 offset_test=None, shrinkage=False, alpha=1e-4, maxiter=1000, thres_disp=100., n_jobs=-3,
+                 random_state=0, verbose=False, mem_limit_gb=None, _lazy=False, **kwargs):
+    """The reference's batched "fast" route (``causarray/nb_glm_fast.py:164-594``), structure for structure,
+    on the device IRLS.
+
+    * no treatments, or a single one: one joint fit capped at ``min(maxiter, 50)`` iterations
+      (``_fit_glm_fast_single``, ``:304-370``);
+    * several treatments (``_fit_glm_fast_per_perturbation``, ``:373-594``): **stage 1** -- covariate-only
+      model on at most 3 000 cells (``np.random.default_rng(random_state).choice``, sorted), a Poisson
+      fit capped at 5 (NB) / 10 (Poisson) iterations, the method-of-moments dispersion from its fitted
+      means (clipped to alpha in [1e-8, 100]) and, for NB, an NB fit capped at 5 iterations; **stage 2** --
+      for every perturbation the 1-D treatment effect against the covariate offset ``X B_cov^T`` with that
+      dispersion held fixed, at most 50 iterations: with one-hot indicators the perturbations decouple,
+      so all of them are one launch of ``ca_glm_fit_treatment`` (control cells do not enter a
+      treatment's score equation, exactly as in the reference's ctrl + pert_k sub-fits).
+
+    The arithmetic inside the reference's stages is crispyx's ``NBGLMBatchFitter`` (un-vendored, absent
+    here): PARITY UNPINNED for it -- this function reproduces the documented structure (subsample, caps,
+    offsets, fixed dispersion, cell-weighted dispersion average) with the statsmodels-form IRLS of
+    ``fit_glm``; ``oracle/glm_fast.py`` restates it for the tests.  Returns like ``fit_glm``.
+    """
+    np.random.seed(random_state)
+    if family not in ['gaussian', 'poisson', 'nb']:
+        raise ValueError('Family not recognized')
+    if family == 'gaussian':
+        raise NotImplementedError('the gaussian family is outside the accelerated GCATE / LFC path')
+    X = np.asarray(X, dtype=np.float64)
+    n, d = X.shape
+    if A is not None:
+        A = np.asarray(A, dtype=np.float64)
+        if A.ndim == 1:
+            A = A[:, None]
+    if offset is not None and offset is not False:
+        if type(offset) == bool and offset is True:
+            offsets = np.log(comp_size_factor(Y, **_filter_params(comp_size_factor, kwargs)))
+        else:
+            offsets = np.asarray(offset, dtype=np.float64).ravel()
+    else:
+        offsets = None
+    one_hot = A is not None and A.shape[1] > 1 and np.all((A == 0) | (A == 1)) and np.all(A.sum(axis=1) <= 1)
+    if A is None or A.shape[1] == 1 or not one_hot:
+        # single joint batch fit (iteration cap of the reference's fast path)
+        return fit_glm(Y, X, A=A, family=family, disp_family=disp_family, disp_glm=disp_glm, impute=impute,
+                       offset=offsets, shrinkage=shrinkage, alpha=alpha, maxiter=min(int(maxiter), 50),
+                       thres_disp=thres_disp, random_state=random_state, verbose=verbose,
+                       mem_limit_gb=mem_limit_gb, _lazy=_lazy, **kwargs)
+    a = A.shape[1]
+    Yd = np.asarray(Y)
+    p = Yd.shape[1]
+    # ---- stage 1: global covariate model on a cell subsample ----
+    if n <= _N_STAGE1:
+        s1 = np.arange(n)
+    else:
+        s1 = np.sort(np.random.default_rng(random_state).choice(n, size=_N_STAGE1, replace=False))
+    dev1 = GlmDevice(len(s1), p)
+    dev1.load_counts(np.ascontiguousarray(Yd[s1], dtype=np.float64))
+    off1 = None if offsets is None else offsets[s1]
+    cap = 5 if family == 'nb' else 10
+    Bp, _, it_p, _ = dev1.fit('poisson', X[s1], off1, None, thres_disp=thres_disp, maxiter=min(int(maxiter), cap),
+                              tol=1e-8, d_guard=-1)
+    n_it = int(it_p.sum())
+    if family == 'nb':
+        # (the dispersion is a gene-level property estimated on the covariate-only design, :239-246; a
+        # caller-supplied disp_glm is used for the NB weights of stage 1 as the reference passes it on)
+        disp1 = dev1.disp_moments(off1)
+        alpha_g = np.clip(1.0 / disp1, 1e-8, 100.0)
+        alpha_g[~np.isfinite(alpha_g)] = 1.0
+        nu_g = 1.0 / alpha_g
+        B_cov, _, it_n, _ = dev1.fit('nb', X[s1], off1, nu_g, thres_disp=np.inf, maxiter=min(int(maxiter), 5), tol=1e-8,
+                                     d_guard=-1)
+        n_it += int(it_n.sum())
+    else:
+        B_cov, nu_g = Bp, None
+    dev1.close()
+    # ---- stage 2: per-perturbation treatment effects against the covariate offset, dispersion fixed ----
+    dev = _as_device(Y, kwargs.get('_glm'))
+    Xf = np.c_[X, A]
+    B0 = np.c_[B_cov, np.zeros((p, a))]
+    B, dv, it2, st2 = dev.fit_treatment('poisson' if family == 'poisson' else 'nb', Xf, B0, offsets, nu_g,
+                                        thres_disp=np.inf, maxiter=min(int(maxiter), 50), tol=1e-8)
+    B[st2 != 0, d:] = 0.0
+    COUNTERS['irls_gene_iters'] += n_it + int(it2.sum())
+    COUNTERS['fits'] += 1
+    disp_out = nu_g if family == 'nb' else disp_glm
+    fit = GlmFit(dev, B, dv, it2, st2, np.zeros(p, dtype=bool))
+    last_fit_info.update(n_genes=int(p), n_refit=0, max_iter=int(it2.max(initial=0)), irls_gene_iters=n_it + int(it2.sum()),
+                         route='fast-two-stage', n_stage1_cells=int(len(s1)))
+    if _lazy:
+        return B, fit, disp_out, offsets, None
+    resid = fit.resid()
+    if impute is not False:
+        X_test = impute if isinstance(impute, np.ndarray) else X
+        off_t = offsets
+        if offset_test is not None and np.asarray(offset_test).shape[0] == X_test.shape[0]:
+            off_t = np.asarray(offset_test, dtype=np.float64).ravel()
+        elif offsets is not None and offsets.shape[0] != X_test.shape[0]:
+            off_t = None
+        eta0 = X_test @ B[:, :d].T
+        if off_t is not None:
+            eta0 = eta0 + off_t[:, None]
+        Yhat_0 = np.repeat(np.exp(np.clip(eta0, -20, 20))[:, :, None], a, axis=2)
+        Yhat_1 = np.exp(np.clip(eta0[:, :, None] + B[:, d:][None, :, :], -20, 20))
+        Yhat = (Yhat_0, Yhat_1)
+    else:
+        Yhat = fit.fitted()
+    return B, Yhat, disp_out, offsets, resid
 
 
 def estimate_disp_auto(Y, X=None, A=None, Y_hat=None, disp_family='gaussian', offset=None, verbose=False, **kwargs):

@@ -194,7 +194,7 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
         if verbose:
             pprint.pprint('Estimating initial latent variables with GLMs...')
         with phase('gcate_init_glm'):
-            Bx, fit, _, _, _ = _glm_mod.fit_glm(Y, X, offset=offset, family=family, disp_glm=nuisance, maxiter=100,
+            Bx, fit, _, _, _ = _glm_mod.fit_glm_auto(Y, X, offset=offset, family=family, disp_glm=nuisance, maxiter=100,
                                                 verbose=verbose, _glm=ws.glm, _lazy=True)
         with phase('gcate_init_svd'):
             ptr = ws.glm.resid_device_ptr()
@@ -211,7 +211,7 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
         if verbose:
             pprint.pprint('Estimating initial coefficients with GLMs...')
         with phase('gcate_init_glm'):
-            B = _glm_mod.fit_glm(Y, A, offset=offset, family=family, disp_glm=nuisance, maxiter=100, verbose=verbose,
+            B = _glm_mod.fit_glm_auto(Y, A, offset=offset, family=family, disp_glm=nuisance, maxiter=100, verbose=verbose,
                                  _glm=ws.glm, _lazy=True)[0]
         u, s, vt = lowrank_product_svd(A[:, d:], B[:, d:], sharded=ws.shard is not None)
         A[:, d:] = u * s[None, :] ** (1 / 2)

@@ -184,6 +184,16 @@ int ca_glm_fit(ca_glm_t h, int family, const double* X, int kx, const double* of
 int ca_glm_fit_ex(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
                   double thres_disp, int maxiter, double tol, int d_guard, const double* ridge,
                   const uint8_t* gene_mask, double* B, double* dev, int32_t* n_iter, int32_t* status);
+/* Second stage of the reference's two-stage "fast" fit (causarray/nb_glm_fast.py:500-567: for every
+ * perturbation a 1-D treatment-effect fit against the covariate offset X B_cov^T with the dispersion
+ * held fixed).  X (n, kx) must contain a one-hot block of treatment indicators; B (p, kx) carries the
+ * covariate coefficients in, which are kept, and returns them together with the fitted treatment
+ * coefficients (all perturbations in one launch: the one-hot columns decouple once the covariate part
+ * is an offset).  Same convergence rule and outputs as ca_glm_fit_ex. */
+int ca_glm_fit_treatment(ca_glm_t h, int family, const double* X, int kx, const double* offset, const double* nu,
+                         double thres_disp, int maxiter, double tol, double* B, double* deviance, int32_t* n_iter,
+                         int32_t* status);
+
 /* Lasso refit of the genes flagged in gene_mask (p, uint8), warm-started from the coefficients of
  * the previous fit of the same width: penalised IRLS whose fixed point minimises
  *   -loglike(beta) / n + sum_k alpha_k |beta_k|,   l1[k] = n * alpha_k  (kx entries, caller's order),

