@@ -94,6 +94,9 @@ _SIGNATURES = {
     "ca_glm_fit_treatment": [_P, _c_int, _D, _c_int, _D, _D, _c_double, _c_int, _c_double, _D, _D, _I32, _I32],
     "ca_glm_resid": [_P, _D],
     "ca_glm_resid_device": [_P, ctypes.POINTER(_P)],
+    "ca_glm_resid_device2": [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int64)],
+    "ca_svd_topr": [_P, _P, ctypes.c_int64, _c_int, _c_int, _c_int, _c_int, _c_int, _c_double, ctypes.c_uint32, _U8, _D, _D,
+                    _D, _I32],
     "ca_glm_fitted": [_P, _D],
     "ca_glm_disp_moments": [_P, _D, _D],
     "ca_aipw_lfc": [_c_int] * 4 + [_D] * 8 + [_U8, ctypes.POINTER(LfcParams)] + [_D] * 5 + [_U8],

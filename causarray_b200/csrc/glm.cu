@@ -289,7 +289,7 @@ __global__ void k_glm_guard(int p, int kx, int d_guard, const double* __restrict
 // signed deviance residuals, written cell-major (n x p) through a tiled transpose
 __global__ void k_glm_resid(const double* __restrict__ Yt, const double* __restrict__ mu_t, long ldn, int n, int p,
                             const double* __restrict__ nu, int family, double thres, const int* __restrict__ status,
-                            double* __restrict__ out, long ldo) {
+                            double* __restrict__ out, long ldo, double* __restrict__ out_t) {
   __shared__ double tile[32][33];
   const int g0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
   for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
@@ -311,6 +311,7 @@ __global__ void k_glm_resid(const double* __restrict__ Yt, const double* __restr
       v = sg * sqrt(fmax(dd, 0.0));
     }
     tile[rr][threadIdx.x] = v;
+    if (out_t && gene < p && cell < n) out_t[(size_t)gene * ldn + cell] = v;   // gene-major copy (for R^T products)
   }
   __syncthreads();
   for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
@@ -824,7 +825,7 @@ extern "C" int ca_glm_resid(ca_glm_t h, double* resid) {
   if (out.alloc((size_t)n * p)) return -1;
   dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
   k_glm_resid<<<grid, block, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, p, h->has_nu ? h->nu.ptr : nullptr, h->family,
-                                         h->thres, h->status.ptr, out.ptr, p);
+                                         h->thres, h->status.ptr, out.ptr, p, nullptr);
   CA_LAUNCH_CHECK();
   CA_CUDA(cudaMemcpyAsync(resid, out.ptr, sizeof(double) * (size_t)n * p, cudaMemcpyDeviceToHost, h->st));
   CA_CUDA(cudaStreamSynchronize(h->st));
@@ -838,10 +839,27 @@ extern "C" int ca_glm_resid_device(ca_glm_t h, void** dev_ptr) {
   if (h->resid.alloc((size_t)n * p)) return -1;
   dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
   k_glm_resid<<<grid, block, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, p, h->has_nu ? h->nu.ptr : nullptr, h->family,
-                                         h->thres, h->status.ptr, h->resid.ptr, p);
+                                         h->thres, h->status.ptr, h->resid.ptr, p, nullptr);
   CA_LAUNCH_CHECK();
   CA_CUDA(cudaStreamSynchronize(h->st));
   *dev_ptr = h->resid.ptr;
+  return 0;
+}
+
+extern "C" int ca_glm_resid_device2(ca_glm_t h, void** dev_ptr, void** dev_ptr_t, int64_t* ldt) {
+  CA_REQUIRE(h && h->mu_t.ptr && dev_ptr && dev_ptr_t && ldt, "fit first");
+  if (glm_ensure_mu(h)) return -1;
+  const int n = h->n, p = h->p;
+  if (h->resid.alloc((size_t)n * p) || h->resid_t.alloc((size_t)p * h->ldn)) return -1;
+  CA_CUDA(cudaMemsetAsync(h->resid_t.ptr, 0, h->resid_t.bytes(), h->st));
+  dim3 grid((n + 31) / 32, (p + 31) / 32), block(32, 8);
+  k_glm_resid<<<grid, block, 0, h->st>>>(h->Yt, h->mu_t.ptr, h->ldn, n, p, h->has_nu ? h->nu.ptr : nullptr, h->family,
+                                         h->thres, h->status.ptr, h->resid.ptr, p, h->resid_t.ptr);
+  CA_LAUNCH_CHECK();
+  CA_CUDA(cudaStreamSynchronize(h->st));
+  *dev_ptr = h->resid.ptr;
+  *dev_ptr_t = h->resid_t.ptr;
+  *ldt = h->ldn;
   return 0;
 }
 

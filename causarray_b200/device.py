@@ -313,6 +313,13 @@ class GlmDevice:
         L.check(self.lib.ca_glm_resid_device(self.h, ctypes.byref(ptr)))
         return ptr.value
 
+    def resid_device_ptrs(self):
+        """Device pointers of the residual matrix of the last fit, cell-major (n, p) and gene-major
+        (p, ld): ``(ptr, ptr_t, ld)``."""
+        ptr, ptr_t, ld = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(0)
+        L.check(self.lib.ca_glm_resid_device2(self.h, ctypes.byref(ptr), ctypes.byref(ptr_t), ctypes.byref(ld)))
+        return ptr.value, ptr_t.value, int(ld.value)
+
     def resid(self):
         out = np.empty((self.n, self.p))
         L.check(self.lib.ca_glm_resid(self.h, L.dptr(out)))

@@ -18,7 +18,7 @@ import scipy.linalg
 
 from . import glm as _glm_mod
 from .device import GcateDevice, GlmDevice, RowsView, device_dtype
-from .svd import topr_svd_device, lowrank_product_svd
+from .svd import topr_svd_device, topr_svd_native, lowrank_product_svd
 from ._timing import phase
 
 type_f = np.float64
@@ -197,8 +197,13 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
             Bx, fit, _, _, _ = _glm_mod.fit_glm_auto(Y, X, offset=offset, family=family, disp_glm=nuisance, maxiter=100,
                                                 verbose=verbose, _glm=ws.glm, _lazy=True)
         with phase('gcate_init_svd'):
-            ptr = ws.glm.resid_device_ptr()
-            u, s, vt = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask, sharded=ws.shard is not None)
+            out = None
+            if ws.shard is None and r + 20 <= 64:
+                out = topr_svd_native(ws.glm, n, p, r, zero_cols=fit.refit_mask)
+            if out is None:     # gene shards (reductions over the process group) / very wide blocks / breakdown
+                ptr = ws.glm.resid_device_ptr()
+                out = topr_svd_device(ptr, n, p, r, zero_cols=fit.refit_mask, sharded=ws.shard is not None)
+            u, s, vt = out
         if u.shape[1] < r:
             raise ValueError('The number of latent factors is larger than the rank of deviance residuals '
                              '({}). Try to decrease the value of r.'.format(u.shape[1]))

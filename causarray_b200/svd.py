@@ -32,6 +32,29 @@ def fix_signs(u, vt=None):
     return u, vt
 
 
+def topr_svd_native(glm, n, p, r, zero_cols=None, oversample=20, max_iter=400, tol=1e-11, seed=0):
+    """Top-``r`` singular triplets of the residual matrix of ``glm``'s last fit through the library's own
+    subspace iteration (``ca_svd_topr``, ``csrc/svd.cu``: hand-written FP64 DMMA products, Cholesky-QR2,
+    Rayleigh-Ritz; no torch / cuBLAS / cuSOLVER).  Returns ``u (n, r)``, ``s (r,)`` ascending, ``vt (r, p)``
+    like ``svds``, or ``None`` when the block iteration broke down numerically (the caller falls back)."""
+    import ctypes
+    from . import _lib as L
+    lib = L.load()
+    ptr, ptr_t, ld = glm.resid_device_ptrs()
+    rr = int(min(r, min(n, p)))
+    U, S, Vt = np.empty((n, rr)), np.empty(rr), np.empty((rr, p))
+    zc = None if zero_cols is None or not np.any(zero_cols) else np.ascontiguousarray(zero_cols, dtype=np.uint8)
+    it = np.zeros(1, dtype=np.int32)
+    rc = lib.ca_svd_topr(ctypes.c_void_p(ptr), ctypes.c_void_p(ptr_t), ld, n, p, rr, int(oversample), int(max_iter),
+                         float(tol), int(seed), L.u8ptr(zc), L.dptr(U), L.dptr(S), L.dptr(Vt), L.i32ptr(it))
+    if rc == -3:
+        return None
+    L.check(rc)
+    u, s, vt = U[:, ::-1].copy(), S[::-1].copy(), Vt[::-1].copy()    # ascending, as svds returns them
+    u, vt = fix_signs(u, vt)
+    return u, s, vt
+
+
 def topr_svd_device(ptr, n, p, r, zero_cols=None, oversample=20, max_iter=400, tol=1e-11, seed=0, sharded=False):
     """Top-``r`` singular triplets of the (n, p) float64 matrix at device pointer ``ptr``.
 

@@ -212,6 +212,9 @@ int ca_glm_resid(ca_glm_t h, double* resid);
  * a host round trip. */
 int ca_glm_resid_device(ca_glm_t h, void** dev_ptr);
 /* Fitted means of the last fit, (n x p). */
+/* Residuals of the last fit on the device in both layouts: *dev_ptr (n, p) cell-major and *dev_ptr_t
+ * (p, *ldt) gene-major -- the two operands of the subspace iteration below.  Valid until the next fit. */
+int ca_glm_resid_device2(ca_glm_t h, void** dev_ptr, void** dev_ptr_t, int64_t* ldt);
 int ca_glm_fitted(ca_glm_t h, double* mu);
 /* Method-of-moments NB size from the last (Poisson) fit (gcate_glm.py:301-306). */
 int ca_glm_disp_moments(ca_glm_t h, const double* offset, double* disp);
@@ -267,6 +270,17 @@ int ca_host_median_mad_rows(const double* t, int a, int m, double* med, double* 
  * standardisation (t - median) / (MAD / Phi^-1(3/4)) (NaN rows when MAD == 0); med_mad (a, 2) or NULL. */
 int ca_inference_tail(const double* t, const double* df, int a, int p, double* pvalue, double* padj,
                       double* pvalue_adj, double* padj_adj, double* med_mad);
+
+/* ------------------------------------------------------------------------
+ * K7: top-r singular triplets of the deviance-residual matrix (GCATE initialisation; replaces
+ * scipy.sparse.linalg.svds of causarray/gcate_opt.py:312 and gcate.py:296).  Block subspace iteration
+ * (width r + oversample <= 64) with Cholesky-QR2 and Rayleigh-Ritz, hand-written FP64 DMMA products.
+ * R (n, p) and Rt (p, ldt) are DEVICE pointers (ca_glm_resid_device2); zero_genes (p, host) or NULL;
+ * U (n, r), S (r), Vt (r, p) host outputs, singular values DESCENDING; returns -3 on a numerical
+ * breakdown (rank-deficient block).
+ * ------------------------------------------------------------------------ */
+int ca_svd_topr(void* R, void* Rt, int64_t ldt, int n, int p, int r, int oversample, int max_iter, double tol,
+                uint32_t seed, const uint8_t* zero_genes, double* U, double* S, double* Vt, int32_t* n_iter);
 
 /* ------------------------------------------------------------------------
  * Measurement hooks (bench.py): per-kernel-class device time from CUDA events
