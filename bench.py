@@ -141,6 +141,8 @@ def gpu_step(batch, resident_ws=None):
                  gene_rows=(alt_iters) * p,
                  cell_evals=res1["line_search_evals"][0] + res2["line_search_evals"][0],
                  gene_evals=res1["line_search_evals"][1] + res2["line_search_evals"][1],
+                 gene_evals_onehot=res1["line_search_evals_onehot"][0] + res2["line_search_evals_onehot"][0],
+                 onehot_cells=max(res1["line_search_evals_onehot"][1], res2["line_search_evals_onehot"][1]),
                  loop_seconds=res1["loop_seconds"] + res2["loop_seconds"], n=n, p=p,
                  gram_flops=cglm.COUNTERS["gram_flops"], gram_flops_structured=cglm.COUNTERS["gram_flops_structured"],
                  n_sig=int(np.nansum(df["padj"].to_numpy() < 0.05)))
@@ -526,12 +528,16 @@ def main():
     # per-kernel-class algorithmic bytes over the timed resident steps (rank 0)
     st_sum = {k: sum(s[k] for s in stats_res) for k in ("cell_updates", "gene_rows", "cell_evals", "gene_evals",
                                                          "irls_gene_iters", "alt_iters", "gram_flops",
-                                                         "gram_flops_structured")}
+                                                         "gram_flops_structured", "gene_evals_onehot")}
+    n_tr = max(s["onehot_cells"] for s in stats_res)
     alg_bytes = {
         # Y read once per active row: cells x p + genes x n doubles
         "rowpass_grad": 8.0 * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
         # one read of the row of Y per candidate evaluation
-        "search": 8.0 * (st_sum["cell_evals"] * p + st_sum["gene_evals"] * n),
+        # (stage-2 gene candidates of the one-hot search read the counts and the linear predictor of the
+        # TREATED cells only: 16 B per entry)
+        "search": 8.0 * (st_sum["cell_evals"] * p + (st_sum["gene_evals"] - st_sum["gene_evals_onehot"]) * n)
+                  + 16.0 * st_sum["gene_evals_onehot"] * n_tr,
         # one read of the gene's counts per IRLS iteration
         "glm_pass": 8.0 * st_sum["irls_gene_iters"] * n,
     }
@@ -561,7 +567,9 @@ def main():
     flops_eval = 2.0 * k_tot + 54.0
     flops_grad = 2.0 * k_tot + 54.0 + 12.0 + 32.0
     alg_flops = {
-        "search": flops_eval * (st_sum["cell_evals"] * p + st_sum["gene_evals"] * n),
+        # one-hot stage-2 candidates: ~19 FP64 instructions per treated entry (no matrix product, no exp)
+        "search": flops_eval * (st_sum["cell_evals"] * p + (st_sum["gene_evals"] - st_sum["gene_evals_onehot"]) * n)
+                  + 38.0 * st_sum["gene_evals_onehot"] * n_tr,
         "rowpass_grad": flops_grad * (st_sum["cell_updates"] * p + st_sum["gene_rows"] * n),
         # IRLS: the round-1 formula 2 n [kx(kx+1)/2 + 2 kx] per gene-iteration, kept so that the
         # fraction is comparable between rounds; the structure-aware count is reported beside it
@@ -602,7 +610,9 @@ def main():
                                                              "design columns (pair products, right-hand side, linear "
                                                              "predictor, ~65 flop-equivalents of exp / log / reciprocals)"}
         elif name == "search":
-            r["algorithmic_flops"] = "(2 k + 54) per evaluated entry of a line-search candidate, k = %d" % k_tot
+            r["algorithmic_flops"] = ("(2 k + 54) per evaluated entry of a line-search candidate, k = %d; 38 per TREATED entry "
+                                      "for the stage-2 gene candidates of the one-hot search (%d of %d cells; control "
+                                      "cells and the matrix product drop out)" % (k_tot, n_tr, n))
         else:
             r["algorithmic_flops"] = "(2 k + 98) per entry of a gradient pass, k = %d" % k_tot
         r["note"] = ("bound by the shared FP64 pipe (DMMA + DFMA + table-driven exp / log), not by HBM: the HBM view is "

@@ -40,6 +40,7 @@ class AltminResult(ctypes.Structure):
         ("total_gene_updates", ctypes.c_int64), ("total_cell_updates", ctypes.c_int64),
         ("cell_evals", ctypes.c_int64), ("gene_evals", ctypes.c_int64),
         ("loop_seconds", ctypes.c_double),
+        ("gene_evals_onehot", ctypes.c_int64), ("onehot_treated_cells", ctypes.c_int64),
     ]
 
 

@@ -81,7 +81,7 @@ static int gcate_alloc(ca_gcate* h) {
   if (h->ell_c.alloc(n) || h->ell_g.alloc(p) || h->ellfin_c.alloc(n) || h->ellfin_g.alloc(p) ||
       h->Graw_c.alloc((size_t)n * h->ldG) || h->Graw_g.alloc((size_t)p * h->ldG) || h->g_c.alloc((size_t)n * kp) ||
       h->g_g.alloc((size_t)p * kp) || h->f0_c.alloc(n) || h->f0_g.alloc(p) || h->ng_c.alloc(n) || h->ng_g.alloc(p) ||
-      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(4) || h->neval_g.alloc(p) || h->alpha_gene.alloc(p) || h->ls_pend.alloc(std::max(n, p)) ||
+      h->W.alloc(64 * 64) || h->scal.alloc(16) || h->evals.alloc(8) || h->neval_g.alloc(p) || h->alpha_gene.alloc(p) || h->ls_pend.alloc(std::max(n, p)) ||
       h->ls_f01.alloc(std::max(n, p)) || h->ls_e01.alloc(std::max(n, p)) || h->ls_list2.alloc(std::max(n, p)))
     return -1;
   CA_CUDA(cudaMemsetAsync(h->Yn.ptr, 0, h->Yn.bytes(), h->st));
@@ -382,6 +382,12 @@ static int upload_padded(double* dst, const double* src, int rows, int k, int kp
 extern "C" int ca_gcate_set_factors(ca_gcate_t h, const double* A, const double* B) {
   CA_REQUIRE(h, "null handle");
   if (A && upload_padded(h->A.ptr, A, h->n, h->k, h->kpad, h->st)) return -1;
+  if (A) {
+    h->hostX.resize((size_t)h->n * h->d);
+    for (int i = 0; i < h->n; ++i)
+      for (int c = 0; c < h->d; ++c) h->hostX[(size_t)i * h->d + c] = A[(size_t)i * h->k + c];
+    h->s2_checked = false;
+  }
   if (B && upload_padded(h->B.ptr, B, h->p, h->k, h->kpad, h->st)) return -1;
   CA_CUDA(cudaStreamSynchronize(h->st));
   h->factors_set = true;
@@ -546,6 +552,58 @@ static int cell_search_sharded(ca_gcate* h, const RowProblem& rp, double alpha, 
   return 0;
 }
 
+// Stage 2 with one-hot treatment indicators: every treated cell belongs to exactly one of the `a`
+// treatment columns of A (values 0 / 1).  Builds the group-sorted treated-cell list, the column map
+// for the linear predictor written by the gene gradient pass and the gathered counts.
+static int s2_prepare(ca_gcate* h) {
+  h->s2_checked = true;
+  h->s2_ok = false;
+  const int n = h->n, d = h->d, a = h->a;
+  if (getenv("CA_NO_S2_ONEHOT") || !h->has_P2 || a < 1 || a > 32 || (int)h->hostX.size() != n * d) return 0;
+  std::vector<int> grp(n, -1), cnt(a, 0);
+  for (int i = 0; i < n; ++i) {
+    const double* x = h->hostX.data() + (size_t)i * d + (d - a);
+    for (int c = 0; c < a; ++c) {
+      if (x[c] == 0.0) continue;
+      if (x[c] != 1.0 || grp[i] >= 0) return 0;     // not an indicator / two treatments in one cell
+      grp[i] = c;
+    }
+    if (grp[i] >= 0) ++cnt[grp[i]];
+  }
+  int ntr = 0;
+  std::vector<int> start(a + 1, 0);
+  for (int c = 0; c < a; ++c) start[c + 1] = start[c] + cnt[c];
+  ntr = start[a];
+  if (ntr == 0) return 0;
+  std::vector<int> cells(ntr), pos(n, -1), cur(start.begin(), start.end() - 1);
+  std::vector<signed char> g8(ntr);
+  for (int i = 0; i < n; ++i)
+    if (grp[i] >= 0) {
+      const int q = cur[grp[i]]++;
+      cells[q] = i;
+      pos[i] = q;
+      g8[q] = (signed char)grp[i];
+    }
+  const long ld = (ntr + 7) / 8 * 8;
+  const bool same = h->s2_cells_host == cells && h->s2_a == a && h->s2_Ytr.ptr;
+  if (h->s2_cells.alloc(ntr) || h->s2_pos.alloc(n) || h->s2_grp.alloc(ntr) || h->s2_Ytr.alloc((size_t)h->p * ld) ||
+      h->s2_Th.alloc((size_t)h->p * ld))
+    return -1;
+  if (!same) {
+    CA_CUDA(cudaMemcpyAsync(h->s2_cells.ptr, cells.data(), sizeof(int) * ntr, cudaMemcpyHostToDevice, h->st));
+    CA_CUDA(cudaMemcpyAsync(h->s2_pos.ptr, pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->st));
+    CA_CUDA(cudaMemcpyAsync(h->s2_grp.ptr, g8.data(), ntr, cudaMemcpyHostToDevice, h->st));
+    if (launch_s2_gather(h->Ynt.ptr, h->ldn, h->p, h->s2_cells.ptr, ntr, h->s2_Ytr.ptr, ld, h->st)) return -1;
+    CA_CUDA(cudaStreamSynchronize(h->st));
+    h->s2_cells_host = cells;
+  }
+  h->s2_ntr = ntr;
+  h->s2_a = a;
+  h->s2_ld = ld;
+  h->s2_ok = true;
+  return 0;
+}
+
 // One alternating iteration, asynchronous on h->st.  On completion
 // scal[0] = sum_j ell_fin_g[j] (log-likelihood sum at the new A, B).
 static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int max_iters, double tol) {
@@ -643,6 +701,13 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       ball_hi = k;
     }
     const bool any_grad = gc_n > 0;
+    if (h->has_P2 && !h->s2_checked && s2_prepare(h)) return -1;
+    const bool s2 = h->has_P2 && h->s2_ok && h->s2_a == a && a > 0 && gc_lo == d - a && gc_n == a;
+    if (s2) {   // the gradient pass also leaves the linear predictor of the treated cells behind
+      rp.theta_out = h->s2_Th.ptr;
+      rp.theta_pos = h->s2_pos.ptr;
+      rp.theta_ld = h->s2_ld;
+    }
     // all genes: the column log-likelihood of inactive genes changes with A
     if (launch_rowpass(rp, h->B.ptr, nullptr, nullptr, p, any_grad, gc_lo, gc_n, h->ell_g.ptr, h->Graw_g.ptr, h->ldG, st))
       return -1;
@@ -712,7 +777,44 @@ static int enqueue_update(ca_gcate* h, double C, double alpha, double beta, int 
       s.e01s = h->ls_e01.ptr;
       s.list2 = h->ls_list2.ptr;
       s.count2 = cnt + 6;
-      if (launch_search(rp, s, st)) return -1;
+      if (s2) {
+        S2Launch q;
+        q.Ytr = h->s2_Ytr.ptr;
+        q.Th = h->s2_Th.ptr;
+        q.grp = h->s2_grp.ptr;
+        q.ldtr = h->s2_ld;
+        q.ntr = h->s2_ntr;
+        q.a = a;
+        q.kpad = kp;
+        q.t_lo = d - a;
+        q.ncols_total = n;
+        q.X = h->B.ptr;
+        q.g = h->g_g.ptr;
+        q.lam = pa.lam;
+        q.f0 = h->f0_g.ptr;
+        q.normg = h->ng_g.ptr;
+        q.tys = h->tys_col.ptr;
+        q.ell0 = h->ell_g.ptr;
+        q.alpha_row = s.alpha_row;
+        q.alpha = alpha;
+        q.beta = beta;
+        q.tol = tol;
+        q.max_iters = max_iters;
+        q.rowlist = h->list_g.ptr;
+        q.count = cnt + 1;
+        q.nrows = p;
+        q.nu = h->nu.ptr;
+        q.inv_nu = h->inv_nu.ptr;
+        q.log_nu = h->log_nu.ptr;
+        q.family = h->family;
+        q.thres = h->thres;
+        q.ell_fin = h->ellfin_g.ptr;
+        q.neval = h->neval_g.ptr;
+        q.eval_total = h->evals.ptr + 1;
+        if (launch_s2_onehot(q, st)) return -1;
+      } else if (launch_search(rp, s, st)) {
+        return -1;
+      }
     }
     if (!h->has_P2 && r > 0) {
       // clip Gamma to [-10, 10] (gcate_opt.py:202-203); re-evaluate genes that were clipped
@@ -928,7 +1030,7 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   if (t == prm->es_max_iters) t = prm->es_max_iters - 1;  // python's loop variable after exhaustion
   if (peer_check(h)) return -1;
   auto t1 = std::chrono::steady_clock::now();
-  unsigned long long ev[4];
+  unsigned long long ev[8];
   CA_CUDA(cudaMemcpy(ev, h->evals.ptr, sizeof ev, cudaMemcpyDeviceToHost));
   res->n_iter = t;
   res->func_val = f;
@@ -938,6 +1040,8 @@ extern "C" int ca_gcate_alter_min(ca_gcate_t h, const ca_altmin_params* prm, ca_
   res->total_cell_updates = tot_c;
   res->cell_evals = (int64_t)ev[0];
   res->gene_evals = (int64_t)ev[1];
+  res->gene_evals_onehot = (int64_t)ev[4];
+  res->onehot_treated_cells = h->s2_ok ? h->s2_ntr : 0;
   if (getenv("CA_TIMING")) {
     std::vector<int> ne(p);
     CA_CUDA(cudaMemcpy(ne.data(), h->neval_g.ptr, sizeof(int) * p, cudaMemcpyDeviceToHost));

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "devbuf.h"
 
 using ca::DevBuf;
@@ -35,6 +36,16 @@ struct ca_gcate {
   DevBuf<int> ls_ne;
   int any_pois = 0;                  // some nu exceeds thres (the NB kernels then keep their Poisson switch)
   bool counts_loaded = false, factors_set = false;
+  // stage-2 one-hot gene line search (search_onehot.cu): host copy of the observed columns of A,
+  // treated cells in group order, their normalised counts and linear predictors
+  std::vector<double> hostX;         // n x d (first d columns of A as uploaded by set_factors)
+  bool s2_checked = false, s2_ok = false;
+  int s2_ntr = 0, s2_a = 0;
+  long s2_ld = 0;
+  std::vector<int> s2_cells_host;
+  DevBuf<int> s2_cells, s2_pos;
+  DevBuf<signed char> s2_grp;
+  DevBuf<double> s2_Ytr, s2_Th;
   // raw counts kept for the GLM / AIPW handles that share them
   DevBuf<double> Yraw, Yraw_t;
   bool raw_loaded = false;

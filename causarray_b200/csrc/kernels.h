@@ -22,7 +22,45 @@ struct RowProblem {
   int any_pois;      // some nu exceeds thres_disp
   int family;
   double thres_disp;
+  // optional (gradient passes only): theta of the columns with theta_pos[col] >= 0 is also written to
+  // theta_out[row * theta_ld + theta_pos[col]] (stage-2 one-hot line search, search_onehot.cu)
+  double* theta_out = nullptr;
+  const int* theta_pos = nullptr;
+  long theta_ld = 0;
 };
+
+// stage-2 gene line search for one-hot treatment indicators (search_onehot.cu)
+struct S2Launch {
+  const double* Ytr;
+  const double* Th;
+  const signed char* grp;
+  long ldtr;
+  int ntr, a, kpad, t_lo, ncols_total;
+  double* X;
+  const double* g;
+  const double* lam;
+  const double* f0;
+  const double* normg;
+  const double* tys;
+  const double* ell0;
+  const double* alpha_row;
+  double alpha, beta, tol;
+  int max_iters;
+  const int* rowlist;
+  const int* count;
+  int nrows;
+  const double* nu;
+  const double* inv_nu;
+  const double* log_nu;
+  int family;
+  double thres;
+  double* ell_fin;
+  int* neval;
+  unsigned long long* eval_total;
+};
+int launch_s2_onehot(const S2Launch& L, cudaStream_t st);
+int launch_s2_gather(const double* Ynt, long ldn, int p, const int* cells, int ntr, double* Ytr, long ldtr,
+                     cudaStream_t st);
 
 struct SearchLaunch {
   double* X;            // rows x kpad, updated in place

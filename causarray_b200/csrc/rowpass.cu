@@ -32,6 +32,9 @@ static int make_cfg(const RowProblem& rp, PassCfg& P) {
   P.fm_tables = fastmath_tables();
   CA_REQUIRE(P.fm_tables, "fastmath tables unavailable");
   P.clip = nb_clip_constants();
+  P.theta_out = rp.theta_out;
+  P.theta_pos = rp.theta_pos;
+  P.theta_ld = rp.theta_ld;
   return 0;
 }
 

@@ -58,6 +58,9 @@ struct PassCfg {
   int tc;  // columns per staged chunk (multiple of 8)
   const double* fm_tables;
   NbClip clip;
+  double* theta_out;      // optional, gradient passes: see RowProblem
+  const int* theta_pos;
+  long theta_ld;
 };
 
 struct SearchArgs {
@@ -258,7 +261,7 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
 // Per iteration a warp handles TWO 8x8 tiles (t and t + 8): four independent per-entry
 // dependency chains per lane and 2 x NACC independent DMMA accumulators (measured latencies:
 // DFMA 8 cycles, DMMA 26 cycles, one DMMA per 16 cycles per SM sub-partition).
-template <int KS, bool GRAD, int NGT, int MODE>
+template <int KS, bool GRAD, int NGT, int MODE, bool TH = false>
 __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables& FT, const int* s_rows,
                                                const double* s_X, const Smem& S, int gc_lo, Pipe& pipe) {
   constexpr int KPAD = 4 * KS;
@@ -359,6 +362,17 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
           dmma884(gacc[j][0], gacc[j][1], dA1, gA[KPAD + 8 * j]);
           dmma884(gacb[j][0], gacb[j][1], dB1, gB[KPAD + 8 * j]);
         }
+        if (TH && row >= 0) {
+          // linear predictor of the selected columns (the treated cells of a stage-2 gene pass) for the
+          // one-hot line search that follows; placed after the likelihood terms so that their
+          // straight-line block stays intact
+          double* tr = P.theta_out + (size_t)row * P.theta_ld;
+          const int cA = col0 + clA, cB = col0 + clB;
+          if (vA0) { const int q = P.theta_pos[cA]; if (q >= 0) tr[q] = pa[0][0]; }
+          if (vA1) { const int q = P.theta_pos[cA + 1]; if (q >= 0) tr[q] = pa[0][1]; }
+          if (hasB && vB0) { const int q = P.theta_pos[cB]; if (q >= 0) tr[q] = pb[0][0]; }
+          if (hasB && vB1) { const int q = P.theta_pos[cB + 1]; if (q >= 0) tr[q] = pb[0][1]; }
+        }
       }
     };
 #pragma unroll 1
@@ -403,9 +417,18 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
   __syncthreads();
 }
 
-template <int KS, bool GRAD, int NGT>
+template <int KS, bool GRAD, int NGT, bool TH = false>
 __device__ __forceinline__ void tile_pass(const PassCfg& P, const FmTables& FT, const int* s_rows, const double* s_X,
                                           const Smem& S, int gc_lo, Pipe& pipe) {
+  if (TH) {   // (theta output: gene passes only, i.e. per-row dispersions)
+    if (P.family != CA_FAMILY_NB)
+      tile_pass_mode<KS, GRAD, NGT, MODE_POIS, TH>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+    else if (P.any_pois)
+      tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW, TH>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+    else
+      tile_pass_mode<KS, GRAD, NGT, MODE_NB_ROW_F, TH>(P, FT, s_rows, s_X, S, gc_lo, pipe);
+    return;
+  }
   if (P.family != CA_FAMILY_NB)
     tile_pass_mode<KS, GRAD, NGT, MODE_POIS>(P, FT, s_rows, s_X, S, gc_lo, pipe);
   else if (P.nu_per_row && P.any_pois)
@@ -434,7 +457,7 @@ __device__ __forceinline__ void pipe_init(Pipe& pipe, unsigned long long* bars) 
 //   ell_out[row]                      = sum_col ell
 //   G_out[row * ldG + c], c < ngt*8   = sum_col dl * M[col, gc_lo + c]   (GRAD)
 // ---------------------------------------------------------------------------
-template <int KS, bool GRAD, int NGT>
+template <int KS, bool GRAD, int NGT, bool TH = false>
 __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_rowpass(PassCfg P, const double* X, const int* rowlist,
                                                        const int* count, int nrows, int gc_lo,
                                                        double* ell_out, double* G_out, int ldG) {
@@ -460,7 +483,7 @@ __global__ void __launch_bounds__(NTHREADS, CA_MINB) k_rowpass(PassCfg P, const 
     S.X[e] = (row >= 0) ? X[(size_t)row * KPAD + c] : 0.0;
   }
   __syncthreads();
-  tile_pass<KS, GRAD, NGT>(P, FT, s_rows, S.X, S, gc_lo, pipe);
+  tile_pass<KS, GRAD, NGT, TH>(P, FT, s_rows, S.X, S, gc_lo, pipe);
   if (threadIdx.x < 8 && s_rows[threadIdx.x] >= 0) ell_out[s_rows[threadIdx.x]] = S.rowsum[threadIdx.x];
   if (GRAD) {
     for (int e = threadIdx.x; e < 8 * NGT * 8; e += NTHREADS) {

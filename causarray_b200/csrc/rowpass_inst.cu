@@ -25,6 +25,14 @@ int launch_rowpass_ks(const PassCfg& P, const double* X, const int* rowlist, con
     const size_t sm = sizeof(double) * smem_doubles(P.tc, KPAD, 1, 1);
     if (set_smem(k_rowpass<KS, false, 1>, sm)) return -1;
     k_rowpass<KS, false, 1><<<grid, NTHREADS, sm, st>>>(P, X, rowlist, count, nrows, 0, ell_out, nullptr, 0);
+  } else if (P.theta_out && P.nu_per_row && gc_n <= 16) {   // gene pass that also leaves theta of the treated cells
+    const size_t sm = sizeof(double) * smem_doubles(P.tc, KPAD, 2, 1);
+    if (set_smem(k_rowpass<KS, true, 2, true>, sm)) return -1;
+    k_rowpass<KS, true, 2, true><<<grid, NTHREADS, sm, st>>>(P, X, rowlist, count, nrows, gc_lo, ell_out, G_out, ldG);
+  } else if (P.theta_out && P.nu_per_row && gc_n <= 32) {
+    const size_t sm = sizeof(double) * smem_doubles(P.tc, KPAD, 4, 1);
+    if (set_smem(k_rowpass<KS, true, 4, true>, sm)) return -1;
+    k_rowpass<KS, true, 4, true><<<grid, NTHREADS, sm, st>>>(P, X, rowlist, count, nrows, gc_lo, ell_out, G_out, ldG);
   } else if (gc_n <= 16) {
     const size_t sm = sizeof(double) * smem_doubles(P.tc, KPAD, 2, 1);
     if (set_smem(k_rowpass<KS, true, 2>, sm)) return -1;

@@ -238,7 +238,8 @@ def alter_min(Y, r, X=None, P1=None, P2=None, A=None, B=None,
     res = {'n_iter': res_c.n_iter, 'func_val': res_c.func_val, 'resid': res_c.resid, 'hist': list(hist),
            'kwargs_glm': kwargs_glm, 'kwargs_ls': kwargs_ls, 'kwargs_es': kwargs_es,
            'total_gene_updates': int(res_c.total_gene_updates), 'total_cell_updates': int(res_c.total_cell_updates),
-           'line_search_evals': (int(res_c.cell_evals), int(res_c.gene_evals)), 'loop_seconds': res_c.loop_seconds}
+           'line_search_evals': (int(res_c.cell_evals), int(res_c.gene_evals)), 'loop_seconds': res_c.loop_seconds,
+           'line_search_evals_onehot': (int(res_c.gene_evals_onehot), int(res_c.onehot_treated_cells))}
     res['X_U'] = A
     res['B_Gamma'] = B
     res['U'] = A[:, d:]

@@ -143,6 +143,9 @@ typedef struct {
   int64_t total_gene_updates, total_cell_updates;
   int64_t cell_evals, gene_evals; /* line-search evaluations actually run */
   double loop_seconds;
+  int64_t gene_evals_onehot;      /* of gene_evals: candidates evaluated by the one-hot stage-2 search, which
+                                     touches only the treated cells */
+  int64_t onehot_treated_cells;   /* cells with a treatment indicator set (0 when that path is not taken) */
 } ca_altmin_result;
 
 /* The optimiser loop of alter_min (gcate_opt.py:337-458) from the factors set
