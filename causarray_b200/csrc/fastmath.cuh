@@ -114,6 +114,86 @@ __device__ __forceinline__ double fm_rcp(double w) {
   return fma(r, e, r);
 }
 
+// N independent evaluations written statement by statement across the N values, so that the generated code
+// has the N dependent chains interleaved IN SOURCE ORDER (ptxas does not reorder the far-apart chains of N
+// consecutive scalar calls when registers are tight: the per-octet IRLS kernel ran its genes one after the
+// other, every dependent DFMA exposed).  Same arithmetic, operation for operation, as the scalar versions.
+template <int N>
+__device__ __forceinline__ void fm_exp_n(const double (&x)[N], double (&out)[N], const double* __restrict__ T) {
+  double t[N], kd[N], r[N], p[N], tj[N];
+  int k[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fma(x[i], FMC[1], FMC[0]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    k[i] = __double2loint(t[i]);
+    kd[i] = t[i] - FMC[0];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) tj[i] = T[k[i] & (FM_EXP_N - 1)];
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(kd[i], FMC[2], x[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(kd[i], FMC[3], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(r[i], FMC[4], FMC[5]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(r[i], p[i], FMC[6]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(r[i], p[i], FMC[7]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = fma(r[i], p[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i] = p[i] * r[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double v = fma(tj[i], p[i], tj[i]);
+    out[i] = __hiloint2double(__double2hiint(v) + ((k[i] >> 7) << 20), __double2loint(v));
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void fm_log_n(const double (&w)[N], double (&out)[N], const double2* __restrict__ LT) {
+  double f[N], r[N], q[N], ed[N];
+  double2 tc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int hi = __double2hiint(w[i]);
+    ed[i] = (double)((hi >> 20) - 1023);
+    f[i] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(w[i]));
+    tc[i] = LT[(hi >> 13) & (FM_LOG_N - 1)];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(f[i], tc[i].x, -1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i], FMC[8], FMC[9]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i], q[i], FMC[10]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i], q[i], FMC[11]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i], q[i], FMC[12]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fma(r[i] * r[i], q[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(ed[i], FMC[13], tc[i].y) + fma(ed[i], FMC[14], q[i]);
+}
+
+template <int N>
+__device__ __forceinline__ void fm_rcp_n(const double (&w)[N], double (&out)[N]) {
+  double r[N], e[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(w[i]));
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-w[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fma(r[i], fma(e[i], e[i], e[i]), r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) e[i] = fma(-w[i], r[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = fma(r[i], e[i], r[i]);
+}
+
 // Comparisons against a constant of known sign done on the integer pipe (IEEE-754 doubles of one
 // sign order like their bit patterns): a DSETP costs a slot on the FP64 pipe, which is the pipe the
 // likelihood kernels are bound by; ISETP pairs run on the ALU.  Exact for every non-NaN input.

@@ -18,15 +18,21 @@
 namespace ca {
 
 // Yp[g][c] = perm[c] >= 0 ? Yt[g][perm[c]] : 0   (one CTA row per gene, coalesced writes)
+// *not_counts is raised when an entry is not a non-negative integer (the IRLS kernel then computes every
+// log y instead of reading its table of log 0 .. log 255).
 __global__ void k_glm_permute_counts(const double* __restrict__ Yt, long ldn, int p, const int* __restrict__ perm,
-                                     int npad, double* __restrict__ Yp, long ldp) {
+                                     int npad, double* __restrict__ Yp, long ldp, int* __restrict__ not_counts) {
   const int gene = blockIdx.y;
   const double* src = Yt + (size_t)gene * ldn;
   double* dst = Yp + (size_t)gene * ldp;
+  bool odd = false;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < npad; c += gridDim.x * blockDim.x) {
     const int s = perm[c];
-    dst[c] = s >= 0 ? src[s] : 0.0;
+    const double v = s >= 0 ? src[s] : 0.0;
+    odd = odd || !(v >= 0.0) || v != floor(v);
+    dst[c] = v;
   }
+  if (__any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) *not_counts = 1;
 }
 
 // mean count per gene (the IRLS starting value mu0 = (y + ybar) / 2)
@@ -200,17 +206,18 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   if (freeze_dense && L.ngroups < 2) return 1;
   const int n = h->n, p = h->p, kx = L.kx, kde = L.kde;
   cudaStream_t st = h->st;
-  const size_t smem = glm_irls_smem_bytes(kde, kx, lasso);
+  const size_t smem = glm_irls_smem_bytes(kde, kx, L.ngroups, lasso);
   if (smem > 226 * 1024) return 1;   // (227 KB of dynamic shared memory per CTA on sm_100a)
   const int ldxd = (kde + 1) | 1;
   // ---- counts in the sorted padded cell order (cached across the fits of a batch) ----
   const long ldp = L.npad;
   if (h->perm_host != L.perm || !h->Yp.ptr || h->Yp_src != h->Yt) {
-    if (h->Yp.alloc((size_t)p * ldp) || h->perm_dev.alloc(L.npad)) return -1;
+    if (h->Yp.alloc((size_t)p * ldp) || h->perm_dev.alloc(L.npad) || h->not_counts.alloc(1)) return -1;
     CA_CUDA(cudaMemcpyAsync(h->perm_dev.ptr, L.perm.data(), sizeof(int) * L.npad, cudaMemcpyHostToDevice, st));
+    CA_CUDA(cudaMemsetAsync(h->not_counts.ptr, 0, sizeof(int), st));
     ProfScope prof(PROF_PREP, st);
     k_glm_permute_counts<<<dim3((L.npad + 1023) / 1024, p), 256, 0, st>>>(h->Yt, h->ldn, p, h->perm_dev.ptr, L.npad,
-                                                                           h->Yp.ptr, ldp);
+                                                                           h->Yp.ptr, ldp, h->not_counts.ptr);
     CA_LAUNCH_CHECK();
     CA_CUDA(cudaStreamSynchronize(st));  // L.perm (host) is read by the copy above
     h->perm_host = L.perm;
@@ -244,7 +251,7 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   }
   const int n_oct = ((genelist_dev ? n_list : p) + 7) / 8;
   if (n_oct <= 0) return 0;
-  const int grid = std::min(n_oct, sm_count);
+  const int grid = std::min(n_oct, 2 * sm_count);   // two CTAs per SM when the shared memory allows (the kernel is persistent either way)
   const int nb = (kde + 7) / 8;
   if (h->irls_scratch.alloc((size_t)grid * L.nseg_tot * (nb + 1) * 64)) return -1;
   CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int) * 2, st));
@@ -283,6 +290,7 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   P.genelist = genelist_dev;
   P.n_list = n_list;
   P.counter = h->counter.ptr;
+  P.not_counts = h->not_counts.ptr;
   P.scratch = h->irls_scratch.ptr;
   P.beta = h->beta.ptr;
   P.dev = h->dev.ptr;

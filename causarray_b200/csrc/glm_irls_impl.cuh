@@ -40,8 +40,12 @@
 
 namespace ca {
 
-constexpr int IRLS_WARPS = 8;
-constexpr int IRLS_THREADS = IRLS_WARPS * 32;
+constexpr int IRLS_WARPS = 4;      // cell ranges of an octet (each with its own staging); NH warps work on a range
+constexpr int IRLS_NH = 2;         // warps per cell range: 8 warps per CTA, two CTAs (octets) per SM
+constexpr int IRLS_LOGY = 256;     // counts below this read log y from shared memory (log y is the same in every
+                                   // iteration; the table holds the values fm_log would return, bit for bit)
+constexpr int IRLS_SOLVERS = 8;
+static_assert(IRLS_WARPS <= 4, "group_sync() names four barriers");    // warps with solve work space (one gene each)
 constexpr int IRLS_CHUNK = 32;    // cells per staged chunk (per warp): four pair-steps of 8 cells
 constexpr int IRLS_MAX_KDE = 16;
 constexpr int IRLS_MAX_SEG = 96;
@@ -80,6 +84,7 @@ struct GlmIrls {
   const int* genelist;                 // genes to fit (nullptr: all p genes)
   int n_list;
   int* counter;                        // octet dispenser (zeroed by the host)
+  const int* not_counts;               // 0: every entry of Yp is a non-negative integer (log y from a table)
   double* scratch;                     // per CTA: nseg_tot x (NB + 1) x 64 doubles
   double* beta;                        // p x kx (in: warm start; out)
   double* dev;                         // p
@@ -101,28 +106,44 @@ struct IrlsShape {
   __host__ __device__ static constexpr int tw(int b, int j) { return b * KDE - 8 * (b * (b - 1) / 2) + (j - 8 * b); }
 };
 
-inline size_t glm_irls_smem_bytes(int kde, int kx, bool lasso) {
+// Work space of one solving warp: the lasso refit factorises the full kx x kx system (+ a copy), the
+// unpenalised fit only the dense block (arrow structure) next to the per-group couplings.
+__host__ __device__ inline size_t glm_irls_work_doubles(int kx, int kde, int ngroups, bool lasso) {
+  return lasso ? glm_solve_work_doubles(kx, true)
+               : glm_solve_work_doubles(kde, false) + (size_t)(ngroups > 1 ? ngroups - 1 : 0) * (kde + 1);
+}
+
+inline size_t glm_irls_smem_bytes(int kde, int kx, int ngroups, bool lasso) {
   const int nb = (kde + 7) / 8;
   const int ntw = nb * kde - 8 * (nb * (nb - 1) / 2);
   const int nt = ntw + nb;
   const int ldxd = (kde + 1) | 1;
   size_t d = 0;
-  d += (size_t)IRLS_WARPS * 2 * (((IRLS_CHUNK * ldxd + 8) + 1) & ~1);  // staging (+ slack for the masked row-block reads)
+  d += (size_t)IRLS_WARPS * 2 * ((((IRLS_CHUNK * ldxd + 8) + 1) & ~1) + 8 * IRLS_CHUNK);  // staging: design rows + counts
   d += (size_t)IRLS_WARPS * 2 * IRLS_CHUNK * 9;               // weights / weighted responses handed from the evaluation to the DMMA phase
   d += (size_t)8 * (kde + 4);                                 // dense coefficients, nu, ybar, flags of the octet
   d += (size_t)nt * 64;                                       // dense totals
   d += (size_t)IRLS_WARPS * 8;                                // deviance partials
   d += (size_t)8 * kx;                                        // coefficients of the octet
-  d += (size_t)IRLS_WARPS * glm_solve_work_doubles(kx, lasso);
+  d += (size_t)IRLS_SOLVERS * glm_irls_work_doubles(kx, kde, ngroups, lasso);
   d += FM_TABLE_DOUBLES;
+  d += IRLS_LOGY;                                             // log 1, log 1, log 2 .. log(IRLS_LOGY - 1)
   return d * sizeof(double);
 }
 
-template <int KDE, bool NBF>
-__global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_constant__ GlmIrls P) {
+// NH warps share a cell range: each evaluates 8 / NH genes of the chunk's 32 cells and owns
+// ceil(NT / NH) of the accumulator tiles (NH = 1: 32 accumulator doubles per lane and 228 registers, one
+// CTA of 8 warps per SM; NH = 2: 16 warps per SM at <= 128 registers -- twice the warps to hide the
+// fixed-latency stalls that left the FP64 pipe 52 % idle).
+template <int KDE, bool NBF, int NH>
+__global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __grid_constant__ GlmIrls P) {
   using S = IrlsShape<KDE>;
   constexpr int NB = S::NB, U = S::U, NTW = S::NTW, NT = S::NT, FLT = S::FLT, LDXD = S::LDXD;
-  constexpr int STG = ((IRLS_CHUNK * LDXD + 8) + 1) & ~1;   // even: every stage starts 16-byte aligned (bulk copies)
+  constexpr int IRLS_THREADS = IRLS_WARPS * 32 * NH;
+  constexpr int GH = 8 / NH;                // genes evaluated per warp
+  constexpr int NTH = (NT + NH - 1) / NH;   // accumulator tiles per warp: tile t belongs to warp t / NTH of the range
+  constexpr int XSTG = ((IRLS_CHUNK * LDXD + 8) + 1) & ~1;  // design rows of a chunk (+ slack for the masked row-block reads); even
+  constexpr int STG = XSTG + 8 * IRLS_CHUNK;                // + the chunk's counts of the 8 genes; every stage starts 16-byte aligned
   constexpr int WLD = 9;                                    // row stride of the weight hand-off buffers (odd)
   extern __shared__ __align__(16) double smem[];
   const int kx = P.kx;
@@ -132,36 +153,53 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
   double* Dp = Tt + NT * 64;                               // IRLS_WARPS * 8
   double* betas = Dp + IRLS_WARPS * 8;                     // 8 * kx
   double* work_all = betas + 8 * kx;
-  const size_t work_d = glm_solve_work_doubles(kx, lasso);
-  double* wbuf_all = work_all + IRLS_WARPS * work_d;       // IRLS_WARPS * 2 * IRLS_CHUNK * WLD
+  const size_t work_d = glm_irls_work_doubles(kx, KDE, P.ngroups, lasso);
+  double* wbuf_all = work_all + IRLS_SOLVERS * work_d;       // IRLS_WARPS * 2 * IRLS_CHUNK * WLD
   double* bdense = wbuf_all + IRLS_WARPS * 2 * IRLS_CHUNK * WLD;  // 8 * KDE
   double* s_nu = bdense + 8 * KDE;                         // 8
   double* s_ybar = s_nu + 8;                               // 8
   double* s_flag = s_ybar + 8;                             // 8: bit 0 Poisson branch, bit 1 observed-information weights
-  double* s_tab = s_flag + 16;
+  double* s_logy = s_flag + 16;                            // IRLS_LOGY
+  double* s_tab = s_logy + IRLS_LOGY;
   __shared__ __align__(8) unsigned long long bars[IRLS_WARPS * 2];
   __shared__ int s_octet, s_nrun, s_anynewton;
   __shared__ int s_gene[8], s_status[8], s_niter[8];
   __shared__ double s_devprev[8], s_dev[8], s_step[8];
   __shared__ signed char s_gcol[64];
+  __shared__ const double* s_yrow[8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cr = warp / NH, half = warp - cr * NH;   // cell range, position inside the range's warp group
   const int lr = lane >> 2, lc = lane & 3;
   const FmTables FT = fm_load_tables(s_tab, P.fm_tables);
-  double* xs = xs_all + warp * 2 * STG;
-  unsigned long long* bar = bars + warp * 2;
-  if (lane == 0) {
+  double* xs = xs_all + cr * 2 * STG;
+  unsigned long long* bar = bars + cr * 2;
+  auto group_sync = [&]() {
+    if (NH == 1)
+      __syncwarp();
+    else
+      switch (cr) {   // immediate barrier numbers: ptxas then reserves IRLS_WARPS + 1 barriers, not all 16
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(32 * NH) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(32 * NH) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(32 * NH) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(32 * NH) : "memory"); break;
+      }
+  };
+  if (lane == 0 && half == 0) {
     mbar_init(bar + 0, 1);
     mbar_init(bar + 1, 1);
   }
   for (int i = lane; i < 2 * STG; i += 32) xs[i] = 0.0;
   if (tid < 64) s_gcol[tid] = P.gcol[tid];
   if (tid == 0) mbar_fence_init();
+  __syncthreads();   // (the exp / log tables are in place)
+  for (int i = tid; i < IRLS_LOGY; i += IRLS_THREADS) s_logy[i] = fm_log(i > 0 ? (double)i : 1.0, FT.log_t);
+  const bool ytab = *P.not_counts == 0;
   __syncthreads();
   fence_proxy_async();
   unsigned fphase = 0;
 
-  const int c_lo = P.chunk_lo[warp], c_hi = P.chunk_lo[warp + 1];
+  const int c_lo = P.chunk_lo[cr], c_hi = P.chunk_lo[cr + 1];
   const int n_oct = ((P.genelist ? P.n_list : P.p) + 7) >> 3;
   double* scratch = P.scratch + (size_t)blockIdx.x * P.nseg_tot * (FLT * 64);
   constexpr double LOG_EPS = -36.04365338911715;  // log(2^-52): statsmodels clips y / mu at FLOAT_EPS
@@ -203,12 +241,12 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
       s_flag[tid] = pois ? 1.0 : 0.0;
     }
     __syncthreads();
-    const double* ybase = P.Yp + (size_t)(c_lo < c_hi ? c_lo : 0) * IRLS_CHUNK + lane;
-    long yoff[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-      yoff[g] = (long)(s_gene[g] >= 0 ? s_gene[g] : (s_gene[0] >= 0 ? s_gene[0] : 0)) * P.ldp;
-    double* wbuf = wbuf_all + warp * 2 * IRLS_CHUNK * WLD;   // w, then w z: [cell of the chunk][gene], row stride WLD
+    if (tid < 8) {
+      const int sg = s_gene[tid];
+      s_yrow[tid] = P.Yp + (size_t)(sg >= 0 ? sg : (s_gene[0] >= 0 ? s_gene[0] : 0)) * P.ldp;
+    }
+    __syncthreads();
+    double* wbuf = wbuf_all + cr * 2 * IRLS_CHUNK * WLD;   // w, then w z: [cell of the chunk][gene], row stride WLD
     double* wzbuf = wbuf + IRLS_CHUNK * WLD;
 
     for (int it = 1;; ++it) {
@@ -230,48 +268,55 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
       __syncthreads();
       const bool any_newton = s_anynewton != 0;
       // ---------------- pass over this warp's chunks ----------------
-      double acc[NT][2];
+      double acc[NTH][2];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
-      double dacc[8];
+      for (int t = 0; t < NTH; ++t) acc[t][0] = acc[t][1] = 0.0;
+      double dacc[GH];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) dacc[g] = 0.0;
-      int gcur = -1, seg = P.seg_ptr[warp];
+      for (int g = 0; g < GH; ++g) dacc[g] = 0.0;
+      int gcur = -1, seg = P.seg_ptr[cr];
       auto issue = [&](int c, int stage) {
         const unsigned bytes = (unsigned)(IRLS_CHUNK * LDXD * sizeof(double));
-        mbar_expect_tx(bar + stage, bytes);
+        mbar_expect_tx(bar + stage, bytes + (unsigned)(8 * IRLS_CHUNK * sizeof(double)));
         bulk_g2s(xs + stage * STG, P.Xd + (size_t)c * IRLS_CHUNK * LDXD, bytes, bar + stage);
+        // the counts of the chunk: 256 contiguous bytes per gene (registers held them before; the prefetched
+        // set was spilled and the spill store waited for the loads, 4 % of the kernel)
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          bulk_g2s(xs + stage * STG + XSTG + g * IRLS_CHUNK, s_yrow[g] + (size_t)c * IRLS_CHUNK,
+                   (unsigned)(IRLS_CHUNK * sizeof(double)), bar + stage);
       };
-      auto flush = [&]() {
+      auto flush = [&](auto half_c) {
+        constexpr int H = decltype(half_c)::value;
         double* dst = scratch + (size_t)seg * (FLT * 64) + lr * 8 + 2 * lc;
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          *reinterpret_cast<double2*>(dst + b * 64) = make_double2(acc[S::tw(b, U)][0], acc[S::tw(b, U)][1]);
-          acc[S::tw(b, U)][0] = acc[S::tw(b, U)][1] = 0.0;
+          if (S::tw(b, U) / NTH == H) {
+            *reinterpret_cast<double2*>(dst + b * 64) =
+                make_double2(acc[S::tw(b, U) % NTH][0], acc[S::tw(b, U) % NTH][1]);
+            acc[S::tw(b, U) % NTH][0] = acc[S::tw(b, U) % NTH][1] = 0.0;
+          }
         }
-        *reinterpret_cast<double2*>(dst + NB * 64) = make_double2(acc[NTW + NB - 1][0], acc[NTW + NB - 1][1]);
-        acc[NTW + NB - 1][0] = acc[NTW + NB - 1][1] = 0.0;
+        if ((NTW + NB - 1) / NTH == H) {
+          *reinterpret_cast<double2*>(dst + NB * 64) =
+              make_double2(acc[(NTW + NB - 1) % NTH][0], acc[(NTW + NB - 1) % NTH][1]);
+          acc[(NTW + NB - 1) % NTH][0] = acc[(NTW + NB - 1) % NTH][1] = 0.0;
+        }
         ++seg;
       };
-      if (lane == 0) {
+      if (lane == 0 && half == 0) {
         if (c_lo < c_hi) issue(c_lo, 0);
         if (c_lo + 1 < c_hi) issue(c_lo + 1, 1);
       }
       // counts of this lane's cell of the chunk, one per gene (256 contiguous bytes per gene and load)
-      double ycur[8], ynext[8];
-      if (c_lo < c_hi) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) ycur[g] = ybase[yoff[g]];
-      }
       for (int c = c_lo; c < c_hi; ++c) {
         const int stage = (c - c_lo) & 1;
-        if (c + 1 < c_hi) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) ynext[g] = ybase[yoff[g] + (size_t)(c + 1 - c_lo) * IRLS_CHUNK];
-        }
         mbar_wait(bar + stage, (fphase >> stage) & 1u);
         fphase ^= 1u << stage;
         const double* xc = xs + stage * STG;
+        double ycur[GH];
+#pragma unroll
+        for (int g = 0; g < GH; ++g) ycur[g] = xc[XSTG + (half * GH + g) * IRLS_CHUNK + lane];
         // ===== evaluation: lane = cell of the chunk, the 8 genes are 8 independent chains =====
         // (one straight-line body per mode -- first pass / regular / observed-information weights --
         // so that ptxas interleaves the eight chains: with the mode tests inside the gene loop every
@@ -286,62 +331,111 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
           const int grp = __ldg(P.gpair + c * 4 + (lane >> 3));
           const int gc = grp > 0 ? (int)s_gcol[grp] : 0;
           const double gsel = grp > 0 ? 1.0 : 0.0;
+          // log y: the same in every iteration -- from the table for counts below IRLS_LOGY, computed (whole
+          // warp, rare) otherwise; kept out of the main body, which must stay ONE basic block
+          double lyv[GH];
+          {
+            bool slow = !ytab;
+#pragma unroll
+            for (int gl = 0; gl < GH; ++gl) {
+              const double y = ycur[gl];
+              slow = slow || !(y < (double)IRLS_LOGY);
+              int yi = __double2int_rz(y);
+              yi = yi < IRLS_LOGY - 1 ? yi : IRLS_LOGY - 1;
+              lyv[gl] = s_logy[yi > 0 ? yi : 0];
+            }
+            if (__any_sync(0xffffffffu, slow)) {
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) lyv[gl] = fm_log(ycur[gl] > 0.0 ? ycur[gl] : 1.0, FT.log_t);
+            }
+          }
+          // The stores of w / w z are deferred to the end of the body: a shared-memory store between two genes
+          // keeps ptxas from hoisting the next gene's table / coefficient loads above it, and the GH chains then
+          // run one after the other (profile of the first 16-warp version: every dependent DFMA stalled).
           auto eval8 = [&](auto first_c, auto newton_c) {
             constexpr bool FIRST = decltype(first_c)::value;
             constexpr bool NEWTON = decltype(newton_c)::value;
+            // every statement runs across the GH genes (fm_*_n): the GH dependent chains are interleaved in
+            // source order, which is the order ptxas keeps
+            double eta[GH], ec[GH], mu[GH], nu[GH];
+            bool pois[GH], nwt[GH];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const double y = ycur[g];
-              const double nu = s_nu[g];
+            for (int gl = 0; gl < GH; ++gl) {
+              const int g = half * GH + gl;
+              nu[gl] = s_nu[g];
               const int fl = (int)s_flag[g];
-              const bool pois = (fl & 1) != 0;
-              double eta, ec, mu;
-              if (FIRST) {
-                mu = 0.5 * (y + s_ybar[g]);
-                eta = fm_log(mu, FT.log_t);
-                ec = eta;
-              } else {
-                const double* bg = bdense + g * KDE;
-                double ea = fma(gsel, betas[g * kx + gc], off), eb = 0.0;
+              pois[gl] = (fl & 1) != 0;
+              nwt[gl] = (fl & 2) != 0;
+            }
+            if (FIRST) {
 #pragma unroll
-                for (int i = 0; i + 1 < KDE; i += 2) {
-                  ea = fma(x[i], bg[i], ea);
-                  eb = fma(x[i + 1], bg[i + 1], eb);
+              for (int gl = 0; gl < GH; ++gl) mu[gl] = 0.5 * (ycur[gl] + s_ybar[half * GH + gl]);
+              fm_log_n<GH>(mu, eta, FT.log_t);
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) ec[gl] = eta[gl];
+            } else {
+              double ea[GH], eb[GH];
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) {
+                ea[gl] = fma(gsel, betas[(half * GH + gl) * kx + gc], off);
+                eb[gl] = 0.0;
+              }
+#pragma unroll
+              for (int i = 0; i + 1 < KDE; i += 2) {
+#pragma unroll
+                for (int gl = 0; gl < GH; ++gl) {
+                  const double* bg = bdense + (half * GH + gl) * KDE;
+                  ea[gl] = fma(x[i], bg[i], ea[gl]);
+                  eb[gl] = fma(x[i + 1], bg[i + 1], eb[gl]);
                 }
-                if (KDE & 1) ea = fma(x[KDE - 1], bg[KDE - 1], ea);
-                eta = ea + eb;
-                ec = eta < 700.0 ? eta : 700.0;
-                ec = ec > -700.0 ? ec : -700.0;
-                mu = fm_exp(ec, FT.exp_t);
               }
-              // unit deviance / 2 : y log(max(y / mu, eps)) - (y - mu)                          (Poisson)
-              //                     y log(max(y / mu, eps)) - (y + nu) log((y + nu) / (mu + nu)) (NB)
-              const double ly = fm_log(y > 0.0 ? y : 1.0, FT.log_t);
-              double lrat = ly - ec;
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) {
+                if (KDE & 1) ea[gl] = fma(x[KDE - 1], bdense[(half * GH + gl) * KDE + KDE - 1], ea[gl]);
+                eta[gl] = ea[gl] + eb[gl];
+                double e = eta[gl] < 700.0 ? eta[gl] : 700.0;
+                ec[gl] = e > -700.0 ? e : -700.0;
+              }
+              fm_exp_n<GH>(ec, mu, FT.exp_t);
+            }
+            // unit deviance / 2 : y log(max(y / mu, eps)) - (y - mu)                          (Poisson)
+            //                     y log(max(y / mu, eps)) - (y + nu) log((y + nu) / (mu + nu)) (NB)
+            double rc[GH], lt[GH];
+            if (NBF) {
+              double den[GH], arg[GH];
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) den[gl] = nu[gl] + mu[gl];
+              fm_rcp_n<GH>(den, rc);
+#pragma unroll
+              for (int gl = 0; gl < GH; ++gl) arg[gl] = (ycur[gl] + nu[gl]) * rc[gl];
+              fm_log_n<GH>(arg, lt, FT.log_t);
+            }
+#pragma unroll
+            for (int gl = 0; gl < GH; ++gl) {
+              const double y = ycur[gl];
+              double lrat = lyv[gl] - ec[gl];
               lrat = lrat > LOG_EPS ? lrat : LOG_EPS;
-              double d2 = y - mu;
-              double wgt = mu;
-              double rc = 0.0;
+              double d2 = y - mu[gl];
+              double wgt = mu[gl];
+              // w z = w (eta - off) + (y - mu) w / mu with w / mu = nu / (nu + mu) resp. 1: no reciprocal of mu
+              double sfac = 1.0;
               if (NBF) {
-                rc = fm_rcp(nu + mu);
-                const double lt = fm_log((y + nu) * rc, FT.log_t);
-                d2 = pois ? d2 : (y + nu) * lt;
-                wgt = pois ? mu : mu * nu * rc;
+                d2 = pois[gl] ? d2 : (y + nu[gl]) * lt[gl];
+                wgt = pois[gl] ? mu[gl] : mu[gl] * nu[gl] * rc[gl];
+                sfac = pois[gl] ? 1.0 : nu[gl] * rc[gl];
               }
-              dacc[g] = fma(vld, fma(y, lrat, -d2), dacc[g]);
-              const double z = (eta - off) + (y - mu) * fm_rcp(mu);
-              double w = wgt, wz = wgt * z;
+              dacc[gl] = fma(vld, fma(y, lrat, -d2), dacc[gl]);
+              double w = wgt, wz = fma(wgt, eta[gl] - off, (y - mu[gl]) * sfac);
               if (NBF && NEWTON) {
                 // observed information of the NB2 log-likelihood: nu mu (nu + y) / (nu + mu)^2;
                 // rhs = w (eta - off) + score (same minimiser, quadratic tail; lasso refit only)
-                const double wn = mu * nu * rc * ((nu + y) * rc);
-                const double wzn = fma(wn, eta - off, (y - mu) * (nu * rc));
-                const bool nw = (fl & 2) != 0;
-                w = nw ? wn : w;
-                wz = nw ? wzn : wz;
+                const double wn = mu[gl] * nu[gl] * rc[gl] * ((nu[gl] + y) * rc[gl]);
+                const double wzn = fma(wn, eta[gl] - off, (y - mu[gl]) * (nu[gl] * rc[gl]));
+                w = nwt[gl] ? wn : w;
+                wz = nwt[gl] ? wzn : wz;
               }
-              wbuf[lane * WLD + g] = w;
-              wzbuf[lane * WLD + g] = wz;
+              wbuf[lane * WLD + half * GH + gl] = w;
+              wzbuf[lane * WLD + half * GH + gl] = wz;
             }
           };
           if (first)
@@ -351,62 +445,77 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
           else
             eval8(std::false_type{}, std::false_type{});
         }
-        __syncwarp();
+        group_sync();
         // ===== Gram strips and right-hand side on the FP64 tensor cores: lane = (cell lc of a step, gene lr) =====
+        auto gram = [&](auto half_c) {
+          constexpr int H = decltype(half_c)::value;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const int g = __ldg(P.gpair + c * 4 + q);
-          if (g != gcur) {
-            if (gcur >= 0) flush();
-            gcur = g;
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cell = (2 * q + h) * 4 + lc;
-            const double* xr = xc + cell * LDXD;
-            const double w = wbuf[cell * WLD + lr], wz = wzbuf[cell * WLD + lr];
-            double xa[NB];
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-              const double t = xr[8 * b + lr];
-              xa[b] = (8 * b + lr < KDE) ? t : 0.0;
+          for (int q = 0; q < 4; ++q) {
+            const int g = __ldg(P.gpair + c * 4 + q);
+            if (g != gcur) {
+              if (gcur >= 0) flush(half_c);
+              gcur = g;
             }
 #pragma unroll
-            for (int j = 0; j < KDE; ++j) {
-              const double bw = w * xr[j];
+            for (int h = 0; h < 2; ++h) {
+              const int cell = (2 * q + h) * 4 + lc;
+              const double* xr = xc + cell * LDXD;
+              const double w = wbuf[cell * WLD + lr], wz = wzbuf[cell * WLD + lr];
+              double xa[NB];
+#pragma unroll
+              for (int b = 0; b < NB; ++b) {
+                const double t = xr[8 * b + lr];
+                xa[b] = (8 * b + lr < KDE) ? t : 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < KDE; ++j) {
+                const double bw = w * xr[j];
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+                  if (j >= 8 * b && S::tw(b, j) / NTH == H)
+                    dmma884(acc[S::tw(b, j) % NTH][0], acc[S::tw(b, j) % NTH][1], xa[b], bw);
+              }
 #pragma unroll
               for (int b = 0; b < NB; ++b)
-                if (j >= 8 * b) dmma884(acc[S::tw(b, j)][0], acc[S::tw(b, j)][1], xa[b], bw);
+                if ((NTW + b) / NTH == H) dmma884(acc[(NTW + b) % NTH][0], acc[(NTW + b) % NTH][1], xa[b], wz);
             }
-#pragma unroll
-            for (int b = 0; b < NB; ++b) dmma884(acc[NTW + b][0], acc[NTW + b][1], xa[b], wz);
           }
-        }
-        __syncwarp();
-        if (lane == 0 && c + 2 < c_hi) issue(c + 2, stage);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) ycur[g] = ynext[g];
+        };
+        if (NH == 1 || half == 0)
+          gram(std::integral_constant<int, 0>{});
+        else
+          gram(std::integral_constant<int, NH - 1>{});
+        group_sync();
+        if (lane == 0 && half == 0 && c + 2 < c_hi) issue(c + 2, stage);
       }
-      if (gcur >= 0) flush();
-      // ---------------- combine the warps (fixed order) ----------------
+      if (gcur >= 0) {
+        if (NH == 1 || half == 0)
+          flush(std::integral_constant<int, 0>{});
+        else
+          flush(std::integral_constant<int, NH - 1>{});
+      }
+      // ---------------- combine the cell ranges (fixed order) ----------------
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < GH; ++g) {
         const double v = warp_sum(dacc[g]);
-        if (lane == g) Dp[warp * 8 + g] = v;
+        if (lane == g) Dp[cr * 8 + half * GH + g] = v;
       }
       for (int w = 0; w < IRLS_WARPS; ++w) {
-        if (warp == w) {
+        if (cr == w) {
           double* dst = Tt + lr * 8 + 2 * lc;
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            double2* pp = reinterpret_cast<double2*>(dst + t * 64);
-            if (w == 0) {
-              *pp = make_double2(acc[t][0], acc[t][1]);
-            } else {
-              double2 v = *pp;
-              v.x += acc[t][0];
-              v.y += acc[t][1];
-              *pp = v;
+          for (int t = 0; t < NTH; ++t) {
+            const int tg = half * NTH + t;
+            if (tg < NT) {
+              double2* pp = reinterpret_cast<double2*>(dst + tg * 64);
+              if (w == 0) {
+                *pp = make_double2(acc[t][0], acc[t][1]);
+              } else {
+                double2 v = *pp;
+                v.x += acc[t][0];
+                v.y += acc[t][1];
+                *pp = v;
+              }
             }
           }
         }
@@ -415,8 +524,7 @@ __global__ void __launch_bounds__(IRLS_THREADS, 1) k_glm_irls(const __grid_const
       if (tid == 0) s_nrun = 0;
       __syncthreads();
       // ---------------- warp g: convergence test and update of gene g ----------------
-      {
-        const int g = warp;
+      for (int g = warp; g < 8; g += IRLS_WARPS * NH) {
         const int gene = s_gene[g];
         bool run = gene >= 0 && s_status[g] == 0;
         if (run) {

@@ -13,12 +13,13 @@ template <int KDE>
 int launch_glm_irls_kde(const GlmIrls& P, int grid, size_t smem, cudaStream_t st) {
   const bool nb = P.family == CA_FAMILY_NB && P.nu != nullptr;
   ProfScope prof(PROF_GLM_PASS, st);
+  constexpr int NTHR = IRLS_WARPS * 32 * IRLS_NH;
   if (nb) {
-    CA_CUDA(cudaFuncSetAttribute(k_glm_irls<KDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_glm_irls<KDE, true><<<grid, IRLS_THREADS, smem, st>>>(P);
+    CA_CUDA(cudaFuncSetAttribute(k_glm_irls<KDE, true, IRLS_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_glm_irls<KDE, true, IRLS_NH><<<grid, NTHR, smem, st>>>(P);
   } else {
-    CA_CUDA(cudaFuncSetAttribute(k_glm_irls<KDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_glm_irls<KDE, false><<<grid, IRLS_THREADS, smem, st>>>(P);
+    CA_CUDA(cudaFuncSetAttribute(k_glm_irls<KDE, false, IRLS_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_glm_irls<KDE, false, IRLS_NH><<<grid, NTHR, smem, st>>>(P);
   }
   CA_LAUNCH_CHECK();
   return 0;

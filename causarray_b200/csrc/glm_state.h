@@ -29,7 +29,7 @@ struct ca_glm {
   const double* Yraw = nullptr;  // n x p cell-major raw counts
   const double* Yt = nullptr;    // p x ldn gene-major raw counts
   ca::DevBuf<double> X, beta, ybar, cst, dev, dev_prev, step, part, mu_t, offset, nu, ridge, resid, resid_t;
-  ca::DevBuf<int> status, n_iter, counter, genelist;
+  ca::DevBuf<int> status, n_iter, counter, genelist, not_counts;
   // persistent IRLS path: counts in group-sorted padded cell order (cached), dense design rows
   ca::DevBuf<double> Yp, Xd, irls_scratch;
   ca::DevBuf<int> perm_dev, gpair;

@@ -28,7 +28,7 @@ static cudaEvent_t get_event() {
 
 static const char* class_name(int cls) {
   static const char* names[PROF_NCLASS] = {"rowpass_grad", "rowpass_ell", "search", "glm_pass", "glm_solve", "aipw",
-                                           "prep"};
+                                           "prep", "search_onehot"};
   return (cls >= 0 && cls < PROF_NCLASS) ? names[cls] : "";
 }
 

@@ -13,6 +13,7 @@ enum ProfClass {
   PROF_GLM_SOLVE,
   PROF_AIPW,
   PROF_PREP,   // upload-side kernels: transpose / normalise / constant sums / size factors
+  PROF_SEARCH_ONEHOT,   // stage-2 gene line search over the treated cells only (search_onehot.cu)
   PROF_NCLASS
 };
 

@@ -15,6 +15,7 @@
 // the search (rowpass_impl.cuh writes it next to the gradient), the counts from a group-sorted copy made
 // once per batch.
 #include <math.h>
+#include <type_traits>
 
 #include "../../include/causarray_b200.h"
 #include "common.cuh"
@@ -65,26 +66,31 @@ struct S2Args {
 };
 
 // log-likelihood of one entry at theta0 + delta (m0 = e^{clamp(theta0)}, E = e^{delta})
-template <bool NB>
+// POIS is uniform over a gene's warp, so the two forms are two code paths, not selects.  Comparisons are plain
+// FP64 compares here: the kernel is bound by instruction issue (55 % of the slots, FP64 pipe 28 %), and the
+// integer-pipe comparisons of fastmath.cuh cost two ISETPs each (a third of this kernel's instructions were
+// compares and selects).
+template <bool POIS>
 __device__ __forceinline__ double s2_entry(const FmTables& FT, const NbClip& clip, double y, double th0, double m0,
-                                           double dl, double E, double nu, double inu, double lnu, bool pois) {
+                                           double dl, double E, double nu, double inu, double lnu) {
   const double xr = th0 + dl;
-  const bool below = fm_lt_pos(xr, 100.0);
-  const double xi = below ? xr : 100.0;
-  const double m = below ? m0 * E : 2.6881171418161356e43;   // e^100: the reference clips theta from above
-  if (!NB) return fma(y, xi, -m);
-  double uc = m * inu;
-  double lu = xi - lnu;
-  const bool lo = fm_lt_pos(uc, clip.u_lo), hi = fm_gt_pos(uc, clip.u_hi);
+  if (POIS) {
+    const bool below = xr < 100.0;
+    const double xi = below ? xr : 100.0;
+    const double m = below ? m0 * E : 2.6881171418161356e43;   // e^100: the reference clips theta from above
+    return fma(y, xi, -m);
+  }
+  // NB: a theta clipped at 100 has u = e^100 / nu far above u_hi (nu <= the Poisson threshold), and so has the
+  // unclipped product m0 E (or its overflow to +inf): the upper clip of u already gives the reference's value
+  double uc = (m0 * E) * inu;
+  double lu = xr - lnu;
+  const bool lo = uc < clip.u_lo, hi = uc > clip.u_hi;
   uc = lo ? clip.u_lo : uc;
   lu = lo ? clip.lu_lo : lu;
   uc = hi ? clip.u_hi : uc;
   lu = hi ? clip.lu_hi : lu;
   const double L = fm_log(1.0 + uc, FT.log_t);
-  const double a = pois ? xi : lu;
-  const double b = pois ? m : L;
-  const double c = pois ? 1.0 : y + nu;
-  return fma(-c, b, y * a);
+  return fma(-(y + nu), L, y * lu);
 }
 
 template <bool NB>
@@ -122,7 +128,8 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
   // evaluates nc candidates with steps tc[0..nc): returns their treated-cell log-likelihood sums
   // (all lanes hold them) and their penalties
   // (base: candidate 0 is the CURRENT point, delta = 0 -- not the prox of it)
-  auto eval = [&](const double* tc, int nc, bool base, double* ell_out, double* pen_out) {
+  auto eval = [&](auto pois_c, const double* tc, int nc, bool base, double* ell_out, double* pen_out) {
+    constexpr bool POIS = decltype(pois_c)::value;
 #pragma unroll
     for (int k = 0; k < S2_NC; ++k) {
       if (k < nc) {
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
         const double m0 = fm_exp(xe, FT.exp_t);
 #pragma unroll
         for (int k = 0; k < S2_NC; ++k)
-          if (k < nc) acc[k] += s2_entry<NB>(FT, clip, y4[u], th0, m0, dl[k][g4[u]], Ee[k][g4[u]], nu, inu, lnu, pois);
+          if (k < nc) acc[k] += s2_entry<POIS>(FT, clip, y4[u], th0, m0, dl[k][g4[u]], Ee[k][g4[u]], nu, inu, lnu);
       }
     }
 #pragma unroll
@@ -175,7 +182,13 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
   // ---- pass 1: t = 0 (baseline of the treated cells) and the first candidate t = alpha ----
   tc[0] = 0.0;
   tc[1] = alpha;
-  eval(tc, 2, true, el, pn);
+  auto eval_any = [&](const double* tcs, int nc, bool base, double* ell_out, double* pen_out) {
+    if (!NB || pois)
+      eval(std::true_type{}, tcs, nc, base, ell_out, pen_out);
+    else
+      eval(std::false_type{}, tcs, nc, base, ell_out, pen_out);
+  };
+  eval_any(tc, 2, true, el, pn);
   const double ell_ctrl = ell0 - el[0];
   int ne = 1;
   double t = alpha;
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
       if (tt < 1e-4) break;                // the reference stops at the first step below 1e-4
     }
     if (nc == 0) break;
-    eval(tc, nc, false, el, pn);
+    eval_any(tc, nc, false, el, pn);
     for (int k = 0; k < nc; ++k) {
       const double ell = ell_ctrl + el[k];
       const double f1 = -(ell + tys) / ncd + pn[k];
@@ -297,7 +310,7 @@ int launch_s2_onehot(const S2Launch& L, cudaStream_t st) {
   CA_REQUIRE(A.fm_tables, "fastmath tables unavailable");
   A.clip = nb_clip_constants();
   CA_REQUIRE(L.a >= 1 && L.a <= 32, "the one-hot search handles at most 32 treatment columns");
-  ProfScope prof(PROF_SEARCH, st);
+  ProfScope prof(PROF_SEARCH_ONEHOT, st);
   const int grid = (L.nrows + S2_WARPS - 1) / S2_WARPS;
   if (L.family == CA_FAMILY_NB)
     k_s2_onehot<true><<<grid, S2_WARPS * 32, 0, st>>>(A);
