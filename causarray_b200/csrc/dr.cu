@@ -21,6 +21,7 @@
 // shared memory in chunks (cp.async).  Treatments are processed in groups of
 // JT so that the 4*JT running sums stay in registers.
 #include <vector>
+#include <algorithm>
 #include <cmath>
 #include <chrono>
 #include <cstdlib>
@@ -44,8 +45,8 @@ struct DrArgs {
   const double* Yt;   // p x ldn gene-major raw counts
   long ldn;
   int n, p, kw, a;
-  const double* rec;  // n x ldr packed records for this treatment group
-  int ldr;            // kw + 2 + 3*JT, forced odd
+  const double* rec;  // n x ldr packed records for this treatment group, cells ordered controls first, then by treatment
+  int ldr;            // kw + 3 + 3*JT (the last field is the cell's index into Yt), forced odd
   int j0, nj;         // treatment group [j0, j0 + nj)
   const double* Bcov; // p x kw
   const double* Btrt; // p x a
@@ -62,21 +63,29 @@ struct DrArgs {
 
 // PASS 0: sums of psi0 / psi1.  PASS 1: centred second moments -> outputs.
 template <int PASS>
-__global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
+__global__ void __launch_bounds__(DR_THREADS, 2) k_aipw(DrArgs D) {
   extern __shared__ __align__(16) double smem[];
   double* Rs = smem;  // 2 * DR_CHUNK * ldr, then the exp / log tables
+  // pass 1: per-treatment constants of the warp's gene (1 / tau_0, 1 / tau_1, shift) live in shared memory --
+  // in registers they kept the kernel at 170 registers and one CTA per SM
+  __shared__ double s_c[DR_WARPS][3 * JT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const FmTables FT = fm_load_tables(smem + 2 * DR_CHUNK * D.ldr, D.fm_tables);
   const int gene = blockIdx.x * DR_WARPS + warp;
   const bool ok_gene = gene < D.p;
   const int ldr = D.ldr, kw = D.kw;
   const double* bcov = D.Bcov ? D.Bcov + (size_t)(ok_gene ? gene : 0) * kw : nullptr;
-  double ej[JT], t0[JT], t1[JT], shift[JT];  // in pass 1, t0 / t1 hold the RECIPROCALS of tau_0 / tau_1
+  double ej[JT];
+  double* t0 = s_c[warp];            // in pass 1, t0 / t1 hold the RECIPROCALS of tau_0 / tau_1
+  double* t1 = s_c[warp] + JT;
+  double* shift = s_c[warp] + 2 * JT;
 #pragma unroll
   for (int j = 0; j < JT; ++j) {
     ej[j] = 1.0;
-    t0[j] = t1[j] = 1.0;
-    shift[j] = 0.0;
+    if (lane == 0) {
+      t0[j] = t1[j] = 1.0;
+      shift[j] = 0.0;
+    }
     if (ok_gene && j < D.nj) {
       if (D.Btrt) ej[j] = exp(D.Btrt[(size_t)gene * D.a + D.j0 + j]);
       if (PASS == 1) {
@@ -87,12 +96,15 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
         const bool est = isfinite(m0) && isfinite(m1) && m0 > 0.0 && m1 > 0.0;
         const double tt0 = est ? fmax(m0, D.thres_diff) : 1.0;
         const double tt1 = est ? fmax(m1, D.thres_diff) : 1.0;
-        shift[j] = m1 / tt1 - m0 / tt0;
-        t0[j] = 1.0 / tt0;   // the per-cell influence values are scaled by multiplication
-        t1[j] = 1.0 / tt1;
+        if (lane == 0) {
+          shift[j] = m1 / tt1 - m0 / tt0;
+          t0[j] = 1.0 / tt0;   // the per-cell influence values are scaled by multiplication
+          t1[j] = 1.0 / tt1;
+        }
       }
     }
   }
+  __syncwarp();
   double acc0[JT], acc1[JT], acc2[JT], acc3[JT];
 #pragma unroll
   for (int j = 0; j < JT; ++j) acc0[j] = acc1[j] = acc2[j] = acc3[j] = 0.0;
@@ -118,7 +130,8 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
         const int cell = c * DR_CHUNK + blk + lane;
         if (cell >= D.n) continue;
         const double* rec = Rc + (blk + lane) * ldr;
-        const double y = yrow[cell];
+        const int ci = (int)rec[kw + 2 + 3 * JT];   // the cell's position in Yt (records are sorted by arm)
+        const double y = yrow[ci];
         const double isf = rec[kw + 1];
         double yh0_raw = 0.0;
         if (!D.Yhat) {
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(DR_THREADS) k_aipw(DrArgs D) {
           if (inc == 0.0) continue;
           double yh0, yh1;
           if (D.Yhat) {
-            const size_t base = (((size_t)cell * D.p + gene) * D.a + (D.j0 + j)) * 2;
+            const size_t base = (((size_t)ci * D.p + gene) * D.a + (D.j0 + j)) * 2;
             yh0 = fmin(D.Yhat[base], D.cap);
             yh1 = fmin(D.Yhat[base + 1], D.cap);
           } else {
@@ -227,7 +240,7 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
     fprintf(stderr, "[run_aipw] %-12s %.3f ms\n", what, std::chrono::duration<double, std::milli>(T1 - T0).count());
     T0 = T1;
   };
-  int ldr = kw + 2 + 3 * JT;
+  int ldr = kw + 3 + 3 * JT;
   if (ldr % 2 == 0) ldr += 1;
   // inclusion, arm counts (causarray/DR_learner.py:212-219, 426-427)
   std::vector<uint8_t> ctrl(n);
@@ -249,12 +262,34 @@ static int run_aipw(const double* Yt_dev, long ldn, int n, int p, int kw, int a,
     CA_CUDA(cudaMemcpyAsync(d_Btrt.ptr, Btrt, sizeof(double) * (size_t)p * a, cudaMemcpyHostToDevice, st));
   }
   lap("alloc+h2d");
+  // Cells are visited controls first, then by treatment: a warp's 32 cells then share their inclusion pattern
+  // (a control cell is part of every treatment's contrast, a treated cell of one) and the per-treatment loop of
+  // the kernel does not diverge; in input order half of the lanes idled through it.  The sums only change in
+  // their rounding.
+  std::vector<int> order(n);
+  {
+    std::vector<int> key(n);
+    for (int i = 0; i < n; ++i) {
+      int k = 0;
+      if (!ctrl[i])
+        for (int j = 0; j < a; ++j)
+          if (A[(size_t)i * a + j] != 0.0) {
+            k = 1 + j;
+            break;
+          }
+      key[i] = k;
+      order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
+  }
   std::vector<std::vector<double>> recs(ngroups, std::vector<double>((size_t)n * ldr, 0.0));
   for (int g = 0; g < ngroups; ++g) {
     std::vector<double>& R = recs[g];
     const int j0 = g * JT, nj = std::min(JT, a - j0);
-    for (int i = 0; i < n; ++i) {
-      double* r = R.data() + (size_t)i * ldr;
+    for (int c = 0; c < n; ++c) {
+      const int i = order[c];
+      double* r = R.data() + (size_t)c * ldr;
+      r[kw + 2 + 3 * JT] = (double)i;
       for (int q = 0; q < kw; ++q) r[q] = W ? W[(size_t)i * kw + q] : 0.0;
       r[kw] = offset ? offset[i] : 0.0;
       const double isf = 1.0 / size_factor[i];

@@ -66,31 +66,63 @@ struct S2Args {
 };
 
 // log-likelihood of one entry at theta0 + delta (m0 = e^{clamp(theta0)}, E = e^{delta})
-// POIS is uniform over a gene's warp, so the two forms are two code paths, not selects.  Comparisons are plain
-// FP64 compares here: the kernel is bound by instruction issue (55 % of the slots, FP64 pipe 28 %), and the
-// integer-pipe comparisons of fastmath.cuh cost two ISETPs each (a third of this kernel's instructions were
-// compares and selects).
-template <bool POIS>
-__device__ __forceinline__ double s2_entry(const FmTables& FT, const NbClip& clip, double y, double th0, double m0,
-                                           double dl, double E, double nu, double inu, double lnu) {
-  const double xr = th0 + dl;
+// The N candidates of one entry, statement by statement across the candidates (fm_log_n: the N dependent chains
+// are interleaved in source order, which ptxas keeps -- N consecutive scalar evaluations ran one after the other
+// with every dependent FP64 operation exposed).  POIS is uniform over a gene's warp, so the two forms are two
+// code paths, not selects.  Comparisons are plain FP64 compares here: the kernel is bound by instruction issue
+// (55 % of the slots, FP64 pipe 28 %), and the integer-pipe comparisons of fastmath.cuh cost two ISETPs each.
+// (M cells x N candidates per call: M = 4, N = 2 in the first pass, M = 1, N = S2_NC afterwards)
+template <bool POIS, int M, int N>
+__device__ __forceinline__ void s2_entries(const FmTables& FT, const NbClip& clip, const double* y, const double* th,
+                                           const int* g, const double (*dl)[32], const double (*Ee)[32], double nu,
+                                           double inu, double lnu, double (&acc)[S2_NC]) {
+  double xe[M], m0[M];
+#pragma unroll
+  for (int u = 0; u < M; ++u) {
+    const double t = th[u] < 700.0 ? th[u] : 700.0;
+    xe[u] = t > -700.0 ? t : -700.0;
+  }
+  fm_exp_n<M>(xe, m0, FT.exp_t);
   if (POIS) {
-    const bool below = xr < 100.0;
-    const double xi = below ? xr : 100.0;
-    const double m = below ? m0 * E : 2.6881171418161356e43;   // e^100: the reference clips theta from above
-    return fma(y, xi, -m);
+#pragma unroll
+    for (int u = 0; u < M; ++u)
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double xr = th[u] + dl[k][g[u]];
+        const bool below = xr < 100.0;
+        const double xi = below ? xr : 100.0;
+        const double m = below ? m0[u] * Ee[k][g[u]] : 2.6881171418161356e43;   // e^100: the reference clips theta from above
+        acc[k] += fma(y[u], xi, -m);
+      }
+    return;
   }
   // NB: a theta clipped at 100 has u = e^100 / nu far above u_hi (nu <= the Poisson threshold), and so has the
   // unclipped product m0 E (or its overflow to +inf): the upper clip of u already gives the reference's value
-  double uc = (m0 * E) * inu;
-  double lu = xr - lnu;
-  const bool lo = uc < clip.u_lo, hi = uc > clip.u_hi;
-  uc = lo ? clip.u_lo : uc;
-  lu = lo ? clip.lu_lo : lu;
-  uc = hi ? clip.u_hi : uc;
-  lu = hi ? clip.lu_hi : lu;
-  const double L = fm_log(1.0 + uc, FT.log_t);
-  return fma(-(y + nu), L, y * lu);
+  double uc[M * N], lu[M * N], w[M * N], L[M * N];
+#pragma unroll
+  for (int u = 0; u < M; ++u)
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      uc[u * N + k] = (m0[u] * Ee[k][g[u]]) * inu;
+      lu[u * N + k] = (th[u] + dl[k][g[u]]) - lnu;
+    }
+#pragma unroll
+  for (int e = 0; e < M * N; ++e) {
+    const bool lo = uc[e] < clip.u_lo, hi = uc[e] > clip.u_hi;
+    uc[e] = lo ? clip.u_lo : uc[e];
+    lu[e] = lo ? clip.lu_lo : lu[e];
+    uc[e] = hi ? clip.u_hi : uc[e];
+    lu[e] = hi ? clip.lu_hi : lu[e];
+  }
+#pragma unroll
+  for (int e = 0; e < M * N; ++e) w[e] = 1.0 + uc[e];
+  fm_log_n<M * N>(w, L, FT.log_t);
+#pragma unroll
+  for (int u = 0; u < M; ++u) {
+    const double yn = y[u] + nu;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] += fma(-yn, L[u * N + k], y[u] * lu[u * N + k]);
+  }
 }
 
 template <bool NB>
@@ -128,8 +160,11 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
   // evaluates nc candidates with steps tc[0..nc): returns their treated-cell log-likelihood sums
   // (all lanes hold them) and their penalties
   // (base: candidate 0 is the CURRENT point, delta = 0 -- not the prox of it)
-  auto eval = [&](auto pois_c, const double* tc, int nc, bool base, double* ell_out, double* pen_out) {
+  // (N = 2: the first pass; N = S2_NC afterwards -- a shorter last batch still evaluates S2_NC candidates, the
+  // extra ones at delta = 0, and ignores them)
+  auto eval = [&](auto pois_c, auto n_c, const double* tc, int nc, bool base, double* ell_out, double* pen_out) {
     constexpr bool POIS = decltype(pois_c)::value;
+    constexpr int N = decltype(n_c)::value;
 #pragma unroll
     for (int k = 0; k < S2_NC; ++k) {
       if (k < nc) {
@@ -141,6 +176,9 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
         double pen = (lane < a && A.lam) ? lm * fabs(x1) : 0.0;
         pen = warp_sum(pen);
         pen_out[k] = A.lam ? pen / (double)a : 0.0;
+      } else if (k < N) {
+        dl[k][lane] = 0.0;
+        Ee[k][lane] = 1.0;
       }
     }
     __syncwarp();
@@ -160,16 +198,14 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
         th4[u] = ok ? trow[c] : 0.0;
         g4[u] = ok ? (int)A.grp[c] : -1;
       }
+      if (N <= 2 && c0 + 128 <= A.ntr) {
+        s2_entries<POIS, 4, N>(FT, clip, y4, th4, g4, dl, Ee, nu, inu, lnu, acc);   // (all 128 cells exist)
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g4[u] < 0) continue;
-        const double th0 = th4[u];
-        double xe = fm_lt_pos(th0, 700.0) ? th0 : 700.0;
-        xe = fm_gt_neg(xe, -700.0) ? xe : -700.0;
-        const double m0 = fm_exp(xe, FT.exp_t);
-#pragma unroll
-        for (int k = 0; k < S2_NC; ++k)
-          if (k < nc) acc[k] += s2_entry<POIS>(FT, clip, y4[u], th0, m0, dl[k][g4[u]], Ee[k][g4[u]], nu, inu, lnu);
+        for (int u = 0; u < 4; ++u) {
+          if (g4[u] < 0) continue;
+          s2_entries<POIS, 1, N>(FT, clip, y4 + u, th4 + u, g4 + u, dl, Ee, nu, inu, lnu, acc);
+        }
       }
     }
 #pragma unroll
@@ -183,10 +219,17 @@ __global__ void __launch_bounds__(S2_WARPS * 32, 2) k_s2_onehot(S2Args A) {
   tc[0] = 0.0;
   tc[1] = alpha;
   auto eval_any = [&](const double* tcs, int nc, bool base, double* ell_out, double* pen_out) {
-    if (!NB || pois)
-      eval(std::true_type{}, tcs, nc, base, ell_out, pen_out);
-    else
-      eval(std::false_type{}, tcs, nc, base, ell_out, pen_out);
+    if (!NB || pois) {
+      if (nc <= 2)
+        eval(std::true_type{}, std::integral_constant<int, 2>{}, tcs, nc, base, ell_out, pen_out);
+      else
+        eval(std::true_type{}, std::integral_constant<int, S2_NC>{}, tcs, nc, base, ell_out, pen_out);
+    } else {
+      if (nc <= 2)
+        eval(std::false_type{}, std::integral_constant<int, 2>{}, tcs, nc, base, ell_out, pen_out);
+      else
+        eval(std::false_type{}, std::integral_constant<int, S2_NC>{}, tcs, nc, base, ell_out, pen_out);
+    }
   };
   eval_any(tc, 2, true, el, pn);
   const double ell_ctrl = ell0 - el[0];
