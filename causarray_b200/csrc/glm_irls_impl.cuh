@@ -44,7 +44,8 @@ constexpr int IRLS_WARPS = 4;      // cell ranges of an octet (each with its own
 constexpr int IRLS_NH = 2;         // warps per cell range: 8 warps per CTA, two CTAs (octets) per SM
 constexpr int IRLS_LOGY = 256;     // counts below this read log y from shared memory (log y is the same in every
                                    // iteration; the table holds the values fm_log would return, bit for bit)
-constexpr int IRLS_SOLVERS = 8;
+constexpr int IRLS_SOLVERS = 8;    // (the lasso refit, whose work space is 4.5 x larger, uses IRLS_SOLVERS_L1 warps
+constexpr int IRLS_SOLVERS_L1 = 8; //  too: its iteration is dominated by the active-set solve, see glm_solve.cuh)
 static_assert(IRLS_WARPS <= 4, "group_sync() names four barriers");    // warps with solve work space (one gene each)
 constexpr int IRLS_CHUNK = 32;    // cells per staged chunk (per warp): four pair-steps of 8 cells
 constexpr int IRLS_MAX_KDE = 16;
@@ -125,7 +126,7 @@ inline size_t glm_irls_smem_bytes(int kde, int kx, int ngroups, bool lasso) {
   d += (size_t)nt * 64;                                       // dense totals
   d += (size_t)IRLS_WARPS * 8;                                // deviance partials
   d += (size_t)8 * kx;                                        // coefficients of the octet
-  d += (size_t)IRLS_SOLVERS * glm_irls_work_doubles(kx, kde, ngroups, lasso);
+  d += (size_t)(lasso ? IRLS_SOLVERS_L1 : IRLS_SOLVERS) * glm_irls_work_doubles(kx, kde, ngroups, lasso);
   d += FM_TABLE_DOUBLES;
   d += IRLS_LOGY;                                             // log 1, log 1, log 2 .. log(IRLS_LOGY - 1)
   return d * sizeof(double);
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
   double* betas = Dp + IRLS_WARPS * 8;                     // 8 * kx
   double* work_all = betas + 8 * kx;
   const size_t work_d = glm_irls_work_doubles(kx, KDE, P.ngroups, lasso);
-  double* wbuf_all = work_all + IRLS_SOLVERS * work_d;       // IRLS_WARPS * 2 * IRLS_CHUNK * WLD
+  const int nsolv = lasso ? IRLS_SOLVERS_L1 : IRLS_SOLVERS;
+  double* wbuf_all = work_all + nsolv * work_d;       // IRLS_WARPS * 2 * IRLS_CHUNK * WLD
   double* bdense = wbuf_all + IRLS_WARPS * 2 * IRLS_CHUNK * WLD;  // 8 * KDE
   double* s_nu = bdense + 8 * KDE;                         // 8
   double* s_ybar = s_nu + 8;                               // 8
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
       if (tid == 0) s_nrun = 0;
       __syncthreads();
       // ---------------- warp g: convergence test and update of gene g ----------------
-      for (int g = warp; g < 8; g += IRLS_WARPS * NH) {
+      for (int g = warp; g < 8 && warp < nsolv; g += nsolv) {   // (work space slot = warp)
         const int gene = s_gene[g];
         bool run = gene >= 0 && s_status[g] == 0;
         if (run) {
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
             // kx^2 assembly were 32 % of the kernel's time, all of it with the FP64 pipe idle).
             const int nd = P.dcol[U] >= 0 ? KDE : KDE - 1;     // an appended unit column is not a coefficient
             const int ngr = P.ngroups - 1;
-            double* wk = work_all + (size_t)g * work_d;
+            double* wk = work_all + (size_t)warp * work_d;
             const GlmSolveWork W = glm_solve_carve(wk, nd);
             double* cg = wk + glm_solve_work_doubles(nd, false);  // ngr x (KDE + 1): c_g[0..KDE-1] (entry U = d_g), r_g
             const int ld = nd + 1;
@@ -655,7 +657,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
               if (!fin) newst = 2;
             }
           } else {
-          const GlmSolveWork W = glm_solve_carve(work_all + (size_t)g * work_d, kx);
+          const GlmSolveWork W = glm_solve_carve(work_all + (size_t)warp * work_d, kx);
           const int ld = kx + 1;
           for (int e = lane; e < kx * kx; e += 32) {
             const int ci = e / kx, cj = e - ci * kx;

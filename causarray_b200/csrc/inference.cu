@@ -95,6 +95,7 @@ struct TailRows {
   double* pva;         // a x p
   double* qva;         // a x p
   double* med_mad;     // a x 2 (median, MAD / Phi^{-1}(3/4))
+  int sort_in_smem;
 };
 
 // bitonic sort of (key, idx) ascending, one CTA, data in global memory
@@ -186,8 +187,11 @@ __global__ void __launch_bounds__(1024) k_tail_rows(TailRows R) {
   const int row = blockIdx.x;
   const double* t = R.t + (size_t)row * R.p;
   const double* df = R.df ? R.df + (size_t)row * R.p : nullptr;
-  double* key = R.key + (size_t)row * R.m;
-  int* idx = R.idx + (size_t)row * R.m;
+  // sort buffers: shared memory when the padded row fits (96 KB at p = 8000; the 4 x 91 compare-exchange
+  // stages of a row then run at shared-memory instead of L2 latency), global scratch otherwise
+  extern __shared__ __align__(16) unsigned char s_sort[];
+  double* key = R.sort_in_smem ? reinterpret_cast<double*>(s_sort) : R.key + (size_t)row * R.m;
+  int* idx = R.sort_in_smem ? reinterpret_cast<int*>(s_sort + sizeof(double) * R.m) : R.idx + (size_t)row * R.m;
   double* pv = R.pv + (size_t)row * R.p;
   double* qv = R.qv + (size_t)row * R.p;
   double* pva = R.pva + (size_t)row * R.p;
@@ -259,7 +263,11 @@ extern "C" int ca_inference_tail(const double* t, const double* df, int a, int p
   R.med_mad = mm.ptr;
   {
     ProfScope prof(PROF_AIPW, st);
-    k_tail_rows<<<a, 1024, 0, st>>>(R);
+    size_t smem = (size_t)m * (sizeof(double) + sizeof(int));
+    R.sort_in_smem = smem <= 200 * 1024;
+    if (!R.sort_in_smem) smem = 0;
+    CA_CUDA(cudaFuncSetAttribute(k_tail_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tail_rows<<<a, 1024, smem, st>>>(R);
     CA_LAUNCH_CHECK();
   }
   CA_CUDA(cudaMemcpyAsync(pv, R.pv, sizeof(double) * np_, cudaMemcpyDeviceToHost, st));
