@@ -253,6 +253,76 @@ __device__ __forceinline__ void eval_entry(const FmTables& FT, const NbClip& cli
   }
 }
 
+// The four entries a lane has in flight (A0, B0, A1, B1 of the tile pair), for the switch-free NB modes:
+// the same operations as four eval_entry calls, written statement by statement ACROSS the entries
+// (fm_exp_n / fm_log_n / fm_rcp_n).  ptxas keeps source order: with four consecutive calls it overlapped
+// the chains only in pairs.  accA takes entries 0 and 2 (in that order), accB entries 1 and 3.
+template <int MODE, bool GRAD, bool RAGGED>
+__device__ __forceinline__ void eval_entries4(const FmTables& FT, const NbClip& clip, const double (&theta)[4],
+                                              const double (&yin)[4], const double (&nu)[4], const double (&inu)[4],
+                                              const double (&lnu)[4], const bool (&valid)[4], double& accA,
+                                              double& accB, double (&d)[4]) {
+  static_assert(mode_fast(MODE), "switch-free NB modes only");
+  double x[4], lu[4], L[4], y[4], c[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    x[e] = fm_lt_pos(theta[e], 100.0) ? theta[e] : 100.0;
+    y[e] = yin[e];
+  }
+  if (!GRAD) {
+    double u[4], w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lu[e] = x[e] - lnu[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lu[e] = fm_lt_neg(lu[e], clip.lu_lo) ? clip.lu_lo : lu[e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) lu[e] = fm_gt_pos(lu[e], clip.lu_hi) ? clip.lu_hi : lu[e];
+    fm_exp_n<4>(lu, u, FT.exp_t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = 1.0 + u[e];
+    fm_log_n<4>(w, L, FT.log_t);
+  } else {
+    double xe[4], m[4], uc[4], w[4], r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xe[e] = fm_gt_neg(x[e], -700.0) ? x[e] : -700.0;
+    fm_exp_n<4>(xe, m, FT.exp_t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uc[e] = m[e] * inu[e];
+      lu[e] = x[e] - lnu[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool lo = fm_lt_pos(uc[e], clip.u_lo), hi = fm_gt_pos(uc[e], clip.u_hi);
+      uc[e] = lo ? clip.u_lo : uc[e];
+      lu[e] = lo ? clip.lu_lo : lu[e];
+      uc[e] = hi ? clip.u_hi : uc[e];
+      lu[e] = hi ? clip.lu_hi : lu[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = 1.0 + uc[e];
+    fm_log_n<4>(w, L, FT.log_t);
+    fm_rcp_n<4>(w, r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      d[e] = (m[e] - y[e]) * r[e];
+      if (RAGGED) d[e] = valid[e] ? d[e] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    c[e] = y[e] + nu[e];
+    if (RAGGED) {
+      y[e] = valid[e] ? y[e] : 0.0;
+      c[e] = valid[e] ? c[e] : 0.0;
+    }
+  }
+  accA = fma(-c[0], L[0], fma(y[0], lu[0], accA));
+  accB = fma(-c[1], L[1], fma(y[1], lu[1], accB));
+  accA = fma(-c[2], L[2], fma(y[2], lu[2], accA));
+  accB = fma(-c[3], L[3], fma(y[3], lu[3], accB));
+}
+
 // One pass over all columns for the 8 rows listed in s_rows (-1 = empty slot; its sums are
 // garbage and ignored by the callers).  s_X: 8 x kpad candidate rows.  On return (after a
 // __syncthreads) s_rowsum[r] holds sum_col ell(y, theta) and, if GRAD, s_G[r*NGT*8 + c] holds
@@ -348,10 +418,25 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
         vB1 = hasB && clB + 1 < nrem;
       }
       double dA0 = 0.0, dA1 = 0.0, dB0 = 0.0, dB1 = 0.0;
-      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, ellA, dA0);
-      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, ellB, dB0);
-      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, ellA, dA1);
-      eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, ellB, dB1);
+      if constexpr (mode_fast(MODE)) {
+        const double th4[4] = {pa[0][0], pb[0][0], pa[0][1], pb[0][1]};
+        const double y4[4] = {yA.x, yB.x, yA.y, yB.y};
+        const double nu4[4] = {cA0.x, cB0.x, cA1.x, cB1.x};
+        const double in4[4] = {cA0.y, cB0.y, cA1.y, cB1.y};
+        const double ln4[4] = {cA0.z, cB0.z, cA1.z, cB1.z};
+        const bool v4[4] = {vA0, vB0, vA1, vB1};
+        double d4[4] = {0.0, 0.0, 0.0, 0.0};
+        eval_entries4<MODE, GRAD, RAGGED>(FT, clip, th4, y4, nu4, in4, ln4, v4, ellA, ellB, d4);
+        dA0 = d4[0];
+        dB0 = d4[1];
+        dA1 = d4[2];
+        dB1 = d4[3];
+      } else {
+        eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, ellA, dA0);
+        eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, ellB, dB0);
+        eval_entry<MODE, GRAD, RAGGED>(FT, clip, pa[0][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, ellA, dA1);
+        eval_entry<MODE, GRAD, RAGGED>(FT, clip, pb[0][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, ellB, dB1);
+      }
       if (GRAD) {
         const double* gA = Mb + (tA * 8 + 2 * lc) * KPAD + gc_lo + lr;
         const double* gB = Mb + (tB * 8 + 2 * lc) * KPAD + gc_lo + lr;
@@ -736,10 +821,21 @@ __device__ __forceinline__ void tile_pass_multi_mode(const PassCfg& P, const FmT
       double dummy = 0.0;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, accA[c], dummy);
-        eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, accB[c], dummy);
-        eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, accA[c], dummy);
-        eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, accB[c], dummy);
+        if constexpr (mode_fast(MODE)) {
+          const double th4[4] = {pa[c][0], pb[c][0], pa[c][1], pb[c][1]};
+          const double y4[4] = {yA.x, yB.x, yA.y, yB.y};
+          const double nu4[4] = {cA0.x, cB0.x, cA1.x, cB1.x};
+          const double in4[4] = {cA0.y, cB0.y, cA1.y, cB1.y};
+          const double ln4[4] = {cA0.z, cB0.z, cA1.z, cB1.z};
+          const bool v4[4] = {vA0, vB0, vA1, vB1};
+          double d4[4];
+          eval_entries4<MODE, false, RAGGED>(FT, clip, th4, y4, nu4, in4, ln4, v4, accA[c], accB[c], d4);
+        } else {
+          eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][0], yA.x, cA0.x, cA0.y, cA0.z, cA0.w != 0.0, vA0, accA[c], dummy);
+          eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][0], yB.x, cB0.x, cB0.y, cB0.z, cB0.w != 0.0, vB0, accB[c], dummy);
+          eval_entry<MODE, false, RAGGED>(FT, clip, pa[c][1], yA.y, cA1.x, cA1.y, cA1.z, cA1.w != 0.0, vA1, accA[c], dummy);
+          eval_entry<MODE, false, RAGGED>(FT, clip, pb[c][1], yB.y, cB1.x, cB1.y, cB1.z, cB1.w != 0.0, vB1, accB[c], dummy);
+        }
       }
     };
 #pragma unroll 1

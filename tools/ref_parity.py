@@ -50,7 +50,38 @@ def make_data(cfg, seed):
     return dict(Y=Y, X=X, A=A, X_A=X_A, disp=sim["disp"], r=r, family=fam, iters=30)
 
 
+def annotate(out, tol=1e-8):
+    """Stop-rule summary of the probed genes.  A fit is BORDERLINE when a deviance change next to its stopping
+    decision lies within 1e-11 of the threshold: the decision then hangs on the rounding of a sum of n unit
+    deviances (~1e-13 .. 1e-12 absolute), on either side -- the reference's own arithmetic (its numpy sums, its
+    least-squares solver) decides such a gene differently from a restatement of the same formulas, too."""
+    flips, border = [], []
+    for q in out.get("probes", []):
+        if any(v["iters_device"] != v["iters_cpu"] for v in q["fits"].values()):
+            flips.append(q["gene"])
+        margins = {}
+        for name, v in q["fits"].items():
+            ch = [c for c in list(v["cpu_last_dev_changes"]) + list(v["device_dev_changes"]) if c > 0.0]
+            if ch:
+                margins[name] = min(abs(c - tol) for c in ch)
+        q["stop_margin"] = margins
+        if margins and min(margins.values()) < 1e-11:
+            border.append({"gene": q["gene"], "fit": min(margins, key=margins.get), "margin": min(margins.values())})
+    out["probed_genes_with_a_stop_rule_flip"] = flips
+    out["probed_genes_with_a_borderline_stop"] = border
+    out["probed_genes_without_flip"] = [q["gene"] for q in out.get("probes", []) if q["gene"] not in flips]
+    d = out.get("irls_gene_iters_ref", 0) - out.get("irls_gene_iters_gpu", 0)
+    out["irls_gene_iters_ref_minus_gpu"] = d
+    return out
+
+
 def main():
+    if len(sys.argv) == 3 and sys.argv[1] == "--annotate":   # re-derive the stop-rule summary of a saved record
+        with open(sys.argv[2]) as fh:
+            rec = json.loads(fh.read())
+        with open(sys.argv[2], "w") as fh:
+            fh.write(json.dumps(annotate(rec)) + "\n")
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--seed", type=int, default=100)
@@ -185,9 +216,7 @@ def main():
                     "device_dev_changes": [abs(hist_g[i][1] - hist_g[i - 1][1]) for i in range(1, len(hist_g))]}
             probes.append(rec)
     out["probes"] = probes
-    flips = [q["gene"] for q in probes if any(v["iters_device"] != v["iters_cpu"] for v in q["fits"].values())]
-    out["probed_genes_with_a_stop_rule_flip"] = flips
-    out["probed_genes_without_flip"] = [q["gene"] for q in probes if q["gene"] not in flips]
+    annotate(out)
     ws.close()
     line = json.dumps(out)
     if args.out:
