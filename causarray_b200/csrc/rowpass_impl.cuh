@@ -380,6 +380,17 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
       const int clA = tA * 8 + 2 * lc, clB = tB * 8 + 2 * lc;  // columns within the chunk
       const double2 yA = *reinterpret_cast<const double2*>(Yb + tA * 8);
       const double2 yB = *reinterpret_cast<const double2*>(Yb + tB * 8);
+      // theta output: the positions of the four columns are requested here, ahead of the products and the
+      // likelihood terms, so that their (L1 / L2) latency is hidden; loaded next to the stores they were
+      // exposed at the end of every tile pair (+30 % on the pass)
+      int qA0 = -1, qA1 = -1, qB0 = -1, qB1 = -1;
+      if (TH && GRAD) {
+        const int cA = col0 + clA, cB = col0 + clB;
+        if (!RAGGED || clA < nrem) qA0 = __ldg(P.theta_pos + cA);
+        if (!RAGGED || clA + 1 < nrem) qA1 = __ldg(P.theta_pos + cA + 1);
+        if (hasB && (!RAGGED || clB < nrem)) qB0 = __ldg(P.theta_pos + cB);
+        if (hasB && (!RAGGED || clB + 1 < nrem)) qB1 = __ldg(P.theta_pos + cB + 1);
+      }
       double pa[NACC][2], pb[NACC][2];
       const double* bpA = Mb + (tA * 8 + lr) * KPAD + lc;
       const double* bpB = Mb + (tB * 8 + lr) * KPAD + lc;
@@ -452,11 +463,10 @@ __device__ __forceinline__ void tile_pass_mode(const PassCfg& P, const FmTables&
           // one-hot line search that follows; placed after the likelihood terms so that their
           // straight-line block stays intact
           double* tr = P.theta_out + (size_t)row * P.theta_ld;
-          const int cA = col0 + clA, cB = col0 + clB;
-          if (vA0) { const int q = P.theta_pos[cA]; if (q >= 0) tr[q] = pa[0][0]; }
-          if (vA1) { const int q = P.theta_pos[cA + 1]; if (q >= 0) tr[q] = pa[0][1]; }
-          if (hasB && vB0) { const int q = P.theta_pos[cB]; if (q >= 0) tr[q] = pb[0][0]; }
-          if (hasB && vB1) { const int q = P.theta_pos[cB + 1]; if (q >= 0) tr[q] = pb[0][1]; }
+          if (qA0 >= 0) tr[qA0] = pa[0][0];
+          if (qA1 >= 0) tr[qA1] = pa[0][1];
+          if (qB0 >= 0) tr[qB0] = pb[0][0];
+          if (qB1 >= 0) tr[qB1] = pb[0][1];
         }
       }
     };
