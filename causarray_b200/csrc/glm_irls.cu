@@ -253,7 +253,10 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   if (n_oct <= 0) return 0;
   const int grid = std::min(n_oct, 2 * sm_count);   // two CTAs per SM when the shared memory allows (the kernel is persistent either way)
   const int nb = (kde + 7) / 8;
-  if (h->irls_scratch.alloc((size_t)grid * L.nseg_tot * (nb + 1) * 64)) return -1;
+  const size_t flush_d = (size_t)grid * L.nseg_tot * (nb + 1) * 64;
+  const size_t gc_d = lasso ? (size_t)grid * IRLS_SOLVERS_L1 * kx * (kx + 1) : 0;
+  const size_t gsum_d = (size_t)grid * (L.ngroups + 1) * (nb + 1) * 64;
+  if (h->irls_scratch.alloc(flush_d + gc_d + gsum_d)) return -1;
   CA_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(int) * 2, st));
   GlmIrls P;
   memset(&P, 0, sizeof P);
@@ -292,6 +295,8 @@ int glm_fit_irls(ca_glm* h, const IrlsPlan& L, const double* X, const double* of
   P.counter = h->counter.ptr;
   P.not_counts = h->not_counts.ptr;
   P.scratch = h->irls_scratch.ptr;
+  P.gc_scratch = h->irls_scratch.ptr + flush_d;
+  P.gsum = h->irls_scratch.ptr + flush_d + gc_d;
   P.beta = h->beta.ptr;
   P.dev = h->dev.ptr;
   P.step = h->step.ptr;

@@ -45,7 +45,8 @@ constexpr int IRLS_NH = 2;         // warps per cell range: 8 warps per CTA, two
 constexpr int IRLS_LOGY = 256;     // counts below this read log y from shared memory (log y is the same in every
                                    // iteration; the table holds the values fm_log would return, bit for bit)
 constexpr int IRLS_SOLVERS = 8;    // (the lasso refit, whose work space is 4.5 x larger, uses IRLS_SOLVERS_L1 warps
-constexpr int IRLS_SOLVERS_L1 = 8; //  too: its iteration is dominated by the active-set solve, see glm_solve.cuh)
+constexpr int IRLS_SOLVERS_L1 = 4; //  in two rounds, and keeps its copy of the Gram matrix in global scratch, so that two
+                                   //  CTAs fit on an SM here too: one octet's solves then overlap the other's arithmetic)
 static_assert(IRLS_WARPS <= 4, "group_sync() names four barriers");    // warps with solve work space (one gene each)
 constexpr int IRLS_CHUNK = 32;    // cells per staged chunk (per warp): four pair-steps of 8 cells
 constexpr int IRLS_MAX_KDE = 16;
@@ -87,6 +88,8 @@ struct GlmIrls {
   int* counter;                        // octet dispenser (zeroed by the host)
   const int* not_counts;               // 0: every entry of Yp is a non-negative integer (log y from a table)
   double* scratch;                     // per CTA: nseg_tot x (NB + 1) x 64 doubles
+  double* gsum;                        // per CTA: (ngroups + 1) x (NB + 1) x 64 doubles: group sums and totals of the flushed tiles
+  double* gc_scratch;                  // lasso refit, per CTA: IRLS_SOLVERS_L1 x kx x (kx + 1) doubles
   double* beta;                        // p x kx (in: warm start; out)
   double* dev;                         // p
   double* step;                        // p (lasso refit: relative size of the last update)
@@ -110,7 +113,7 @@ struct IrlsShape {
 // Work space of one solving warp: the lasso refit factorises the full kx x kx system (+ a copy), the
 // unpenalised fit only the dense block (arrow structure) next to the per-group couplings.
 __host__ __device__ inline size_t glm_irls_work_doubles(int kx, int kde, int ngroups, bool lasso) {
-  return lasso ? glm_solve_work_doubles(kx, true)
+  return lasso ? glm_solve_work_doubles(kx, true) - (size_t)kx * (kx + 1)   // (the Gram copy is in global scratch)
                : glm_solve_work_doubles(kde, false) + (size_t)(ngroups > 1 ? ngroups - 1 : 0) * (kde + 1);
 }
 
@@ -204,6 +207,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
   const int c_lo = P.chunk_lo[cr], c_hi = P.chunk_lo[cr + 1];
   const int n_oct = ((P.genelist ? P.n_list : P.p) + 7) >> 3;
   double* scratch = P.scratch + (size_t)blockIdx.x * P.nseg_tot * (FLT * 64);
+  double* gsum = P.gsum + (size_t)blockIdx.x * (P.ngroups + 1) * (FLT * 64);
   constexpr double LOG_EPS = -36.04365338911715;  // log(2^-52): statsmodels clips y / mu at FLOAT_EPS
 
   for (;;) {
@@ -523,6 +527,23 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
         }
         __syncthreads();
       }
+      // ---------------- per-group and total sums of the flushed tiles ----------------
+      // (all threads, independent outputs; the solving warps then read ONE value per matrix entry -- summing
+      // up to nseg_tot L2-resident values per entry inside the assembly was a chain of dependent L2
+      // latencies, ~10 % of an unpenalised octet iteration and a third of a lasso one.  Same summation order.)
+      {
+        constexpr int GS = FLT * 64;
+        for (int e = tid; e < (P.ngroups + 1) * GS; e += IRLS_THREADS) {
+          const int gg = e / GS, o = e - gg * GS;
+          double v = 0.0;
+          if (gg < P.ngroups) {
+            for (int q = P.gseg_ptr[gg]; q < P.gseg_ptr[gg + 1]; ++q) v += scratch[(size_t)P.gseg_list[q] * GS + o];
+          } else {
+            for (int s2 = 0; s2 < P.nseg_tot; ++s2) v += scratch[(size_t)s2 * GS + o];
+          }
+          gsum[e] = v;
+        }
+      }
       if (tid == 0) s_nrun = 0;
       __syncthreads();
       // ---------------- warp g: convergence test and update of gene g ----------------
@@ -563,7 +584,8 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
           }
         }
         if (run) {
-          const double* sc0 = scratch + g;   // column g of every flushed tile
+          const double* gs0 = gsum + g;                                  // column g of the group sums ...
+          const double* gt0 = gsum + (size_t)P.ngroups * (FLT * 64) + g; // ... and of the totals over all segments
           int newst = 0;
           if (!lasso) {
             // Arrow structure of the normal equations: dense block D (KDE columns) + one diagonal entry
@@ -583,7 +605,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
               const int gg = e / CL + 1, i = e - (gg - 1) * CL;
               double v = 0.0;
               const int off = i < KDE ? (i >> 3) * 64 + (i & 7) * 8 : NB * 64 + (U & 7) * 8;
-              for (int q = P.gseg_ptr[gg]; q < P.gseg_ptr[gg + 1]; ++q) v += sc0[(size_t)P.gseg_list[q] * (FLT * 64) + off];
+              v = gs0[(size_t)gg * (FLT * 64) + off];
               if (i == U && P.ridge) v += P.ridge[P.gcol[gg]];
               cg[e] = v;
             }
@@ -592,7 +614,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
               const int a = i < j ? i : j, bb = i < j ? j : i;
               double v = 0.0;
               if (bb == U) {
-                for (int s2 = 0; s2 < P.nseg_tot; ++s2) v += sc0[(size_t)s2 * (FLT * 64) + (a >> 3) * 64 + (a & 7) * 8];
+                v = gt0[(a >> 3) * 64 + (a & 7) * 8];
               } else {
                 v = Tt[S::tw(a >> 3, bb) * 64 + (a & 7) * 8 + g];
               }
@@ -602,7 +624,7 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
             for (int i = lane; i < nd; i += 32) {
               double v = 0.0;
               if ((i >> 3) == NB - 1) {
-                for (int s2 = 0; s2 < P.nseg_tot; ++s2) v += sc0[(size_t)s2 * (FLT * 64) + NB * 64 + (i & 7) * 8];
+                v = gt0[NB * 64 + (i & 7) * 8];
               } else {
                 v = Tt[(NTW + (i >> 3)) * 64 + (i & 7) * 8 + g];
               }
@@ -657,7 +679,8 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
               if (!fin) newst = 2;
             }
           } else {
-          const GlmSolveWork W = glm_solve_carve(work_all + (size_t)warp * work_d, kx);
+          const GlmSolveWork W = glm_solve_carve(work_all + (size_t)warp * work_d, kx,
+                                                 P.gc_scratch + ((size_t)blockIdx.x * IRLS_SOLVERS_L1 + warp) * kx * (kx + 1));
           const int ld = kx + 1;
           for (int e = lane; e < kx * kx; e += 32) {
             const int ci = e / kx, cj = e - ci * kx;
@@ -667,17 +690,15 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
             if (di >= 0 && dj >= 0) {
               const int a = di < dj ? di : dj, bb = di < dj ? dj : di;
               if (bb == U) {
-                for (int s = 0; s < P.nseg_tot; ++s) v += sc0[(size_t)s * (FLT * 64) + (a >> 3) * 64 + (a & 7) * 8];
+                v = gt0[(a >> 3) * 64 + (a & 7) * 8];
               } else {
                 v = Tt[S::tw(a >> 3, bb) * 64 + (a & 7) * 8 + g];
               }
             } else if (di >= 0 || dj >= 0) {
               const int a = di >= 0 ? di : dj, gg = di >= 0 ? gj : gi;
-              for (int q = P.gseg_ptr[gg]; q < P.gseg_ptr[gg + 1]; ++q)
-                v += sc0[(size_t)P.gseg_list[q] * (FLT * 64) + (a >> 3) * 64 + (a & 7) * 8];
+              v = gs0[(size_t)gg * (FLT * 64) + (a >> 3) * 64 + (a & 7) * 8];
             } else if (gi == gj) {
-              for (int q = P.gseg_ptr[gi]; q < P.gseg_ptr[gi + 1]; ++q)
-                v += sc0[(size_t)P.gseg_list[q] * (FLT * 64) + (U >> 3) * 64 + (U & 7) * 8];
+              v = gs0[(size_t)gi * (FLT * 64) + (U >> 3) * 64 + (U & 7) * 8];
             }
             if (P.ridge && ci == cj) v += P.ridge[ci];
             W.L[ci * ld + cj] = v;
@@ -687,13 +708,12 @@ __global__ void __launch_bounds__(IRLS_WARPS * 32 * NH, 2) k_glm_irls(const __gr
             double v = 0.0;
             if (di >= 0) {
               if ((di >> 3) == NB - 1) {
-                for (int s = 0; s < P.nseg_tot; ++s) v += sc0[(size_t)s * (FLT * 64) + NB * 64 + (di & 7) * 8];
+                v = gt0[NB * 64 + (di & 7) * 8];
               } else {
                 v = Tt[(NTW + (di >> 3)) * 64 + (di & 7) * 8 + g];
               }
             } else {
-              for (int q = P.gseg_ptr[gg]; q < P.gseg_ptr[gg + 1]; ++q)
-                v += sc0[(size_t)P.gseg_list[q] * (FLT * 64) + NB * 64 + (U & 7) * 8];
+              v = gs0[(size_t)gg * (FLT * 64) + NB * 64 + (U & 7) * 8];
             }
             W.b[c] = v;
           }

@@ -17,15 +17,18 @@ __host__ __device__ inline size_t glm_solve_work_doubles(int kx, bool lasso) {
   return (size_t)kx * (kx + 1) + 3 * kx + (lasso ? (size_t)kx * (kx + 1) + 3 * kx : 0);
 }
 
-__device__ __forceinline__ GlmSolveWork glm_solve_carve(double* base, int kx) {
+// gc_elsewhere: the lasso refit's copy of the Gram matrix lives outside `base` (the persistent IRLS kernel
+// keeps it in an L2-resident global scratch so that two CTAs fit on an SM); `base` then holds
+// glm_solve_work_doubles(kx, true) - kx (kx + 1) doubles.
+__device__ __forceinline__ GlmSolveWork glm_solve_carve(double* base, int kx, double* gc_elsewhere = nullptr) {
   const int ld = kx + 1;
   GlmSolveWork w;
   w.L = base;
   w.sc = w.L + kx * ld;
   w.b = w.sc + kx;
   w.invd = w.b + kx;   // reciprocals of the Cholesky diagonal
-  w.Gc = w.invd + kx;  // lasso refit: copy of the scaled Gram matrix (the factorisation is in place)
-  w.b0 = w.Gc + kx * ld;
+  w.Gc = gc_elsewhere ? gc_elsewhere : w.invd + kx;  // lasso refit: copy of the scaled Gram matrix (the factorisation is in place)
+  w.b0 = gc_elsewhere ? w.invd + kx : w.Gc + kx * ld;
   w.t2 = w.b0 + kx;
   w.zf = w.t2 + kx;    // 1.0 where the coefficient is held at zero
   return w;
