@@ -47,6 +47,31 @@ def test_glm_fit_vs_oracle(fam):
     np.testing.assert_allclose(dm, dm_ref, rtol=1e-9)
 
 
+@pytest.mark.parametrize("kind", ["fractional", "large"])
+def test_glm_log_y_table_fallback(kind):
+    """The IRLS kernel reads log y of small integer counts from a table; responses that are not small
+    non-negative integers (normalised / fractional values, counts of 256 and more) take the computed
+    path -- both against the oracle."""
+    from causarray_b200.device import GlmDevice
+    Y, X, off, disp = _glm_problem("nb", 5)
+    Y = np.asarray(Y, dtype=np.float64).copy()
+    if kind == "fractional":
+        Y[::3] += 0.5
+    else:
+        Y[:, ::4] *= 300.0      # every fourth gene far above the table's range
+        assert Y.max() >= 256
+    n, p = Y.shape
+    B_ref, _, _, _, _, status_ref, it_ref = og.fit_glm_original(Y, X, None, family="nb", disp_glm=disp, offset=off,
+                                                             maxiter=100)
+    dev = GlmDevice(n, p)
+    dev.load_counts(Y)
+    B, dv, n_iter, status = dev.fit("nb", X, off, disp, maxiter=100, tol=1e-8, d_guard=2)
+    ok = (status == 0) & (status_ref == 0)
+    assert ok.sum() >= p - 4
+    np.testing.assert_allclose(B[ok], B_ref[ok], rtol=1e-7, atol=1e-8)
+    assert (n_iter[ok] != it_ref[ok]).sum() <= max(1, p // 50)
+
+
 @pytest.mark.parametrize("fam,d_cov,r", [("nb", 2, 4), ("poisson", 3, 8)])
 def test_glm_orthogonal_block_layout(fam, d_cov, r):
     """One-hot treatment block: the tile-skipping internal layout (dense part of one / two tiles)
