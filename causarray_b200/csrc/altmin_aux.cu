@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include "kernels.h"
+#include "devbuf.h"
 
 namespace ca {
 
@@ -48,10 +49,29 @@ int launch_transpose(const double* src, int rows, int cols, long ld_in, double* 
 }
 
 // ---- row sums of the constant term Tys -------------------------------------
+// Tys_ij = -lgamma(y + 1) [+ lgamma(nu + y) - lgamma(nu) for NB entries].  Counts are small integers, so
+// the libm values are looked up instead of recomputed per entry (two lgamma calls per entry made these two
+// launches 1.7 ms of a benchmark batch): lgamma(k + 1), k < TYS_K1, from a table every CTA fills with the
+// same libm calls, and lgamma(nu + k) - lgamma(nu), k < TYS_K2, per gene -- from shared memory when the row
+// is a gene, from a p x TYS_K2 table built by k_tys_nb_table when the columns are genes.  Entries outside
+// the tables (or not integers) take the libm path, so every term is bit-identical to the direct evaluation.
+constexpr int TYS_K1 = 256;
+constexpr int TYS_K2 = 32;
+
+__global__ void k_tys_nb_table(const double* __restrict__ nu, int p, double thres, double* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p * TYS_K2) return;
+  const int c = i / TYS_K2, k = i - c * TYS_K2;
+  const double nc = nu[c];
+  tab[i] = !(nc > thres) ? lgamma(nc + (double)k) - lgamma(nc) : 0.0;
+}
+
 __global__ void k_tys_rowsum(const double* __restrict__ Yr, long ldY, int nrows, int ncols,
                              const double* __restrict__ nu, int nu_per_row, int family, double thres,
-                             double* __restrict__ out) {
+                             const double* __restrict__ nbtab, double* __restrict__ out) {
   __shared__ double scratch[32];
+  __shared__ double s_lg1[TYS_K1];
+  __shared__ double s_nb[TYS_K2];
   const int row = blockIdx.x;
   const double* y = Yr + (size_t)row * ldY;
   double nur = 1.0, lgr = 0.0;
@@ -61,16 +81,22 @@ __global__ void k_tys_rowsum(const double* __restrict__ Yr, long ldY, int nrows,
     nb_row = !(nur > thres);
     lgr = lgamma(nur);
   }
+  for (int k = threadIdx.x; k < TYS_K1; k += blockDim.x) s_lg1[k] = lgamma((double)k + 1.0);
+  if (nb_row)
+    for (int k = threadIdx.x; k < TYS_K2; k += blockDim.x) s_nb[k] = lgamma(nur + (double)k) - lgr;
+  __syncthreads();
   double s = 0.0;
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
     const double v = y[c];
-    double t = -lgamma(v + 1.0);
+    const int vi = (v >= 0.0 && v < (double)TYS_K1) ? (int)v : -1;
+    const bool integral = vi >= 0 && (double)vi == v;
+    double t = integral ? -s_lg1[vi] : -lgamma(v + 1.0);
     if (family == CA_FAMILY_NB) {
       if (nu_per_row) {
-        if (nb_row) t += lgamma(nur + v) - lgr;
+        if (nb_row) t += (integral && vi < TYS_K2) ? s_nb[vi] : lgamma(nur + v) - lgr;
       } else {
         const double nc = nu[c];
-        if (!(nc > thres)) t += lgamma(nc + v) - lgamma(nc);
+        if (!(nc > thres)) t += (integral && vi < TYS_K2) ? nbtab[(size_t)c * TYS_K2 + vi] : lgamma(nc + v) - lgamma(nc);
       }
     }
     s += t;
@@ -82,8 +108,15 @@ __global__ void k_tys_rowsum(const double* __restrict__ Yr, long ldY, int nrows,
 int launch_tys_rowsum(const double* Yr, long ldY, int nrows, int ncols, const double* nu, int nu_per_row,
                       int family, double thres, double* out, cudaStream_t st) {
   if (nrows <= 0) return 0;
-  k_tys_rowsum<<<nrows, 256, 0, st>>>(Yr, ldY, nrows, ncols, nu, nu_per_row, family, thres, out);
+  DevBuf<double> tab;
+  if (family == CA_FAMILY_NB && !nu_per_row) {
+    if (tab.alloc((size_t)ncols * TYS_K2)) return -1;
+    k_tys_nb_table<<<(ncols * TYS_K2 + 255) / 256, 256, 0, st>>>(nu, ncols, thres, tab.ptr);
+    CA_LAUNCH_CHECK();
+  }
+  k_tys_rowsum<<<nrows, 256, 0, st>>>(Yr, ldY, nrows, ncols, nu, nu_per_row, family, thres, tab.ptr, out);
   CA_LAUNCH_CHECK();
+  if (tab.ptr) CA_CUDA(cudaStreamSynchronize(st));   // the table returns to the caching allocator with this scope
   return 0;
 }
 
