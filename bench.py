@@ -259,7 +259,8 @@ def gene_shard_record(rank, world, barrier):
             "allreduce_doubles_per_iteration": {"cell_gradient_and_loglik": int(n * (ldg + 1)),
                                                 "line_search_objectives_per_round": int(n), "scalars": 2},
             "transport": ("single GPU" if world == 1 else
-                          "k_peer_allreduce over NVLink peer memory (2 ranks) / NCCL (CA_PEER_REDUCE unset, > 2 ranks)")}
+                          "k_peer_allreduce over NVLink peer memory (2 and 4 ranks; 8 with CA_PEER_REDUCE=1), "
+                          "NCCL otherwise")}
 
 
 def cpu_step(batch, n_jobs):

@@ -224,6 +224,33 @@ def test_lean_logistic_is_sklearn():
                                   LogisticRegression(**kw).fit(X, y).predict_proba(Xte)[:, 1])
 
 
+def test_direct_lbfgsb_driver_is_scipy_minimize():
+    """The propensity fits drive scipy's compiled L-BFGS-B routine directly (the loop of
+    ``_minimize_lbfgsb`` without ScalarFunction / OptimizeResult): same iterates, bit for bit, as
+    ``scipy.optimize.minimize(method='L-BFGS-B', jac=True)`` -- also when the iteration cap stops it."""
+    import scipy.optimize
+    from causarray_b200 import dr
+    rng = np.random.default_rng(5)
+    for n, d, maxiter in ((400, 6, 100), (1500, 12, 100), (800, 9, 3)):
+        X = rng.standard_normal((n, d))
+        y = (rng.random(n) < 1.0 / (1.0 + np.exp(-X[:, 0]))).astype(float)
+
+        def func(w):
+            z = X @ w
+            pr = 1.0 / (1.0 + np.exp(-z))
+            return float(np.sum(np.logaddexp(0.0, z) - y * z) / n + 0.5e-3 * (w @ w)), X.T @ (pr - y) / n + 1e-3 * w
+
+        ftol = 64 * np.finfo(float).eps
+        ref = scipy.optimize.minimize(func, np.zeros(d), method='L-BFGS-B', jac=True,
+                                      options={'maxiter': maxiter, 'maxls': 50, 'gtol': 1e-4, 'ftol': ftol}).x
+        assert np.array_equal(dr._lbfgsb_direct(func, np.zeros(d), maxiter, 50, 1e-4, ftol), ref)
+    # the gate: the first fit of a process is run both ways and the direct driver is only used when they agree
+    dr._LBFGSB_DIRECT = None
+    out = dr._lbfgsb_minimize(func, np.zeros(d), 100, 50, 1e-4, ftol)
+    assert dr._LBFGSB_DIRECT is True
+    assert np.array_equal(out, dr._lbfgsb_minimize(func, np.zeros(d), 100, 50, 1e-4, ftol))
+
+
 def test_fdx_control_matches_reference_golden():
     """FDX control (multiplier bootstrap as one GEMM, step-down thresholds from a reversed running
     maximum, augmentation) against the REAL reference's loop implementation
