@@ -18,6 +18,8 @@ lbfgs, as in the reference -- SURVEY.md section 2, row 7).
 import contextlib
 import gc
 import os
+import sys
+import time
 import warnings
 from typing import Literal
 
@@ -743,6 +745,7 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
     The counts of each batch are uploaded once and stay on the device through the GCATE fit,
     the outcome GLM and the AIPW reduction.
     """
+    _t_call = time.perf_counter()
     from .estimators import _dense_counts
     import scipy.sparse as _sp
     gcate_kwargs = {} if gcate_kwargs is None else gcate_kwargs
@@ -785,6 +788,8 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
                                      "cache_path to start over.")
     col_of = {name: i for i, name in enumerate(names)}
     new = {}
+    if os.environ.get('CA_TIMING'):
+        print('[gcate_lfc_batch] set-up %.3f s' % (time.perf_counter() - _t_call), file=sys.stderr)
     # multi-GPU: every rank takes the batches i with i % world == rank (no data-path collective);
     # the frames are gathered on rank 0 at the end (causarray_b200/parallel.py)
     from . import parallel as _par
@@ -842,8 +847,12 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
     finally:
         if _gc_was_on:
             gc.enable()
+    _t_loop = time.perf_counter()
     if _world > 1:
         new = _par.gather_frames(new)
+        if os.environ.get('CA_TIMING'):
+            print('[gcate_lfc_batch] rank %d: batches %.3f s, gather %.3f s' % (_rank, _t_loop - _t_call,
+                                                                                  time.perf_counter() - _t_loop), file=sys.stderr)
         if new is None:
             return None   # only rank 0 returns the table
         if cache_path is not None:   # HDF5 is not concurrent-safe: rank 0 writes everything
@@ -856,7 +865,11 @@ def gcate_lfc_batch(Y, X, A, r, W_A=None, batch_size=10, n_batches=None, max_cel
             result = pd.concat(frames, axis=0).reset_index(drop=True)
     else:
         result = pd.concat([new[i] for i in idx_all], axis=0).reset_index(drop=True)
-    return _add_log2fc_columns(result)
+    result = _add_log2fc_columns(result)
+    if os.environ.get('CA_TIMING'):
+        print('[gcate_lfc_batch] rank %d: batches done at %.3f s, table at %.3f s' % (_rank, _t_loop - _t_call,
+                                                                                      time.perf_counter() - _t_call), file=sys.stderr)
+    return result
 
 
 def LFC_batch(*args, **kwargs):

@@ -33,18 +33,39 @@ def foreign_batches(n_batches, rank, world_size):
 
 def gather_frames(frames_by_batch, dst=0):
     """Gather ``{batch_i: DataFrame}`` dicts from all ranks on ``dst``; returns the merged
-    dict there and ``None`` elsewhere.  Single-process: returns the input."""
+    dict there and ``None`` elsewhere.  Single-process: returns the input.
+
+    The pickled frames travel as one byte tensor per rank through ``all_gather`` (the ring the job's
+    all-reduces already use).  ``dist.gather_object`` took 0.94 s for the 14 frames of a 200-perturbation run
+    on two GPUs -- as long as six batches: NCCL sets up its point-to-point channels on the first ``gather``,
+    and the object API copies the 100 MB payload several times."""
     rank, world = dist_info()
     if world == 1:
         return frames_by_batch
+    import pickle
+    import numpy as np
+    import torch
     import torch.distributed as dist
-    out = [None] * world if rank == dst else None
-    dist.gather_object(frames_by_batch, out, dst=dst)
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    payload = pickle.dumps(frames_by_batch, protocol=5)
+    mine = torch.from_numpy(np.frombuffer(payload, dtype=np.uint8).copy())
+    n_mine = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n_mine) for _ in range(world)]
+    dist.all_gather(sizes, n_mine)
+    sizes = [int(t.item()) for t in sizes]
+    width = max(sizes)
+    send = torch.zeros(width, dtype=torch.uint8, device=dev)
+    send[:mine.numel()] = mine.to(dev)
+    recv = [torch.empty(width, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(recv, send)
     if rank != dst:
         return None
     merged = {}
-    for part in out:
-        merged.update(part)
+    for r in range(world):
+        if r == rank:
+            merged.update(frames_by_batch)       # (this rank's own frames need no round trip)
+        else:
+            merged.update(pickle.loads(memoryview(recv[r][:sizes[r]].cpu().numpy())))
     return merged
 
 
