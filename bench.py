@@ -258,9 +258,9 @@ def gene_shard_record(rank, world, barrier):
             "objective_after_23_iterations": float(f),
             "allreduce_doubles_per_iteration": {"cell_gradient_and_loglik": int(n * (ldg + 1)),
                                                 "line_search_objectives_per_round": int(n), "scalars": 2},
-            "transport": ("single GPU" if world == 1 else
-                          "k_peer_allreduce over NVLink peer memory (2 and 4 ranks; 8 with CA_PEER_REDUCE=1), "
-                          "NCCL otherwise")}
+            "transport": {0: "single GPU", 1: "NCCL all-reduce",
+                          2: "k_peer_allreduce over NVLink peer memory"}[int(dev.lib.ca_gcate_transport(dev.h))],
+            "transport_rule": "peer memory on 2 and 4 ranks (8 with CA_PEER_REDUCE=1), NCCL otherwise"}
 
 
 def cpu_step(batch, n_jobs):

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ca_gcate_destroy": [_P],
     "ca_comm_unique_id": [_U8],
     "ca_gcate_set_shard": [_P, _c_int, _c_int, ctypes.c_int64, _U8],
+    "ca_gcate_transport": [_P],
     "ca_gcate_load_counts": [_P, _D, _D, _D],
     "ca_gcate_upload_counts": [_P, _D] + [ctypes.POINTER(ctypes.c_int64)] * 3,
     "ca_gcate_upload_counts_typed": [_P, ctypes.c_void_p, _c_int] + [ctypes.POINTER(ctypes.c_int64)] * 3,

@@ -179,6 +179,12 @@ extern "C" int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_t
   return 0;
 }
 
+// 0: one rank (no exchange), 1: NCCL all-reduce, 2: one-shot all-reduce over NVLink peer memory (comm.cu)
+extern "C" int ca_gcate_transport(ca_gcate_t h) {
+  if (!h || h->world <= 1) return 0;
+  return h->peer ? 2 : 1;
+}
+
 static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_or_null) {
   const int n = h->n, p = h->p;
   std::vector<double> ones;

@@ -78,6 +78,10 @@ class GcateDevice:
         assert uid.size == 128
         L.check(self.lib.ca_gcate_set_shard(self.h, int(rank), int(world), int(p_total), L.u8ptr(uid)))
 
+    def transport(self):
+        """How the cell-step reductions of a sharded handle travel: 'none', 'nccl' or 'nvlink-peer'."""
+        return ('none', 'nccl', 'nvlink-peer')[int(self.lib.ca_gcate_transport(self.h))]
+
     def load_counts(self, Y, size_factor=None, nu=None):
         Y = L.f64(Y)
         assert Y.shape == (self.n, self.p)

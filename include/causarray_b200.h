@@ -58,6 +58,8 @@ int ca_gcate_load_counts(ca_gcate_t h, const double* Y, const double* size_facto
  * ca_gcate_set_shard: collective over the ranks, before the counts are loaded. */
 int ca_comm_unique_id(uint8_t* out128);
 int ca_gcate_set_shard(ca_gcate_t h, int rank, int world, int64_t p_total, const uint8_t* id128);
+/* transport of the cell-step reductions of a sharded handle: 0 none (one rank), 1 NCCL, 2 NVLink peer memory */
+int ca_gcate_transport(ca_gcate_t h);
 /* The same in three steps, so that the input checks of fit_gcate
  * (causarray/gcate.py:12-17: integer-valued, no all-zero gene) and the
  * median-of-ratios size factors (causarray/utils.py:179-219) run on the device

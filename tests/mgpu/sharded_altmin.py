@@ -44,6 +44,8 @@ def main():
     res, hist = dev.alter_min(ls, es, 0.0, d)
     A, B = dev.get_factors()
     ok = True
+    if rank == 0:
+        print("world %d, cell-step reductions over: %s" % (world, dev.transport()), flush=True)
 
     def check(name, got, want, tol):
         nonlocal ok
