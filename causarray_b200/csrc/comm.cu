@@ -191,37 +191,49 @@ int peer_setup(void* comm, int rank, int world, cudaStream_t st, PeerArena** out
   if (!comm || world < 2 || world > PEER_MAX_WORLD || (world & (world - 1)) != 0 || !g_api.all_gather) return 0;
   const char* env = getenv("CA_PEER_REDUCE");
   if (env && env[0] == '0') return 0;
-  // validated on two and on four GPUs (tests/mgpu/sharded_altmin.py and sharded_fit_gcate.py under
-  // torchrun, round 2: identical iteration counts and factors on 4 ranks with CA_PEER_REDUCE=1 and =0);
-  // the 8-rank instantiation stays opt-in (CA_PEER_REDUCE=1) until it has run on hardware
+  // run on two, four and eight GPUs (tests/mgpu/sharded_altmin.py and sharded_fit_gcate.py under torchrun,
+  // round 2: identical iteration counts and factors with CA_PEER_REDUCE=1 and =0); on by default up to four
+  // ranks, the 8-rank instantiation stays opt-in (CA_PEER_REDUCE=1): bench.py's 8-GPU gene_shard record was
+  // measured over NCCL only
   if (world > 4 && !(env && env[0] == '1')) return 0;
+  // The function is COLLECTIVE (one all-gather, one all-reduce): a local failure must not make this rank leave
+  // before the peers' collectives have been matched -- it is recorded in `ok` and agreed on at the end.  Only a
+  // failure of the exchange itself (its few hundred bytes of device scratch, or NCCL) returns early.
+  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+  unsigned char* dscratch = nullptr;   // [rec] send | [rec * world] receive | [8] agreement flag
+  const size_t off_recv = (rec + 15) / 16 * 16, off_flag = off_recv + (rec * world + 15) / 16 * 16;
+  CA_CUDA(cudaMalloc((void**)&dscratch, off_flag + sizeof(double)));
   PeerArena* a = new PeerArena();
   a->rank = rank;
   a->world = world;
   int ok = 1;
+  auto give_up = [&](int rc) {   // every exit that does not hand the arena to the caller
+    for (int q = 0; q < world; ++q)
+      if (q != rank && a->peer[q]) cudaIpcCloseMemHandle(a->peer[q]);
+    if (a->base) cudaFree(a->base);
+    cudaFree(dscratch);
+    cudaGetLastError();
+    delete a;
+    return rc;
+  };
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
-  if (cudaMalloc(&a->base, PEER_ARENA_BYTES) != cudaSuccess || cudaMemset(a->base, 0, PEER_ARENA_BYTES) != cudaSuccess ||
+  if (cudaMalloc(&a->base, PEER_ARENA_BYTES) != cudaSuccess) a->base = nullptr;
+  if (!a->base || cudaMemset(a->base, 0, PEER_ARENA_BYTES) != cudaSuccess ||
       cudaIpcGetMemHandle(&mine, a->base) != cudaSuccess)
     ok = 0;
   cudaGetLastError();
   // exchange the handles (and whether each rank got this far) through the communicator
-  const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
   unsigned char hrec[sizeof(cudaIpcMemHandle_t) + 8] = {0};
   memcpy(hrec, &mine, sizeof(mine));
   hrec[sizeof(mine)] = (unsigned char)ok;
-  unsigned char* dsend = nullptr;
-  unsigned char* drecv = nullptr;
-  std::vector<unsigned char> all(rec * world);
-  CA_CUDA(cudaMalloc((void**)&dsend, rec));
-  CA_CUDA(cudaMalloc((void**)&drecv, rec * world));
-  CA_CUDA(cudaMemcpyAsync(dsend, hrec, rec, cudaMemcpyHostToDevice, st));
-  ncclResult_t r = g_api.all_gather(dsend, drecv, rec, ncclChar, (ncclComm_t)comm, st);
-  if (r != ncclSuccess) return nccl_fail(r, "ncclAllGather");
-  CA_CUDA(cudaMemcpyAsync(all.data(), drecv, rec * world, cudaMemcpyDeviceToHost, st));
-  CA_CUDA(cudaStreamSynchronize(st));
-  cudaFree(dsend);
-  cudaFree(drecv);
+  std::vector<unsigned char> all(rec * world, 0);
+  if (cudaMemcpyAsync(dscratch, hrec, rec, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = 0;
+  ncclResult_t r = g_api.all_gather(dscratch, dscratch + off_recv, rec, ncclChar, (ncclComm_t)comm, st);
+  if (r != ncclSuccess) return give_up(nccl_fail(r, "ncclAllGather"));
+  if (cudaMemcpyAsync(all.data(), dscratch + off_recv, rec * world, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    ok = 0;
   for (int q = 0; q < world; ++q) ok &= (int)all[q * rec + sizeof(mine)];
   if (ok) {
     for (int q = 0; q < world && ok; ++q) {
@@ -236,25 +248,19 @@ int peer_setup(void* comm, int rank, int world, cudaStream_t st, PeerArena** out
         ok = 0;
       }
     }
-    cudaGetLastError();
   }
+  cudaGetLastError();
   // every rank must take the same path: agree through one more reduction
-  double* dflag = nullptr;
+  double* dflag = reinterpret_cast<double*>(dscratch + off_flag);
   double hflag = ok ? 0.0 : 1.0;
-  CA_CUDA(cudaMalloc((void**)&dflag, sizeof(double)));
-  CA_CUDA(cudaMemcpyAsync(dflag, &hflag, sizeof(double), cudaMemcpyHostToDevice, st));
-  if (comm_allreduce_sum(comm, dflag, 1, st)) return -1;
-  CA_CUDA(cudaMemcpyAsync(&hflag, dflag, sizeof(double), cudaMemcpyDeviceToHost, st));
-  CA_CUDA(cudaStreamSynchronize(st));
-  cudaFree(dflag);
-  if (hflag != 0.0) {
-    for (int q = 0; q < world; ++q)
-      if (q != rank && a->peer[q]) cudaIpcCloseMemHandle(a->peer[q]);
-    if (a->base) cudaFree(a->base);
-    cudaGetLastError();
-    delete a;
-    return 0;
-  }
+  const bool sent = cudaMemcpyAsync(dflag, &hflag, sizeof(double), cudaMemcpyHostToDevice, st) == cudaSuccess;
+  if (comm_allreduce_sum(comm, dflag, 1, st)) return give_up(-1);
+  if (!sent || cudaMemcpyAsync(&hflag, dflag, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    hflag = 1.0;   // (this rank cannot know the verdict: it falls back alone -- and reports it below)
+  cudaGetLastError();
+  if (hflag != 0.0) return give_up(0);   // some rank could not map the arenas: all of them use NCCL
+  cudaFree(dscratch);
   *out = a;
   return 0;
 }
