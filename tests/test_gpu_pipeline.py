@@ -85,6 +85,26 @@ def test_gcate_lfc_batch_smoke():
     np.testing.assert_array_equal(df["tau"].to_numpy(), df2["tau"].to_numpy())
 
 
+def test_gcate_lfc_batch_cache_round_trip(tmp_path):
+    """Resumable HDF5 cache of the batch driver (reference DR_learner.py:705-760): a second call with the
+    same cache_path reads every batch back and returns the same table.  Needs pytables (not in every image)."""
+    pytest.importorskip("tables")
+    import causarray_b200 as cb
+    from causarray_b200.synth import simulate_screen
+    sim = simulate_screen(n_ctrl=120, n_perts=4, cells_per_pert=40, p=120, r=2, seed=5, base_lo=0.0, base_hi=2.0)
+    kw = dict(batch_size=2, max_cells=2000, n_ctrl=100, family="nb",
+              gcate_kwargs=dict(disp_glm=sim["disp"], kwargs_es_1=dict(max_iters=6), kwargs_es_2=dict(max_iters=6)),
+              lfc_kwargs=dict(usevar="unequal", disp_glm=sim["disp"]), random_state=0)
+    path = str(tmp_path / "lfc_cache.h5")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df = cb.gcate_lfc_batch(sim["Y"], sim["X"], sim["A"], 2, cache_path=path, **kw)
+        df2 = cb.gcate_lfc_batch(sim["Y"], sim["X"], sim["A"], 2, cache_path=path, **kw)
+    assert os.path.exists(path)
+    np.testing.assert_array_equal(df["tau"].to_numpy(), df2["tau"].to_numpy())
+    np.testing.assert_array_equal(df["batch"].to_numpy(), df2["batch"].to_numpy())
+
+
 def test_estimate_r_golden(golden_dir):
     """JIC sweep over the number of latent factors against the REAL reference's estimate_r
     (causarray/gcate.py:196-325; golden generated by tests/golden/make_golden.py)."""
