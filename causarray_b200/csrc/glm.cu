@@ -481,6 +481,8 @@ extern "C" int ca_glm_load_counts(ca_glm_t h, const double* Y) {
   CA_CUDA(cudaStreamSynchronize(h->st));
   h->Yraw = h->Yraw_own.ptr;
   h->Yt = h->Yt_own.ptr;
+  h->Yp_src = nullptr;   // the group-sorted copy of the IRLS kernel belongs to the previous counts (same buffer!)
+  h->mu_valid = false;
   return 0;
 }
 
@@ -490,6 +492,8 @@ extern "C" int ca_glm_share_counts(ca_glm_t h, ca_gcate_t g) {
   h->Yraw = g->Yraw.ptr;
   h->Yt = g->Yraw_t.ptr;
   h->ldn = g->ldn;
+  h->Yp_src = nullptr;
+  h->mu_valid = false;
   return 0;
 }
 

@@ -47,6 +47,26 @@ def test_glm_fit_vs_oracle(fam):
     np.testing.assert_allclose(dm, dm_ref, rtol=1e-9)
 
 
+def test_glm_reload_counts_same_handle():
+    """Replacing the counts of a handle (same shape, same design) must not reuse the group-sorted copy the IRLS
+    kernel made of the PREVIOUS counts (the device buffer, hence its address, is the same)."""
+    from causarray_b200.device import GlmDevice
+    Y, X, off, disp = _glm_problem("nb", 3)
+    n, p = Y.shape
+    h = p // 2
+    Y1, Y2 = np.ascontiguousarray(Y[:, :h]), np.ascontiguousarray(Y[:, h:2 * h])
+    dev = GlmDevice(n, h)
+    dev.load_counts(Y1)
+    B1 = dev.fit("nb", X, off, disp[:h], maxiter=100, tol=1e-8, d_guard=-1)[0]
+    dev.load_counts(Y2)
+    B2 = dev.fit("nb", X, off, disp[h:2 * h], maxiter=100, tol=1e-8, d_guard=-1)[0]
+    fresh = GlmDevice(n, h)
+    fresh.load_counts(Y2)
+    B2f = fresh.fit("nb", X, off, disp[h:2 * h], maxiter=100, tol=1e-8, d_guard=-1)[0]
+    assert not np.array_equal(B1, B2)
+    np.testing.assert_array_equal(B2, B2f)
+
+
 @pytest.mark.parametrize("kind", ["fractional", "large"])
 def test_glm_log_y_table_fallback(kind):
     """The IRLS kernel reads log y of small integer counts from a table; responses that are not small
