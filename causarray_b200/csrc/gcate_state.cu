@@ -187,6 +187,10 @@ extern "C" int ca_gcate_transport(ca_gcate_t h) {
 
 static int finish_load(ca_gcate* h, const double* nu_host, const double* Ys_dev_or_null) {
   const int n = h->n, p = h->p;
+  // new counts: the gathered treated-cell counts of the one-hot stage-2 search belong to the previous ones
+  h->s2_cells_host.clear();
+  h->s2_checked = false;
+  h->s2_ok = false;
   std::vector<double> ones;
   if (!nu_host) {
     ones.assign(p, 1.0);
