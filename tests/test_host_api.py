@@ -251,6 +251,36 @@ def test_direct_lbfgsb_driver_is_scipy_minimize():
     assert np.array_equal(out, dr._lbfgsb_minimize(func, np.zeros(d), 100, 50, 1e-4, ftol))
 
 
+def test_direct_lbfgsb_driver_gate_falls_back(monkeypatch):
+    """A direct driver that does not reproduce scipy's iterates (another scipy behind the private interface)
+    is never used: the probe fit returns scipy's answer and later fits go through ``minimize``."""
+    import scipy.optimize
+    from causarray_b200 import dr
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((300, 5))
+    y = (rng.random(300) < 0.4).astype(float)
+
+    def func(w):
+        z = X @ w
+        return float(np.sum(np.logaddexp(0.0, z) - y * z) / 300 + 0.5e-3 * (w @ w)), X.T @ (1 / (1 + np.exp(-z)) - y) / 300 + 1e-3 * w
+
+    ftol = 64 * np.finfo(float).eps
+    ref = scipy.optimize.minimize(func, np.zeros(5), method='L-BFGS-B', jac=True,
+                                  options={'maxiter': 100, 'maxls': 50, 'gtol': 1e-4, 'ftol': ftol}).x
+    monkeypatch.setattr(dr, '_LBFGSB_DIRECT', None)
+    monkeypatch.setattr(dr, '_lbfgsb_direct', lambda *a, **k: ref + 1e-9)        # "works", but differently
+    assert np.array_equal(dr._lbfgsb_minimize(func, np.zeros(5), 100, 50, 1e-4, ftol), ref)
+    assert dr._LBFGSB_DIRECT is False
+    assert np.array_equal(dr._lbfgsb_minimize(func, np.zeros(5), 100, 50, 1e-4, ftol), ref)
+
+    def boom(*a, **k):
+        raise TypeError('setulb() takes 16 positional arguments')
+    monkeypatch.setattr(dr, '_LBFGSB_DIRECT', None)
+    monkeypatch.setattr(dr, '_lbfgsb_direct', boom)
+    assert np.array_equal(dr._lbfgsb_minimize(func, np.zeros(5), 100, 50, 1e-4, ftol), ref)
+    assert dr._LBFGSB_DIRECT is False
+
+
 def test_fdx_control_matches_reference_golden():
     """FDX control (multiplier bootstrap as one GEMM, step-down thresholds from a reversed running
     maximum, augmentation) against the REAL reference's loop implementation
